@@ -1,0 +1,205 @@
+/*
+ * psim_b200.h — C ABI of libpsim_b200.so, the B200 (sm_100a) implementation of ParticleSim's
+ * force hot path.  Plain pointers and sizes only; no torch, no C++ types.
+ *
+ * The reference (PMantix/ParticleSim, Rust) has no FFI layer for this path: the boundary is the
+ * method surface of `Quadtree` and `CellList` that `src/simulation` calls.  Each entry point below
+ * names the reference interface it replaces (file:line relative to the reference root).  The Rust
+ * binding a maintainer would add is shown in INTEGRATION.md and checked in under rust/.
+ *
+ * Threading: one host thread per context; contexts are independent (one per GPU).
+ * Ownership: the caller owns every host buffer it passes; the library owns all device memory.
+ * Errors: every function returns 0 (PSIM_OK) or a negative PSIM_E_* code and never aborts or
+ * throws across the ABI; psim_last_error() gives the message of the last failure on a context.
+ * There is no CPU fallback: without a CUDA device psim_create fails with PSIM_E_CUDA.
+ *
+ * Body order: like the reference's in-place partition (quadtree.rs:56-63), psim_build PERMUTES
+ * the bodies held by the context into tree order.  Every index-based call afterwards refers to the
+ * post-build order; psim_get_permutation tells the host how to reorder its own Vec<Body>.
+ */
+#ifndef PSIM_B200_H
+#define PSIM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSIM_OK 0
+#define PSIM_E_CUDA (-1)
+#define PSIM_E_ARG (-2)
+#define PSIM_E_OOM (-3)
+#define PSIM_E_NODE_OVERFLOW (-4) /* more tree nodes than the arena holds (raise node_factor) */
+#define PSIM_E_STATE (-5)         /* call order: e.g. field before build */
+#define PSIM_E_NCCL (-6)
+
+#define PSIM_BUILD_CONTAINING 0 /* Quadtree::build, quadtree.rs:153-170 (root = tight AABB square) */
+#define PSIM_BUILD_DOMAIN 1     /* Quadtree::build_with_domain, quadtree.rs:173-195 */
+
+#define PSIM_SR_LJ 1u             /* forces.rs:182-231 */
+#define PSIM_SR_REPULSION 2u      /* forces.rs:250-289 */
+#define PSIM_SR_STACK_PRESSURE 4u /* forces.rs:294-321 */
+
+typedef struct psim_ctx psim_ctx;
+
+/* Quadtree::new(theta, epsilon, leaf_capacity, thread_capacity) (quadtree.rs:24-34) plus the
+ * SimConfig fields the path reads (config.rs:126,204,213-216; units.rs:32-34). */
+typedef struct {
+  float theta;
+  float epsilon;
+  uint32_t leaf_capacity;
+  uint32_t thread_capacity; /* only its effect on the tree shape is kept */
+  float lj_force_max;       /* LJ_FORCE_MAX = 200 */
+  uint32_t collision_passes;/* COLLISION_PASSES = 7 (LJ clamp = passes * lj_force_max) */
+  uint32_t stack_pressure_enabled;
+  float stack_pressure;
+  float stack_pressure_decay;
+  uint32_t parity_mode;     /* 1: IEEE sqrt/div, reference operation order (default); 0: fast math */
+  float node_factor;        /* node arena = node_factor * max_bodies + 1024 compact nodes (default 4) */
+  uint32_t reserved[5];
+} psim_config;
+
+/* one row per Species (body/types.rs:12-36), the SpeciesProps columns the path reads (species.rs:7-24) */
+typedef struct {
+  float mass, radius, damping;
+  float lj_epsilon, lj_sigma, lj_cutoff;
+  float polar_offset, polar_charge;
+  float repulsion_strength, repulsion_cutoff;
+  uint32_t lj_enabled, repulsion_enabled;
+} psim_species;
+
+/* Node in the reference's field order (quadtree/node.rs:6-14), fixed C layout, 64 bytes. */
+typedef struct {
+  uint64_t children; /* first of 4 contiguous children, 0 = leaf */
+  uint64_t next;     /* skip pointer, 0 = end */
+  float pos[2];
+  float mass;
+  float quad_center[2];
+  float quad_size;
+  uint64_t bodies_start, bodies_end;
+  float charge;
+  uint32_t _pad;
+} psim_node;
+
+typedef struct {
+  uint64_t n_bodies;
+  uint64_t n_electrons;
+  uint64_t compact_nodes;   /* non-empty cells held on the device */
+  uint64_t reference_nodes; /* 4 * internal + 1: what Vec<Node> holds in the reference */
+  uint32_t max_depth;
+  uint32_t depth_cap;       /* first depth refused by the 1e-6 size rule / 32-level key */
+  uint32_t zero_leaves;     /* refused or thread-capacity leaves with zeroed aggregates (Q2) */
+  uint32_t cap_leaves;      /* multi-body leaves that stopped at depth_cap */
+  float root_center[2];
+  float root_size;
+  uint32_t grid_x, grid_y;
+  uint64_t traversal_warp_steps; /* nodes visited by warps since psim_reset_counters */
+  uint64_t kernel_launches;      /* kernels launched by this context since psim_reset_counters */
+} psim_stats;
+
+/* ---- lifecycle ---- */
+void psim_default_config(psim_config *cfg);
+void psim_default_species_table(psim_species *rows21); /* species.rs:26-408 */
+int32_t psim_create(int32_t device, uint64_t max_bodies, uint64_t max_electrons,
+                    const psim_config *cfg, psim_ctx **out);
+int32_t psim_destroy(psim_ctx *ctx);
+const char *psim_last_error(const psim_ctx *ctx);
+int32_t psim_set_config(psim_ctx *ctx, const psim_config *cfg);
+/* run on this CUDA stream (cudaStream_t as an integer); 0 = the legacy default stream */
+int32_t psim_set_stream(psim_ctx *ctx, uint64_t cuda_stream);
+int32_t psim_sync(psim_ctx *ctx);
+int32_t psim_stats_get(psim_ctx *ctx, psim_stats *out);
+int32_t psim_reset_counters(psim_ctx *ctx);
+
+/* ---- data in / out (host pointers; arrays marked opt may be NULL) ---- */
+/* species.rs get_species_props table; nrows <= 32 */
+int32_t psim_upload_species_table(psim_ctx *ctx, const psim_species *rows, uint32_t nrows);
+/* Vec<Body> hot fields (body/types.rs:38-62).  opt NULL => zeros (mass: 1). */
+int32_t psim_upload_bodies(psim_ctx *ctx, uint64_t n, const float *pos_xy, const float *z_opt,
+                           const float *vel_xy_opt, const float *vz_opt, const float *mass_opt,
+                           const float *radius_opt, const float *charge_opt,
+                           const uint8_t *species_opt);
+/* only positions / charges changed on the host */
+int32_t psim_update_positions(psim_ctx *ctx, uint64_t n, const float *pos_xy);
+int32_t psim_update_charges(psim_ctx *ctx, uint64_t n, const float *charge);
+/* Body::electrons flattened: body index (current order), rel_pos, vel (body/electron.rs:9-13) */
+int32_t psim_upload_electrons(psim_ctx *ctx, uint64_t m, const uint32_t *body, const float *rel_xy,
+                              const float *vel_xy_opt);
+/* every pointer opt; orig_index[i] = index the body had at psim_upload_bodies time */
+int32_t psim_download_bodies(psim_ctx *ctx, float *pos_xy, float *z, float *vel_xy, float *vz,
+                             float *acc_xy, float *az, float *mass, float *radius, float *charge,
+                             uint8_t *species, float *e_field_xy, uint32_t *orig_index);
+int32_t psim_download_electrons(psim_ctx *ctx, uint32_t *body, float *rel_xy, float *vel_xy);
+
+/* ---- src/quadtree ---- */
+/* Quadtree::build (mode 0) / build_with_domain(hw, hh) (mode 1): quadtree.rs:153-195.
+ * Morton keys -> onesweep sort -> tree construction -> bottom-up aggregation.  Permutes bodies. */
+int32_t psim_build(psim_ctx *ctx, int32_t mode, float hw, float hh);
+/* out[i] = position, before the last psim_build, of the body now at i */
+int32_t psim_get_permutation(psim_ctx *ctx, uint32_t *out);
+/* 32-level quadrant keys of the bodies in current (sorted) order */
+int32_t psim_get_keys(psim_ctx *ctx, uint64_t *out);
+/* Vec<Node> for the renderer / diagnostics consumers (renderer/draw/mod.rs:62-63,851-900) */
+int32_t psim_download_nodes(psim_ctx *ctx, psim_node *out, uint64_t cap, uint64_t *count);
+/* Quadtree::field (quadtree.rs:418-427) + the attract epilogue (forces.rs:37-43):
+ * e_field = acc_pos(pos, 1, radius) + bg; if write_acc: acc = charge * e_field / mass.
+ * out pointers opt (host, current order). */
+int32_t psim_field(psim_ctx *ctx, float k_e, float bg_x, float bg_y, int32_t write_acc,
+                   float *out_e_field_xy, float *out_acc_xy);
+/* Quadtree::acc_pos (quadtree.rs:350-407) for m points; q NULL => 1, radius NULL => 0, which is
+ * Quadtree::field_at_point (quadtree.rs:504-507) */
+int32_t psim_acc_points(psim_ctx *ctx, uint64_t m, const float *pts_xy, const float *q_opt,
+                        const float *radius_opt, float k_e, float *out_xy);
+/* the loop at simulation.rs:1186-1196 over Body::update_electrons (body/electron.rs:19-46) */
+int32_t psim_update_electrons(psim_ctx *ctx, float bg_x, float bg_y, float dt, float k_e);
+
+/* ---- src/cell_list.rs ---- */
+/* CellList::update_domain_size + cell_size + rebuild (cell_list.rs:27-45) */
+int32_t psim_cell_build(psim_ctx *ctx, float hw, float hh, float cell_size);
+/* CSR dump: offsets[gx*gy + 1], indices[n] (per-cell body lists in index order) */
+int32_t psim_cell_download(psim_ctx *ctx, uint64_t *gx, uint64_t *gy, uint32_t *offsets_opt,
+                           uint32_t *indices_opt);
+/* CellList::find_neighbors_within (cell_list.rs:57-85) for m bodies, CSR result in the reference's
+ * order; metals_only = metal_neighbor_count's filter (cell_list.rs:92-127).  indices_opt may be
+ * NULL to get offsets (counts) only; *total receives offsets[m]. */
+int32_t psim_neighbors_within(psim_ctx *ctx, uint64_t m, const uint32_t *body_idx, float cutoff,
+                              int32_t metals_only, uint32_t *offsets, uint32_t *indices_opt,
+                              uint64_t indices_cap, uint64_t *total);
+
+/* ---- src/simulation/forces.rs + Simulation::iterate ---- */
+/* simulation.rs:1000-1003 */
+int32_t psim_reset_acc(psim_ctx *ctx);
+/* simulation.rs:1798-1802 */
+int32_t psim_use_cell_list(const psim_ctx *ctx, float hw, float hh, float density_threshold);
+/* forces.rs:14-25: build(CONTAINING) and, when use_cell_list, the grid at
+ * cell_size = max(3 * max_lj_cutoff, max_repulsion_cutoff, max_lj_cutoff) */
+int32_t psim_prepare_spatial_structures(psim_ctx *ctx, float hw, float hh, float density_threshold);
+/* apply_lj_forces / apply_repulsive_forces / apply_stack_pressure accumulated into acc.
+ * Needs a cell grid whose cell_size >= the largest cutoff in use. */
+int32_t psim_short_range(psim_ctx *ctx, uint32_t flags);
+/* Simulation::iterate (simulation.rs:1437-1486); base damping = damping_base ^ (dt / 0.01) */
+int32_t psim_iterate(psim_ctx *ctx, float dt, float damping_base, float hw, float hh, float hd,
+                     int32_t enable_out_of_plane);
+
+/* One pass of the hot path exactly in Simulation::step's order (simulation.rs:1000-1196), with no
+ * host round trip in between: reset acc -> prepare_spatial_structures -> field + attract ->
+ * LJ / repulsion / stack pressure -> iterate -> build_with_domain -> update_electrons. */
+typedef struct {
+  float hw, hh, hd;
+  float dt, damping_base;
+  float k_e;
+  float bg_x, bg_y;
+  float density_threshold;
+  uint32_t enable_out_of_plane;
+  uint32_t do_short_range;  /* 0: Coulomb only (config 2) */
+  uint32_t do_electrons;    /* second build + electron field sampling + drift */
+  uint32_t do_iterate;
+  uint32_t reserved[3];
+} psim_step_params;
+int32_t psim_step(psim_ctx *ctx, const psim_step_params *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,311 @@
+// tree_logic.cuh — per-body / per-node bodies of the tree kernels, written once as host+device
+// functions so that tests/emu can run the very same construction logic serially on the CPU and
+// compare it with the oracle before any GPU time is spent.  The product only ever calls these from
+// the __global__ wrappers in tree.cuh.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <vector_functions.h>
+#include <vector_types.h>
+
+#include "psim_core.cuh"
+
+namespace psim {
+
+constexpr int kLevels = kMaxLevels + 1;  // node depths 0..32
+
+struct TreeMeta {
+  RootQuad root;
+  uint32_t n;
+  uint32_t num_nodes;       // compact nodes
+  uint32_t num_internal;    // internal nodes (== number of 4-child groups in the reference shape)
+  uint32_t max_depth;
+  uint32_t dcap;
+  uint32_t err;             // bit0 node arena overflow
+  uint32_t num_zero_leaves; // refused / thread-capacity leaves
+  uint32_t num_cap_leaves;  // multi-body leaves stopped by the 32-level key or the 1e-6 size rule
+  uint32_t level_count[kLevels];
+  uint32_t level_start[kLevels + 1];
+  uint32_t level_cursor[kLevels];
+};
+
+struct NodeSums {  // per internal node: running sums over its body range
+  double aq, aqx, aqy;  // Σ|q|, Σ|q|x, Σ|q|y
+  double m, mx, my;     // Σm, Σm x, Σm y
+  double x, y;          // Σx, Σy
+};
+
+struct TreeArrays {
+  float4* nodeA;      // {pos.x, pos.y, charge, quad.size}
+  uint4* nodeB;       // {next, body_start, body_count, depth | flags}
+  float* node_mass;
+  uint32_t* parent;   // compact index of the parent (root: 0xffffffff)
+  NodeSums* sums;
+  uint32_t* level_nodes;  // internal nodes bucketed by depth
+  uint32_t node_cap;
+};
+
+// Node in the reference's field order (node.rs:6-14), 64 bytes; == psim_node of the C ABI
+struct PsimNodeOut {
+  uint64_t children, next;
+  float pos[2];
+  float mass;
+  float quad_center[2];
+  float quad_size;
+  uint64_t bodies_start, bodies_end;
+  float charge;
+  uint32_t _pad;
+};
+
+PSIM_HD float f_div(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fdiv_rn(a, b);
+#else
+  return a / b;
+#endif
+}
+PSIM_HD float f_sub(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fsub_rn(a, b);
+#else
+  return a - b;
+#endif
+}
+
+// root square: Quad::new_containing (quad.rs:31-34) from the reduced AABB, or new_for_domain (:38-43)
+PSIM_HD RootQuad root_from_bounds(float mnx, float mny, float mxx, float mxy) {
+  RootQuad r;
+  r.cx = f_mul(f_add(mnx, mxx), 0.5f);
+  r.cy = f_mul(f_add(mny, mxy), 0.5f);
+  r.size = fmaxf(f_sub(mxx, mnx), f_sub(mxy, mny));
+  return r;
+}
+PSIM_HD RootQuad root_for_domain(float hw, float hh) {
+  RootQuad r;
+  r.cx = 0.0f, r.cy = 0.0f;
+  r.size = fmaxf(f_mul(2.0f, hw), f_mul(2.0f, hh));
+  return r;
+}
+
+PSIM_HD void meta_reset(TreeMeta* meta, RootQuad r, uint32_t n) {
+  meta->root = r;
+  meta->n = n;
+  meta->num_nodes = 0;
+  meta->num_internal = 0;
+  meta->max_depth = 0;
+  meta->dcap = (uint32_t)depth_cap(r.size);
+  meta->err = 0;
+  meta->num_zero_leaves = 0;
+  meta->num_cap_leaves = 0;
+  for (int l = 0; l < kLevels; ++l) meta->level_count[l] = 0, meta->level_cursor[l] = 0;
+}
+
+// (λ_i + 1) | ℓ_i << 8
+PSIM_HD uint16_t body_levels(const uint64_t* keys, uint32_t n, uint32_t i, uint32_t c_eff, int dcap) {
+  const int lam = lambda_at(keys, i);
+  int ell = 0;
+  if (lam < kMaxLevels) ell = leaf_depth(keys, n, i, lam, c_eff, dcap);
+  return (uint16_t)((uint32_t)(lam + 1) | ((uint32_t)ell << 8));
+}
+PSIM_HD int le_lambda(uint16_t le) { return (int)(le & 0xff) - 1; }
+PSIM_HD int le_ell(uint16_t le) { return (int)(le >> 8); }
+PSIM_HD uint32_t le_nodes(uint16_t le) {
+  const int lam = le_lambda(le), ell = le_ell(le);
+  return lam < ell ? (uint32_t)(ell - lam) : 0u;
+}
+
+PSIM_HD void level_scan(TreeMeta* meta, uint32_t node_cap) {
+  uint32_t run = 0;
+  for (int l = 0; l < kLevels; ++l) {
+    meta->level_start[l] = run;
+    run += meta->level_count[l];
+    meta->level_cursor[l] = 0;
+  }
+  meta->level_start[kLevels] = run;
+  meta->num_internal = run;
+  if (meta->num_nodes > node_cap) meta->err |= 1u;
+}
+
+// All nodes whose first body is i: the leaf at depth ℓ_i and the internal cells above it down to
+// depth λ_i + 1.  Leaf aggregation follows quadtree.rs:281-306.  `sink` hands out level-bucket
+// slots and counts diagnostics (atomics on the device, plain counters in the emulation).
+template <class Sink>
+PSIM_HD void emit_nodes_for_body(const uint64_t* keys, uint32_t n, uint32_t i, uint16_t lev,
+                                 const uint32_t* nodebase, uint32_t M, const float4* pqr,
+                                 const float4* accm, uint32_t leaf_capacity, uint32_t thread_capacity,
+                                 float root_size, int dcap, const TreeArrays& t, Sink& sink) {
+  const int lam = le_lambda(lev), ell = le_ell(lev);
+  if (!(lam < ell)) return;
+  const uint32_t base = nodebase[i];
+  uint32_t j = i + 1;
+  for (int d = ell; d > lam; --d) {
+    j = run_end(keys, n, i, j, d);
+    const uint32_t node = base + (uint32_t)(d - lam - 1);
+    const uint32_t next = (j < n) ? nodebase[j] : M;
+    const uint32_t count = j - i;
+    const float size = ldexpf(root_size, -d);  // size *= 0.5 per level, exact
+    if (d == ell) {
+      const bool agg = leaf_is_aggregated(count, leaf_capacity, thread_capacity);
+      float tm = 0.0f, tq = 0.0f, wx = 0.0f, wy = 0.0f;
+      if (agg) {
+        for (uint32_t b = i; b < j; ++b) {
+          const float4 p = pqr[b];
+          tm = f_add(tm, accm[b].w);
+          wx = f_add(wx, f_mul(p.x, p.z));
+          wy = f_add(wy, f_mul(p.y, p.z));
+          tq = f_add(tq, p.z);
+        }
+        if (fabsf(tq) > 1e-6f) {
+          wx = f_div(wx, tq);
+          wy = f_div(wy, tq);
+        }
+      } else {
+        sink.zero_leaf();
+      }
+      if (count > 1 && d == dcap) sink.cap_leaf();
+      t.nodeA[node] = make_float4(wx, wy, tq, size);
+      t.node_mass[node] = tm;
+      t.nodeB[node] = make_uint4(next, i, count, (uint32_t)d | kNodeLeaf | (agg ? 0u : kNodeZeroAgg));
+    } else {
+      t.nodeB[node] = make_uint4(next, i, count, (uint32_t)d);
+      t.level_nodes[sink.level_slot(d)] = node;
+    }
+    if (d == 0) t.parent[node] = 0xffffffffu;
+  }
+}
+
+// One internal node of the bottom-up sweep: quadtree.rs:103-151.
+// mass/charge: the reference's ((c0 + c1) + c2) + c3 over the 4 children; absent (empty) children
+// are +0.0 terms.  Centre: |q|-weighted, else mass-weighted, else centroid, from sums
+// carried up in double (the reference runs one f32 running sum over the node's whole range).
+PSIM_HD void aggregate_node(uint32_t node, float root_size, const float4* pqr, const float4* accm,
+                            const TreeArrays& t) {
+  const uint4 nb = t.nodeB[node];
+  NodeSums s = {0, 0, 0, 0, 0, 0, 0, 0};
+  float charge = 0.0f, msum = 0.0f;
+  uint32_t c = node + 1;
+  while (c < nb.x) {
+    const uint4 cb = t.nodeB[c];
+    charge = f_add(charge, t.nodeA[c].z);
+    msum = f_add(msum, t.node_mass[c]);
+    t.parent[c] = node;
+    if (cb.w & kNodeLeaf) {
+      for (uint32_t b = cb.y; b < cb.y + cb.z; ++b) {
+        const float4 p = pqr[b];
+        const double aq = fabs((double)p.z), m = (double)accm[b].w;
+        s.aq += aq, s.aqx += aq * (double)p.x, s.aqy += aq * (double)p.y;
+        s.m += m, s.mx += m * (double)p.x, s.my += m * (double)p.y;
+        s.x += (double)p.x, s.y += (double)p.y;
+      }
+    } else {
+      const NodeSums cs = t.sums[c];
+      s.aq += cs.aq, s.aqx += cs.aqx, s.aqy += cs.aqy;
+      s.m += cs.m, s.mx += cs.mx, s.my += cs.my;
+      s.x += cs.x, s.y += cs.y;
+    }
+    c = cb.x;
+  }
+  t.sums[node] = s;
+  float px, py;
+  if (s.aq > (double)1e-6f) {
+    px = (float)(s.aqx / s.aq), py = (float)(s.aqy / s.aq);
+  } else if (s.m > (double)1e-6f) {
+    px = (float)(s.mx / s.m), py = (float)(s.my / s.m);
+  } else if (nb.z > 0) {
+    px = (float)(s.x / (double)nb.z), py = (float)(s.y / (double)nb.z);
+  } else {
+    px = 0.0f, py = 0.0f;
+  }
+  const float size = ldexpf(root_size, -(int)(nb.w & kNodeDepthMask));
+  t.nodeA[node] = make_float4(px, py, charge, size);
+  t.node_mass[node] = msum;
+}
+
+// ---- export in the reference's shape (node.rs:6-14): ROOT = 0, the 4 children of the r-th
+// internal node (pre-order rank r) at 4r+1 .. 4r+4 (quadtree.rs:65-66 hands out groups the same
+// way; the reference's raw group order is schedule dependent), `next` = sibling or the
+// parent's next, 0 at the end (quadtree.rs:82-87).
+PSIM_HD uint64_t export_index(uint32_t node, const uint32_t* parent, const uint32_t* irank,
+                              const uint4* nodeB, const uint64_t* keys) {
+  if (node == 0) return 0;
+  const uint4 nb = nodeB[node];
+  const unsigned q = digit_at(keys[nb.y], (int)(nb.w & kNodeDepthMask));
+  return 4ull * irank[parent[node]] + 1ull + q;
+}
+
+PSIM_HD void export_node(uint32_t node, const uint64_t* keys, RootQuad root, const TreeArrays& t,
+                         const uint32_t* irank, PsimNodeOut* out, uint64_t out_cap) {
+  const uint4 nb = t.nodeB[node];
+  const int depth = (int)(nb.w & kNodeDepthMask);
+  const uint64_t key = keys[nb.y];
+  const uint64_t me = export_index(node, t.parent, irank, t.nodeB, keys);
+  // reference `next`: next sibling slot, or the first ancestor's; 0 when the walk ends
+  uint64_t next = 0;
+  {
+    uint32_t a = node;
+    while (a != 0) {
+      const uint4 ab = t.nodeB[a];
+      const unsigned q = digit_at(keys[ab.y], (int)(ab.w & kNodeDepthMask));
+      if (q < 3) {
+        next = export_index(a, t.parent, irank, t.nodeB, keys) + 1;
+        break;
+      }
+      a = t.parent[a];
+    }
+  }
+  const RootQuad quad = quad_at(root, key, depth);
+  const bool leaf = (nb.w & kNodeLeaf) != 0;
+  if (me < out_cap) {
+    PsimNodeOut o;
+    o.children = leaf ? 0ull : 4ull * irank[node] + 1ull;
+    o.next = next;
+    const float4 a = t.nodeA[node];
+    o.pos[0] = a.x, o.pos[1] = a.y;
+    o.mass = t.node_mass[node];
+    o.quad_center[0] = quad.cx, o.quad_center[1] = quad.cy;
+    o.quad_size = quad.size;
+    o.bodies_start = nb.y, o.bodies_end = (uint64_t)nb.y + nb.z;
+    o.charge = a.z;
+    o._pad = 0;
+    out[me] = o;
+  }
+  if (!leaf) {
+    // materialise the empty children: Node::new(next, quad, s..s) with s = the split point
+    const uint64_t group = 4ull * irank[node] + 1ull;
+    uint32_t c = node + 1;
+    unsigned q = 0;
+    while (q < 4) {
+      unsigned cq = 4;
+      uint32_t cstart = nb.y + nb.z;
+      uint32_t cnext = 0;
+      if (c < nb.x) {
+        const uint4 cb = t.nodeB[c];
+        cq = digit_at(keys[cb.y], depth + 1);
+        cstart = cb.y;
+        cnext = cb.x;
+      }
+      for (; q < cq && q < 4; ++q) {
+        if (group + q < out_cap) {
+          const RootQuad cqd = quad_child(quad, q);
+          PsimNodeOut o;
+          o.children = 0;
+          o.next = (q < 3) ? group + q + 1 : next;
+          o.pos[0] = 0.0f, o.pos[1] = 0.0f;
+          o.mass = 0.0f;
+          o.quad_center[0] = cqd.cx, o.quad_center[1] = cqd.cy;
+          o.quad_size = cqd.size;
+          o.bodies_start = cstart, o.bodies_end = cstart;
+          o.charge = 0.0f;
+          o._pad = 0;
+          out[group + q] = o;
+        }
+      }
+      if (cq < 4) {
+        q = cq + 1;
+        c = cnext;
+      }
+    }
+  }
+}
+
+}  // namespace psim
