@@ -234,6 +234,28 @@ struct Quadtree {
       size_t i = nodes[node].children;
       size_t s = nodes[node].b_start, e = nodes[node].b_end;
       if (s >= bodies.size() || e > bodies.size() || s > e) continue;
+#ifdef ORC_HP_AGG
+      // variant (not the reference): the same three fallbacks with f64 running sums, used to
+      // separate "summation-order noise in the node centres" from every other source of difference
+      {
+        double tm = 0, ta = 0, ax = 0, ay = 0, mx = 0, my = 0, cx = 0, cy = 0;
+        for (size_t b = s; b < e; ++b) {
+          const double q = fabs((double)bodies[b].charge), m = bodies[b].mass;
+          const double x = bodies[b].pos.x, y = bodies[b].pos.y;
+          tm += m, ta += q, ax += q * x, ay += q * y, mx += m * x, my += m * y, cx += x, cy += y;
+        }
+        V2 wp;
+        if (ta > (double)1e-6f) wp = v2((float)(ax / ta), (float)(ay / ta));
+        else if (tm > (double)1e-6f) wp = v2((float)(mx / tm), (float)(my / tm));
+        else if (e - s > 0) wp = v2((float)(cx / (double)(e - s)), (float)(cy / (double)(e - s)));
+        else wp = v2(0, 0);
+        nodes[node].pos = wp;
+        nodes[node].mass = nodes[i].mass + nodes[i + 1].mass + nodes[i + 2].mass + nodes[i + 3].mass;
+        nodes[node].charge =
+            nodes[i].charge + nodes[i + 1].charge + nodes[i + 2].charge + nodes[i + 3].charge;
+        continue;
+      }
+#endif
       float total_mass = 0.0f;
       for (size_t b = s; b < e; ++b) total_mass += bodies[b].mass;
       float total_abs_charge = 0.0f;
@@ -821,6 +843,23 @@ uint64_t orc_canonical(const OrcSim *s, OrcCanon *out, uint64_t cap) {
   uint32_t md = 0;
   canon_walk(s->qt, count, out, cap, md);
   return count;
+}
+
+// Overwrite node centres, given in canonical DFS pre-order (test hook: lets a test run the
+// reference traversal on a tree whose centres were computed elsewhere).
+void orc_set_canonical_pos(OrcSim *s, const float *pos_xy, uint64_t count) {
+  if (s->bodies.empty()) return;
+  std::vector<size_t> stack{0};
+  uint64_t k = 0;
+  while (!stack.empty() && k < count) {
+    size_t nd = stack.back();
+    stack.pop_back();
+    s->qt.nodes[nd].pos = v2(pos_xy[2 * k], pos_xy[2 * k + 1]);
+    ++k;
+    size_t c = s->qt.nodes[nd].children;
+    if (c != 0)
+      for (int q = 3; q >= 0; --q) stack.push_back(c + (size_t)q);
+  }
 }
 
 uint32_t orc_max_depth(const OrcSim *s) {

@@ -104,6 +104,8 @@ void orc_build(OrcSim *, int mode, float hw, float hh, int threads);
 uint64_t orc_num_nodes(const OrcSim *);   /* highest live node index + 1 */
 void orc_get_nodes(const OrcSim *, OrcNode *out);
 uint64_t orc_canonical(const OrcSim *, OrcCanon *out, uint64_t cap); /* returns count */
+/* test hook: overwrite node centres, canonical DFS pre-order */
+void orc_set_canonical_pos(OrcSim *, const float *pos_xy, uint64_t count);
 uint32_t orc_max_depth(const OrcSim *);
 uint32_t orc_flags(const OrcSim *); /* bit0: some subdivision went deeper than 32 levels;
                                        bit1: a degenerate (refused) leaf exists;

@@ -68,7 +68,8 @@ _LIBS: dict[str, C.CDLL] = {}
 
 
 def load(variant: str = "") -> C.CDLL:
-    """variant: "" (plain), "uvfma" (fused Vec2::mag_sq), "native" (-O3 -march=native, timing)."""
+    """variant: "" (plain), "uvfma" (fused Vec2::mag_sq), "hp" (f64 node-centre sums; not the
+    reference), "native" (-O3 -march=native, timing)."""
     if variant in _LIBS:
         return _LIBS[variant]
     name = "liboracle.so" if not variant else f"liboracle_{variant}.so"
@@ -95,6 +96,7 @@ def load(variant: str = "") -> C.CDLL:
         "orc_num_nodes": (u64, [vp]),
         "orc_get_nodes": (None, [vp, vp]),
         "orc_canonical": (u64, [vp, vp, u64]),
+        "orc_set_canonical_pos": (None, [vp, pf, u64]),
         "orc_max_depth": (u32, [vp]),
         "orc_flags": (u32, [vp]),
         "orc_field": (None, [vp, f, i, pc]),
@@ -219,6 +221,10 @@ class OracleSim:
         if m:
             self.lib.orc_canonical(self.h, out.ctypes.data, m)
         return out
+
+    def set_canonical_pos(self, pos):
+        pos = _f32(pos, (-1, 2))
+        self.lib.orc_set_canonical_pos(self.h, _ptr(pos), len(pos))
 
     def max_depth(self):
         return int(self.lib.orc_max_depth(self.h))

@@ -1,0 +1,79 @@
+"""CPU: the device construction logic (psim_core.cuh + tree_logic.cuh, compiled as plain C++ by
+tests/emu) and the warp-lockstep traversal scheme, against the oracle.  This checks the ALGORITHM
+before GPU time is spent; the GPU tests check the kernels themselves through the C ABI."""
+import numpy as np
+import pytest
+
+from helpers import (KE, Emu, assert_same_topology, canonical_from_nodes, check_next_pointers, clustered,
+                     electrolyte, oracle_for, rel_l2, uniform_pm1)
+
+
+def run(bodies, mode, leaf=1, thread=1024, theta=1.0, variant="hp"):
+    emu = Emu()
+    o = oracle_for(bodies, theta=theta, leaf=leaf, thread=thread, variant=variant)
+    o.build() if mode == 0 else o.build_with_domain(bodies["hw"], bodies["hh"])
+    emu.build(bodies, mode, leaf, thread)
+    nodes = emu.nodes()
+    check_next_pointers(nodes)
+    ec, oc = canonical_from_nodes(nodes), o.canonical()
+    assert_same_topology(ec, oc)
+    assert np.array_equal(ec["charge"], oc["charge"])
+    return emu, o, ec, oc
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 100, 5000])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_topology_small(n, mode):
+    emu, o, ec, oc = run(uniform_pm1(n), mode)
+    assert np.array_equal(emu.perm.astype(np.int64), o.permutation())
+    assert np.array_equal(ec["mass"], oc["mass"])
+
+
+@pytest.mark.parametrize("gen,n,mode,theta", [(uniform_pm1, 20000, 0, 1.0), (electrolyte, 20000, 1, 0.5),
+                                              (clustered, 30000, 0, 1.0)])
+def test_lockstep_traversal_is_bit_exact_given_equal_centres(gen, n, mode, theta):
+    bodies = gen(n)
+    emu, o, ec, oc = run(bodies, mode, theta=theta)
+    assert np.array_equal(emu.perm.astype(np.int64), o.permutation())
+    assert np.array_equal(ec["pos"], oc["pos"])  # f64 sums on both sides round to the same f32
+    sb = emu.sorted_bodies()
+    fe, steps, pairs = emu.walk(sb[:, :2], radius=sb[:, 3], theta=theta)
+    fo, counters = o.acc_points(sb[:, :2], radius=sb[:, 3], k_e=KE)
+    assert np.array_equal(fe, fo)
+    assert pairs == counters[2]
+    # and with the device centres injected into the strict reference-order tree
+    s = oracle_for(bodies, theta=theta)
+    s.build() if mode == 0 else s.build_with_domain(bodies["hw"], bodies["hh"])
+    s.set_canonical_pos(ec["pos"])
+    fi, _ = s.acc_points(sb[:, :2], radius=sb[:, 3], k_e=KE)
+    assert np.array_equal(fe, fi)
+
+
+@pytest.mark.parametrize("leaf,thread", [(8, 32), (4, 1024), (1, 1), (3, 2), (16, 5), (2, 1024)])
+def test_capacities(leaf, thread):
+    for bodies, mode in ((uniform_pm1(5000), 0), (clustered(5000), 1)):
+        emu, o, ec, oc = run(bodies, mode, leaf, thread)
+        operm = o.permutation()
+        lm = oc["is_leaf"] == 1
+        for a, b in zip(oc["start"][lm], oc["end"][lm]):
+            assert set(operm[a:b]) == set(emu.perm[a:b].astype(np.int64))
+
+
+def test_degenerate_inputs():
+    b = uniform_pm1(1000)
+    b["pos"][10:15] = b["pos"][10]
+    b["pos"][500] = b["pos"][501]
+    for leaf, thread in [(1, 1024), (4, 1024), (8, 4)]:
+        emu, o, ec, oc = run(b, 0, leaf, thread)
+        assert o.flags() & 2 and emu.meta()["zero_leaves"] >= 1
+    b = uniform_pm1(64)
+    b["pos"][:] = b["pos"][0]
+    for mode in (0, 1):
+        emu, o, ec, oc = run(b, mode)
+        assert len(ec) == 1
+    b = uniform_pm1(3)
+    b["pos"][:] = [[100, 100], [np.nextafter(np.float32(100), np.float32(200)), 100], [5, 5]]
+    for half in (300.0, 8000.0):
+        b["hw"] = b["hh"] = half
+        emu, o, ec, oc = run(b, 1)
+        assert o.max_depth() >= 25

@@ -1,0 +1,217 @@
+"""GPU parity: cell list, neighbour queries, LJ / repulsion / stack pressure, integrator, electron
+update and the fused step — through the C ABI against the oracle.  Index work is bit-exact; float
+work within 1e-5 relative L2 (gather order differs from the reference's serial pair loop)."""
+import numpy as np
+import pytest
+
+from helpers import KE, clustered, electrolyte, oracle_for, rel_l2, uniform_pm1
+from test_gpu_tree import make_sim
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def both_after_build(bodies, variant="hp", **kw):
+    sim = make_sim(bodies, **kw)
+    o = oracle_for(bodies, variant=variant)
+    sim.quadtree.build(sim.bodies)
+    o.build()
+    assert np.array_equal(o.permutation(), sim.bodies.id.astype(np.int64))
+    return sim, o
+
+
+@pytest.mark.parametrize("cell_size", [11.88, 3.96, 50.0])
+def test_cell_list_contents(cuda_device, cell_size):
+    bodies = clustered(30_000)
+    # a few bodies outside the domain: coord() clamps them into the border cells
+    bodies["pos"][:5] *= 1.5
+    sim, o = both_after_build(bodies)
+    hw, hh = bodies["hw"], bodies["hh"]
+    sim.cell_list.update_domain_size(hw, hh)
+    sim.cell_list.cell_size = cell_size
+    sim.cell_list.rebuild(sim.bodies)
+    o.cell_set_domain(hw, hh)
+    o.cell_rebuild(cell_size)
+    gx, gy, off, idx = sim.cell_list.cells()
+    assert (gx, gy) == o.cell_dims()
+    rng = np.random.default_rng(3)
+    nonempty = np.nonzero(np.diff(off))[0]
+    for c in np.concatenate([rng.choice(nonempty, 300), rng.integers(0, gx * gy, 100)]):
+        assert np.array_equal(idx[off[c]:off[c + 1]].astype(np.int64), o.cell_contents(int(c)))
+    assert off[-1] == len(bodies["pos"])
+    sim.close()
+
+
+def test_neighbor_queries(cuda_device):
+    bodies = clustered(30_000)
+    sim, o = both_after_build(bodies)
+    hw, hh = bodies["hw"], bodies["hh"]
+    sim.cell_list.update_domain_size(hw, hh)
+    sim.cell_list.cell_size = 11.88
+    sim.cell_list.rebuild(sim.bodies)
+    o.cell_set_domain(hw, hh)
+    o.cell_rebuild(11.88)
+    rng = np.random.default_rng(5)
+    q = rng.choice(len(bodies["pos"]), 400, replace=False)
+    for cutoff in (3.96, 7.5, 30.0):
+        got = sim._neighbors(q, cutoff, False)
+        for i, g in zip(q, got):
+            assert np.array_equal(g, o.cell_neighbors(int(i), cutoff))  # same order as the reference
+            assert set(g) == set(o.tree_neighbors(int(i), cutoff))        # the tree query gives the same set
+        metal = sim._neighbors(q[:100], cutoff, True)
+        for i, g in zip(q[:100], metal):
+            assert len(g) == o.cell_metal_neighbor_count(int(i), cutoff)
+    assert sim.cell_list.metal_neighbor_count(sim.bodies, int(q[0]), 3.96) == o.cell_metal_neighbor_count(int(q[0]), 3.96)
+    sim.close()
+
+
+def test_lj_forces(cuda_device):
+    from particlesim_b200 import forces
+    bodies = clustered(40_000)
+    sim = make_sim(bodies)
+    o = oracle_for(bodies, variant="hp")
+    hw, hh = bodies["hw"], bodies["hh"]
+    sim.reset_acc()
+    forces.prepare_spatial_structures(sim)
+    forces.attract(sim)
+    coul = sim.bodies.acc.copy()
+    forces.apply_lj_forces(sim)
+    o.reset_acc()
+    o.prepare_spatial_structures(hw, hh)
+    o.attract(KE)
+    o.apply_lj_forces(True)
+    ob = o.get_bodies()
+    assert np.array_equal(ob["id"], sim.bodies.id)
+    lj_dev = sim.bodies.acc - coul
+    assert np.abs(lj_dev).max() > 0, "the clustered set must exercise LJ pairs"
+    assert rel_l2(sim.bodies.acc, ob["acc"]) <= TOL
+    sim.close()
+
+
+def test_repulsion_and_stack_pressure(cuda_device):
+    from particlesim_b200 import SimConfig, default_species_table, forces
+    bodies = electrolyte(30_000)
+    table = default_species_table()
+    for sp in (0, 3, 4, 5):
+        table["repulsion_enabled"][sp] = 1
+    cfg = SimConfig(stack_pressure_enabled=True, stack_pressure=0.5, stack_pressure_decay=30.0)
+    sim = make_sim(bodies, config=cfg, species_table=table)
+    sim.config.coulomb_constant = float(KE)
+    o = oracle_for(bodies, variant="hp")
+    o.set_species_table(table)
+    hw, hh = bodies["hw"], bodies["hh"]
+    sim.reset_acc()
+    forces.prepare_spatial_structures(sim)
+    forces.attract(sim)
+    forces.apply_lj_forces(sim)
+    forces.apply_repulsive_forces(sim)
+    forces.apply_stack_pressure(sim)
+    o.reset_acc()
+    o.prepare_spatial_structures(hw, hh)
+    o.attract(KE)
+    base = o.get_bodies()["acc"].copy()
+    o.apply_lj_forces(True)
+    o.apply_repulsive_forces(True)
+    o.apply_stack_pressure(True, 0.5, 30.0, hw)
+    ob = o.get_bodies()
+    assert np.abs(ob["acc"] - base).max() > 0
+    assert rel_l2(sim.bodies.acc, ob["acc"]) <= TOL
+    sim.close()
+
+
+@pytest.mark.parametrize("enable_z", [False, True])
+def test_iterate(cuda_device, enable_z):
+    from particlesim_b200 import SimConfig, forces
+    bodies = electrolyte(30_000)
+    rng = np.random.default_rng(11)
+    bodies["vel"] = rng.normal(0, 2.0, bodies["pos"].shape).astype(np.float32)  # fast enough to hit the walls
+    z = rng.uniform(-1, 1, len(bodies["pos"])).astype(np.float32)
+    vz = rng.normal(0, 0.2, len(bodies["pos"])).astype(np.float32)
+    cfg = SimConfig(damping_base=0.98, enable_out_of_plane=enable_z)
+    from particlesim_b200 import Bodies, Simulation
+    b = Bodies(bodies["pos"], z=z, vel=bodies["vel"], vz=vz, mass=bodies["mass"], radius=bodies["radius"],
+               charge=bodies["charge"], species=bodies["species"])
+    sim = Simulation(b, bodies["hw"], bodies["hh"], domain_depth=1.0, dt=5.0, config=cfg)
+    sim.config.coulomb_constant = float(KE)
+    o = oracle_for(bodies, variant="hp")
+    o.set_bodies(bodies["pos"], z=z, vel=bodies["vel"], vz=vz, mass=bodies["mass"], radius=bodies["radius"],
+                 charge=bodies["charge"], species=bodies["species"])
+    hw, hh = bodies["hw"], bodies["hh"]
+    sim.reset_acc()
+    forces.prepare_spatial_structures(sim)
+    forces.attract(sim)
+    sim.iterate()
+    o.reset_acc()
+    o.prepare_spatial_structures(hw, hh)
+    o.attract(KE)
+    o.iterate(5.0, 0.98, hw, hh, 1.0, enable_z)
+    ob = o.get_bodies()
+    sim.download(("pos", "vel", "z", "vz"))
+    assert np.abs(sim.bodies.pos[:, 0]).max() <= hw and np.abs(sim.bodies.pos[:, 1]).max() <= hh
+    assert rel_l2(sim.bodies.pos, ob["pos"]) <= 1e-6
+    assert rel_l2(sim.bodies.vel, ob["vel"]) <= TOL
+    if enable_z:
+        assert rel_l2(sim.bodies.z, ob["z"]) <= TOL and rel_l2(sim.bodies.vz, ob["vz"]) <= TOL
+    else:
+        assert np.array_equal(sim.bodies.z, ob["z"])
+    sim.close()
+
+
+def test_update_electrons(cuda_device):
+    bodies = electrolyte(30_000)
+    hw, hh = bodies["hw"], bodies["hh"]
+    sim = make_sim(bodies)
+    sim.background_e_field = (0.003, 0.001)
+    sim.quadtree.build_with_domain(sim.bodies, hw, hh)
+    sim.update_electrons()
+    o = oracle_for(bodies, variant="hp")
+    o.build_with_domain(hw, hh)
+    o.update_electrons((0.003, 0.001), 5.0, KE, threads=0)
+    ebody, erel, evel = o.get_electrons()
+    assert np.array_equal(sim.bodies.ebody, ebody)
+    assert rel_l2(sim.bodies.erel, erel) <= TOL
+    assert rel_l2(sim.bodies.evel, evel) <= TOL
+    sim.close()
+
+
+def test_fused_step_matches_the_call_sequence(cuda_device):
+    """psim_step == reset_acc, prepare_spatial_structures, attract, LJ, repulsion, stack pressure,
+    iterate, build_with_domain, update_electrons (simulation.rs:1000-1196) on the oracle"""
+    bodies = electrolyte(40_000)
+    # make some bodies LJ species so the short-range pass has work
+    sel = np.arange(0, 4000)
+    bodies["species"][sel] = 1
+    bodies["charge"][sel] = 0.0
+    bodies["radius"][sel] = 1.52
+    bodies["mass"][sel] = 6.94
+    keep = ~np.isin(bodies["ebody"], sel)
+    bodies["ebody"], bodies["erel"] = bodies["ebody"][keep], bodies["erel"][keep]
+    hw, hh = bodies["hw"], bodies["hh"]
+    sim = make_sim(bodies)
+    sim.step_device()
+    sim.download(("pos", "vel", "acc", "e_field"))
+    sim.download_electrons()
+    orig = np.zeros(len(sim.bodies), np.uint32)
+    sim._call("psim_download_bodies", *([None] * 11), orig.ctypes.data)
+    o = oracle_for(bodies, variant="hp")
+    o.reset_acc()
+    o.prepare_spatial_structures(hw, hh)
+    o.attract(KE)
+    o.apply_lj_forces(True)
+    o.apply_repulsive_forces(True)
+    o.iterate(5.0, 1.0, hw, hh, 1.0, False)
+    o.build_with_domain(hw, hh)
+    o.update_electrons((0.0, 0.0), 5.0, KE, threads=0)
+    ob = o.get_bodies()
+    assert np.array_equal(ob["id"], orig.astype(np.uint64))
+    assert rel_l2(sim.bodies.pos, ob["pos"]) <= 1e-6
+    assert rel_l2(sim.bodies.vel, ob["vel"]) <= TOL
+    assert rel_l2(sim.bodies.acc, ob["acc"]) <= TOL
+    ebody, erel, evel = o.get_electrons()
+    sb = np.zeros(len(ebody), np.uint32)
+    sr = np.zeros((len(ebody), 2), np.float32)
+    sv = np.zeros((len(ebody), 2), np.float32)
+    sim._call("psim_download_electrons", sb.ctypes.data, sr.ctypes.data, sv.ctypes.data)
+    assert np.array_equal(sb, ebody)
+    assert rel_l2(sr, erel) <= TOL and rel_l2(sv, evel) <= TOL
+    sim.close()

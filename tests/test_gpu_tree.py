@@ -1,0 +1,169 @@
+"""GPU parity: keys, sort permutation, node topology, leaf membership, aggregates — through the C ABI,
+against the oracle on the same seeded inputs.  Bit-exact for everything integer; charge and mass
+bit-exact; node centres to rounding (see DESIGN.md "node centres")."""
+import numpy as np
+import pytest
+
+from helpers import (KE, Emu, assert_same_topology, canonical_from_nodes, check_next_pointers, clustered,
+                     electrolyte, oracle_for, uniform_pm1)
+
+pytestmark = pytest.mark.gpu
+
+
+def make_sim(bodies, **kw):
+    from particlesim_b200 import Bodies, Simulation
+    b = Bodies(bodies["pos"], vel=bodies.get("vel"), mass=bodies.get("mass"), radius=bodies.get("radius"),
+               charge=bodies.get("charge"), species=bodies.get("species"), ebody=bodies.get("ebody"),
+               erel=bodies.get("erel"))
+    sim = Simulation(b, bodies["hw"], bodies["hh"], **kw)
+    sim.config.coulomb_constant = float(KE)
+    return sim
+
+
+def build_both(bodies, mode, leaf=1, thread=1024, variant=""):
+    sim = make_sim(bodies, leaf_capacity=leaf, thread_capacity=thread)
+    o = oracle_for(bodies, leaf=leaf, thread=thread, variant=variant)
+    if mode == 0:
+        sim.quadtree.build(sim.bodies)
+        o.build()
+    else:
+        sim.quadtree.build_with_domain(sim.bodies, bodies["hw"], bodies["hh"])
+        o.build_with_domain(bodies["hw"], bodies["hh"])
+    return sim, o
+
+
+CASES = [
+    ("uniform_1", lambda: uniform_pm1(1)), ("uniform_2", lambda: uniform_pm1(2)),
+    ("uniform_3", lambda: uniform_pm1(3)), ("uniform_33", lambda: uniform_pm1(33)),
+    ("uniform_4097", lambda: uniform_pm1(4097)), ("uniform_100k", lambda: uniform_pm1(100_000)),
+    ("electrolyte_50k", lambda: electrolyte(50_000)), ("clustered_60k", lambda: clustered(60_000)),
+]
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("name,gen", CASES)
+def test_topology_permutation_aggregates(cuda_device, name, gen, mode):
+    bodies = gen()
+    sim, o = build_both(bodies, mode)
+    n = len(bodies["pos"])
+    # keys: sorted, and equal to the fp32-recurrence replay of the emulation
+    keys = sim.quadtree.keys()
+    assert np.all(keys[:-1] <= keys[1:])
+    emu = Emu()
+    emu.build(bodies, mode)
+    assert np.array_equal(keys, emu.keys)
+    # permutation: element for element (C = 1, duplicate-free)
+    assert np.array_equal(sim.bodies.id.astype(np.int64), o.permutation())
+    assert np.array_equal(sim.bodies.pos, o.get_bodies()["pos"])
+    # topology
+    nodes = sim.quadtree.nodes
+    check_next_pointers(nodes)
+    dc, oc = canonical_from_nodes(nodes), o.canonical()
+    assert_same_topology(dc, oc)
+    st = sim.stats()
+    assert st["reference_nodes"] == len(oc) and st["max_depth"] == o.max_depth()
+    # aggregates
+    assert np.array_equal(dc["charge"], oc["charge"])
+    assert np.array_equal(dc["mass"], oc["mass"])
+    leaf = oc["is_leaf"] == 1
+    assert np.array_equal(dc["pos"][leaf], oc["pos"][leaf])
+    scale = max(1.0, float(np.abs(bodies["pos"]).max()))
+    assert np.abs(dc["pos"].astype(np.float64) - oc["pos"]).max() <= 2e-6 * scale * max(1.0, np.sqrt(n) / 30)
+    sim.close()
+
+
+@pytest.mark.parametrize("name,gen", [("uniform_100k", lambda: uniform_pm1(100_000)),
+                                      ("clustered_60k", lambda: clustered(60_000))])
+def test_centres_equal_f64_oracle(cuda_device, name, gen):
+    """against the oracle variant that sums node centres in f64, centres agree to 1 ulp"""
+    bodies = gen()
+    sim, o = build_both(bodies, 0, variant="hp")
+    dc, oc = canonical_from_nodes(sim.quadtree.nodes), o.canonical()
+    assert_same_topology(dc, oc)
+    a, b = dc["pos"].astype(np.float64), oc["pos"].astype(np.float64)
+    ulp = np.spacing(np.abs(oc["pos"]).astype(np.float32)).astype(np.float64)
+    assert np.all(np.abs(a - b) <= ulp)
+    sim.close()
+
+
+@pytest.mark.parametrize("leaf,thread", [(8, 32), (4, 1024), (1, 1), (3, 2), (16, 5), (2, 1024)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_leaf_and_thread_capacity(cuda_device, leaf, thread, mode):
+    bodies = clustered(20_000)
+    sim, o = build_both(bodies, mode, leaf, thread)
+    dc, oc = canonical_from_nodes(sim.quadtree.nodes), o.canonical()
+    assert_same_topology(dc, oc)
+    # leaf membership as sets (order inside a multi-body leaf is the unstable partition's)
+    operm, dperm = o.permutation(), sim.bodies.id.astype(np.int64)
+    lm = oc["is_leaf"] == 1
+    for a, b in zip(oc["start"][lm], oc["end"][lm]):
+        assert set(operm[a:b]) == set(dperm[a:b])
+    assert np.array_equal(dc["charge"], oc["charge"])
+    assert np.allclose(dc["mass"], oc["mass"], rtol=1e-6, atol=0)
+    sim.close()
+
+
+def test_coincident_bodies_make_refused_leaves(cuda_device):
+    """coincident bodies beyond the leaf capacity stay one zero-aggregate leaf"""
+    b = uniform_pm1(1000)
+    b["pos"][10:15] = b["pos"][10]
+    b["pos"][500] = b["pos"][501]
+    for leaf, thread in [(1, 1024), (4, 1024), (8, 4)]:
+        sim, o = build_both(b, 0, leaf, thread)
+        dc, oc = canonical_from_nodes(sim.quadtree.nodes), o.canonical()
+        assert_same_topology(dc, oc)
+        assert np.array_equal(dc["charge"], oc["charge"])
+        assert o.flags() & 2
+        assert sim.stats()["zero_leaves"] >= 1
+        sim.close()
+
+
+def test_all_bodies_identical_and_empty(cuda_device):
+    b = uniform_pm1(64)
+    b["pos"][:] = b["pos"][0]
+    for mode in (0, 1):
+        sim, o = build_both(b, mode)
+        dc, oc = canonical_from_nodes(sim.quadtree.nodes), o.canonical()
+        assert_same_topology(dc, oc)
+        assert len(dc) == 1 and dc["charge"][0] == 0.0 and dc["mass"][0] == 0.0
+        sim.close()
+    # empty input: build is a no-op (quadtree.rs:155-158)
+    from particlesim_b200 import Bodies, Simulation
+    sim = Simulation(Bodies(np.zeros((0, 2), np.float32)), 10.0, 10.0)
+    sim.quadtree.build(sim.bodies)
+    assert sim.stats()["compact_nodes"] == 0 and len(sim.quadtree.nodes) == 0
+    sim.quadtree.field(sim.bodies, KE)
+    sim.close()
+
+
+def test_adjacent_floats_deep_chain(cuda_device):
+    """two bodies one ulp apart: the fp32 centre recurrence decides the depth, not a fixed grid"""
+    b = uniform_pm1(3)
+    b["pos"][:] = [[100, 100], [np.nextafter(np.float32(100), np.float32(200)), 100], [5, 5]]
+    for half in (300.0, 8000.0):
+        b["hw"] = b["hh"] = half
+        sim, o = build_both(b, 1)
+        assert_same_topology(canonical_from_nodes(sim.quadtree.nodes), o.canonical())
+        assert sim.stats()["max_depth"] == o.max_depth() >= 25
+        sim.close()
+
+
+def test_single_body_degenerate_parameters(cuda_device):
+    """src/body/tests/anion.rs:48-49: Quadtree::new(0.5, 0.01, 1, 1) builds on one body"""
+    b = uniform_pm1(1)
+    sim, o = build_both(b, 0, 1, 1)
+    dc, oc = canonical_from_nodes(sim.quadtree.nodes), o.canonical()
+    assert_same_topology(dc, oc)
+    assert dc["charge"][0] == oc["charge"][0] == 0.0  # thread_capacity 1: the leaf is never aggregated
+    sim.close()
+
+
+def test_node_arena_overflow_is_an_error(cuda_device):
+    from particlesim_b200 import PsimError
+    bodies = clustered(5000)
+    with pytest.raises(PsimError) as e:
+        sim = make_sim(bodies, node_factor=1.0)
+        sim._cfg  # noqa: B018
+        # node_factor 1.0 => arena of n + 1024 nodes < 1.7 n
+        sim.quadtree.build(sim.bodies)
+    assert e.value.code == -4
