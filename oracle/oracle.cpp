@@ -321,8 +321,16 @@ struct Quadtree {
       std::lock_guard<std::mutex> g(m);
       queue.push_back(v);
     }
+    std::vector<uint8_t> extra_claims;  // nodes past the reference's fixed claim array (it would
+                                        // panic there: more than 4N+1024 nodes); single worker only
     bool claim(size_t node) {
-      if (node >= claims.size()) return true;  // arena grew (single-worker only)
+      if (node >= claims.size()) {
+        const size_t k = node - claims.size();
+        if (k >= extra_claims.size()) extra_claims.resize((k + 1) * 2, 0);
+        if (extra_claims[k]) return false;
+        extra_claims[k] = 1;
+        return true;
+      }
       uint8_t z = 0;
       return claims[node].compare_exchange_strong(z, 1);
     }
@@ -873,6 +881,7 @@ uint32_t orc_max_depth(const OrcSim *s) {
 uint32_t orc_flags(const OrcSim *s) {
   uint32_t f = s->qt.flags.load();
   if (!s->bodies.empty() && orc_max_depth(s) > 32) f |= 1u;
+  if (!s->bodies.empty() && orc_num_nodes(s) > 4 * s->bodies.size() + 1024) f |= 8u;
   return f;
 }
 

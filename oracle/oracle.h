@@ -109,7 +109,9 @@ void orc_set_canonical_pos(OrcSim *, const float *pos_xy, uint64_t count);
 uint32_t orc_max_depth(const OrcSim *);
 uint32_t orc_flags(const OrcSim *); /* bit0: some subdivision went deeper than 32 levels;
                                        bit1: a degenerate (refused) leaf exists;
-                                       bit2: chain coincidence test differs from "all bit-identical" */
+                                       bit2: chain coincidence test differs from "all bit-identical";
+                                       bit3: more than 4N+1024 nodes (the reference's fixed claim
+                                             array, quadtree.rs:207, would be indexed out of bounds) */
 /* Quadtree::field: e_field[i] = acc_pos(pos_i, 1, radius_i).  threads as above (rayon par_iter). */
 void orc_field(OrcSim *, float k_e, int threads, OrcCounters *ctr);
 /* acc_pos for arbitrary points (field_at_point is q=1, radius=0) */

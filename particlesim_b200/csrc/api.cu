@@ -422,7 +422,7 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
   }
   const uint32_t c_eff = effective_capacity(ctx->cfg.leaf_capacity, ctx->cfg.thread_capacity);
   tree_count_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, st>>>(
-      ctx->keys[0], ctx->keys[1], ctx->tree_plan, kTreePasses, n, c_eff, ctx->meta, ctx->le);
+      ctx->keys[0], ctx->keys[1], ctx->tree_plan, kTreePasses, b.pqr, n, c_eff, ctx->meta, ctx->le);
   LAUNCHED(ctx);
   CK(exclusive_scan(LeCountFn{ctx->le}, n, ctx->nodebase, ctx->scan_partials, &ctx->meta->num_nodes, st));
   ctx->launches += 3;

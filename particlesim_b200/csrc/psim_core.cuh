@@ -156,14 +156,55 @@ PSIM_HD uint32_t run_end(const uint64_t* keys, uint32_t n, uint32_t i, uint32_t 
   return b;
 }
 
-// Depth of the leaf cell that contains body i, and whether body i is the first body of that leaf.
+// Smallest j in [0, hi] such that every body in [j, i] shares at least `d` levels with body i.
+// Requires hi <= i and that bodies [hi, i] already do.
+PSIM_HD uint32_t run_begin(const uint64_t* keys, uint32_t i, uint32_t hi, int d) {
+  if (d <= 0) return 0;
+  const uint64_t ki = keys[i];
+  if (hi == 0 || lcp_levels(ki, keys[hi - 1]) < d) return hi;
+  uint32_t step = 1, in = hi - 1;  // `in` is inside
+  while (true) {
+    if (step > in) break;
+    if (lcp_levels(ki, keys[in - step]) < d) break;
+    in -= step;
+    step <<= 1;
+  }
+  // first index known outside is in - step (or "-1"); binary search in (out, in)
+  int64_t a = (int64_t)in - (int64_t)step, b = in;  // a outside (or < 0), b inside
+  if (a < -1) a = -1;
+  while (b - a > 1) {
+    const int64_t mid = a + ((b - a) >> 1);
+    if (lcp_levels(ki, keys[mid]) >= d)
+      b = mid;
+    else
+      a = mid;
+  }
+  return (uint32_t)b;
+}
+
+// the reference's coincidence test on one consecutive pair: (w[0].pos - w[1].pos).mag_sq() < 1e-12
+// (quadtree.rs:49-51); pos4 = {x, y, ., .}
+template <class P4>
+PSIM_HD bool close_pair(const P4* pos4, uint32_t a, uint32_t b) {
+  const float dx = f_add(pos4[a].x, -pos4[b].x), dy = f_add(pos4[a].y, -pos4[b].y);
+  return f_add(f_mul(dx, dx), f_mul(dy, dy)) < 1e-12f;
+}
+
+constexpr uint32_t kCloseScanLimit = 1024;
+
+// Depth of the leaf cell that contains body i.
 //   lam   : λ_i
 //   c_eff : effective_capacity()
 //   dcap  : depth_cap(root size)
-// A body inside a run of equal keys that is not the run's first body never starts a leaf.
-// Device rule for coincident bodies: a run of equal 32-level keys that is larger than
-// c_eff becomes one refused leaf at the depth where the run is alone in its cell.
-PSIM_HD int leaf_depth(const uint64_t* keys, uint32_t n, uint32_t i, int lam, uint32_t c_eff, int dcap) {
+// Body i starts that leaf iff λ_i < ℓ_i.  Stop rules, in the reference's terms (quadtree.rs:44-54,
+// 249-257, 281): the cell holds <= c_eff bodies; or every consecutive pair of its bodies is within
+// 1e-6 A (refused: zero-aggregate leaf); or its size is below 1e-6 / the key is used up.
+// The coincidence chain is evaluated in sorted order (the reference uses the partition's current
+// order; the two agree unless a cell holds >= 3 bodies strung out at sub-1e-6 spacing), and runs
+// longer than kCloseScanLimit are continued by key equality (exact for identical positions).
+template <class P4>
+PSIM_HD int leaf_depth(const uint64_t* keys, const P4* pos4, uint32_t n, uint32_t i, int lam,
+                       uint32_t c_eff, int dcap) {
   const uint64_t ki = keys[i];
   // the c_eff-th largest value among L_j = lcp(k_{i-j}, k_i) and R_j = lcp(k_i, k_{i+j})
   uint32_t l = 1, r = 1;
@@ -183,11 +224,27 @@ PSIM_HD int leaf_depth(const uint64_t* keys, uint32_t n, uint32_t i, int lam, ui
     }
   }
   int d = v + 1;
-  if (d > kMaxLevels) {
-    // more than c_eff bodies share all 32 levels with body i: refused leaf where the run is alone
-    const uint32_t rb = run_end(keys, n, i, i + 1, kMaxLevels);
-    const int lam_rb = (rb < n) ? lcp_levels(ki, keys[rb]) : -1;
-    d = (lam > lam_rb ? lam : lam_rb) + 1;
+  const bool cl = i > 0 && close_pair(pos4, i - 1, i);
+  const bool cr = i + 1 < n && close_pair(pos4, i, i + 1);
+  if (cl || cr || d > kMaxLevels) {
+    // run of consecutively coincident bodies around i: [ra, rb)
+    uint32_t ra = i, rb = i + 1, steps = 0;
+    while (ra > 0 && steps < kCloseScanLimit && close_pair(pos4, ra - 1, ra)) --ra, ++steps;
+    if (steps == kCloseScanLimit) ra = run_begin(keys, i, ra, kMaxLevels);
+    steps = 0;
+    while (rb < n && steps < kCloseScanLimit && close_pair(pos4, rb - 1, rb)) ++rb, ++steps;
+    if (steps == kCloseScanLimit) rb = run_end(keys, n, i, rb, kMaxLevels);
+    if (d > kMaxLevels) {
+      // bodies that share all 32 levels but are not coincident (sub-resolution separation, NaN):
+      // the key cannot split them, so the whole equal-key run stops where it is alone in its cell
+      const uint32_t ka = run_begin(keys, i, i, kMaxLevels), kb = run_end(keys, n, i, i + 1, kMaxLevels);
+      if (ka < ra) ra = ka;
+      if (kb > rb) rb = kb;
+    }
+    const int la = (ra > 0) ? lcp_levels(keys[ra - 1], ki) : -1;
+    const int lb = (rb < n) ? lcp_levels(ki, keys[rb]) : -1;
+    const int d_same = (la > lb ? la : lb) + 1;
+    if (d_same < d) d = d_same;
   }
   return d < dcap ? d : dcap;
 }

@@ -101,8 +101,9 @@ __global__ void __launch_bounds__(256)
 // per body: λ_i and ℓ_i (packed), plus per-depth internal-node counts and the maximum depth
 __global__ void __launch_bounds__(256)
     tree_count_kernel(const uint64_t* __restrict__ keys0, const uint64_t* __restrict__ keys1,
-                      const SortPlan* __restrict__ plan, int npass, uint32_t n, uint32_t c_eff,
-                      TreeMeta* __restrict__ meta, uint16_t* __restrict__ le) {
+                      const SortPlan* __restrict__ plan, int npass, const float4* __restrict__ pqr,
+                      uint32_t n, uint32_t c_eff, TreeMeta* __restrict__ meta,
+                      uint16_t* __restrict__ le) {
   const uint64_t* __restrict__ keys = plan->src[npass] ? keys1 : keys0;
   __shared__ uint32_t s_cnt[kLevels];
   __shared__ uint32_t s_maxd;
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(256)
   const int dcap = (int)meta->dcap;
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const uint16_t lev = body_levels(keys, n, i, c_eff, dcap);
+    const uint16_t lev = body_levels(keys, pqr, n, i, c_eff, dcap);
     le[i] = lev;
     const int lam = le_lambda(lev), ell = le_ell(lev);
     if (lam < ell) {

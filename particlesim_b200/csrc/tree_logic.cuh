@@ -101,10 +101,11 @@ PSIM_HD void meta_reset(TreeMeta* meta, RootQuad r, uint32_t n) {
 }
 
 // (λ_i + 1) | ℓ_i << 8
-PSIM_HD uint16_t body_levels(const uint64_t* keys, uint32_t n, uint32_t i, uint32_t c_eff, int dcap) {
+PSIM_HD uint16_t body_levels(const uint64_t* keys, const float4* pqr, uint32_t n, uint32_t i,
+                             uint32_t c_eff, int dcap) {
   const int lam = lambda_at(keys, i);
   int ell = 0;
-  if (lam < kMaxLevels) ell = leaf_depth(keys, n, i, lam, c_eff, dcap);
+  if (lam < kMaxLevels) ell = leaf_depth(keys, pqr, n, i, lam, c_eff, dcap);
   return (uint16_t)((uint32_t)(lam + 1) | ((uint32_t)ell << 8));
 }
 PSIM_HD int le_lambda(uint16_t le) { return (int)(le & 0xff) - 1; }

@@ -90,7 +90,7 @@ uint32_t emu_build(void* h, uint32_t n, const float* pos_xy, const float* mass, 
   std::vector<uint32_t> nodebase(n + 1);
   uint32_t run = 0;
   for (uint32_t i = 0; i < n; ++i) {
-    le[i] = body_levels(e.keys.data(), n, i, c_eff, dcap);
+    le[i] = body_levels(e.keys.data(), e.pqr.data(), n, i, c_eff, dcap);
     nodebase[i] = run;
     run += le_nodes(le[i]);
     const int lam = le_lambda(le[i]), ell = le_ell(le[i]);

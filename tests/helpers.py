@@ -147,7 +147,11 @@ def clustered(n, seed=SEED, rho=RHO):
     r = np.abs(rng.lognormal(np.log(20.0), 0.5, n_cl))
     ang = rng.uniform(0, 2 * np.pi, n_cl)
     p_cl = cent[which] + np.stack([r * np.cos(ang), r * np.sin(ang)], 1)
-    p_cl = np.round(p_cl / 3.04) * 3.04 + rng.normal(0, 0.05, (n_cl, 2))
+    # one body per lattice site (the reference fills lattices site by site, app/spawn.rs:141-195);
+    # bodies that land on an occupied site are moved to a free site of a growing ring around it
+    site = np.round(p_cl / 3.04).astype(np.int64)
+    site = _unique_sites(site, rng)
+    p_cl = site * 3.04 + rng.normal(0, 0.05, (n_cl, 2))
     # filaments: random walks on the lattice
     p_f = []
     left = n_fil
@@ -155,10 +159,15 @@ def clustered(n, seed=SEED, rho=RHO):
         ln = int(min(left, rng.integers(200, 2000)))
         start = rng.uniform(-L / 2 + 100, L / 2 - 100, 2)
         steps = rng.integers(0, 4, ln)
-        d = np.array([[3.04, 0], [-3.04, 0], [0, 3.04], [0, 3.04]])[steps]
-        p_f.append(start + np.cumsum(d, 0) + rng.normal(0, 0.05, (ln, 2)))
+        d = np.array([[1, 0], [-1, 0], [0, 1], [0, 1]])[steps]
+        walk = np.round(start / 3.04).astype(np.int64) + np.cumsum(d, 0)
+        walk = walk[np.sort(np.unique(walk, axis=0, return_index=True)[1])]  # self-avoiding
+        p_f.append(walk * 3.04 + 1.52 + rng.normal(0, 0.05, walk.shape))
+        ln = max(len(walk), 1)
         left -= ln
     p_f = np.concatenate(p_f) if p_f else np.zeros((0, 2))
+    n_fil = len(p_f)
+    n_bg = n - n_cl - n_fil
     p_bg = rng.uniform(-L / 2, L / 2, (n_bg, 2))
     pos = np.clip(np.concatenate([p_cl, p_f, p_bg]), -L / 2, L / 2).astype(np.float32)
     pos = _dedupe(pos, rng, L)
@@ -170,6 +179,20 @@ def clustered(n, seed=SEED, rho=RHO):
     sh = rng.permutation(n)
     return dict(pos=pos[sh], charge=charge[sh], radius=radius[sh], species=species[sh], mass=mass[sh],
                 hw=L / 2, hh=L / 2)
+
+
+def _unique_sites(site, rng):
+    """make integer lattice sites unique: duplicates random-walk until they find a free site"""
+    site = site.copy()
+    for _ in range(200):
+        key = site[:, 0] * 4_000_003 + site[:, 1]
+        _, first = np.unique(key, return_index=True)
+        if len(first) == len(site):
+            break
+        dup = np.ones(len(site), bool)
+        dup[first] = False
+        site[dup] += rng.integers(-2, 3, (int(dup.sum()), 2))
+    return site
 
 
 def _dedupe(pos, rng, L):
