@@ -6,8 +6,8 @@ Three comparisons, each with its tolerance written out:
   (b) reference-order oracle with the DEVICE's node centres injected: <= 1e-5 — the traversal itself
   (c) strict reference-order oracle: the reference's own f32 running sums put its node centres off
       by ~1e-4 A at these sizes, which flips the opening test for a few targets sitting exactly on a
-      MAC boundary; those targets differ by one node's truncation error.  Asserted: >= 99 % of targets
-      within 1e-5, global rel-L2 <= 2e-3 (see DESIGN.md "node centres").
+      MAC boundary; those targets differ by one node's truncation error.  Asserted: median per-target
+      error <= 1e-6, >= 99 % of targets within 1e-4, global rel-L2 <= 2e-3 (DESIGN.md "node centres").
 plus the BH-vs-FP64-direct error, which must be the same for device and oracle.
 """
 import numpy as np
@@ -64,9 +64,10 @@ def test_field_parity(cuda_device, name, gen, mode, theta):
     # (c) strict oracle
     o, e_strict, counters = oracle("")
     per = per_target_rel(dev, e_strict)
-    frac_ok = float((per <= TOL).mean())
+    frac_ok = float((per <= 1e-4).mean())
     err_strict = rel_l2(dev, e_strict)
-    assert frac_ok >= 0.99 and err_strict <= 2e-3, f"(c) {frac_ok:.5f} of targets within 1e-5, rel-L2 {err_strict:.3e}"
+    assert np.median(per) <= 1e-6 and frac_ok >= 0.99 and err_strict <= 2e-3, \
+        f"(c) median {np.median(per):.2e}, {frac_ok:.5f} of targets within 1e-4, rel-L2 {err_strict:.3e}"
     # BH-vs-direct (algorithmic error at this theta), sampled
     rng = np.random.default_rng(1)
     pick = rng.choice(len(dev), 2000, replace=False)
@@ -74,7 +75,7 @@ def test_field_parity(cuda_device, name, gen, mode, theta):
     bh_dev, bh_orc = rel_l2(dev[pick], direct), rel_l2(e_strict[pick], direct)
     assert abs(bh_dev - bh_orc) <= 0.02 * bh_orc + 1e-6
     print(f"\n{name} theta={theta}: hp {err_hp:.2e} (bit-equal {np.array_equal(dev, e_hp)}), injected {err_inj:.2e}, "
-          f"strict {err_strict:.2e} ({frac_ok:.5f} within 1e-5), BH-vs-direct dev {bh_dev:.4f} oracle {bh_orc:.4f}, "
+          f"strict {err_strict:.2e} (median {np.median(per):.1e}, {frac_ok:.5f} within 1e-4), BH-vs-direct dev {bh_dev:.4f} oracle {bh_orc:.4f}, "
           f"V/A/P per target {np.array(counters) / len(dev)}")
     sim.close()
 
