@@ -111,6 +111,13 @@ int32_t psim_set_stream(psim_ctx *ctx, uint64_t cuda_stream);
 int32_t psim_sync(psim_ctx *ctx);
 int32_t psim_stats_get(psim_ctx *ctx, psim_stats *out);
 int32_t psim_reset_counters(psim_ctx *ctx);
+/* Diagnostics for the roofline (not on the hot path):
+ * interaction counters of Quadtree::field on the current tree, summed over all bodies:
+ * out[0] = internal nodes opened, out[1] = monopoles accepted (non-empty nodes), out[2] = direct
+ * body terms, out[3] = warp steps.  The reference's node visits are n + 4 * out[0]. */
+int32_t psim_field_counters(psim_ctx *ctx, uint64_t *out4);
+/* measured FP32 FMA throughput of this device in TFLOP/s (2 flops per FMA), and the SM count */
+int32_t psim_fp32_peak(psim_ctx *ctx, float *tflops, int32_t *sm_count);
 
 /* ---- data in / out (host pointers; arrays marked opt may be NULL) ---- */
 /* species.rs get_species_props table; nrows <= 32 */
@@ -120,6 +127,10 @@ int32_t psim_upload_bodies(psim_ctx *ctx, uint64_t n, const float *pos_xy, const
                            const float *vel_xy_opt, const float *vz_opt, const float *mass_opt,
                            const float *radius_opt, const float *charge_opt,
                            const uint8_t *species_opt);
+/* the per-step host -> device refresh of a resident body set: positions, velocities and charges
+ * (what the rest of Simulation::step changes on the host); electrons and all other fields stay */
+int32_t psim_update_state(psim_ctx *ctx, uint64_t n, const float *pos_xy, const float *vel_xy_opt,
+                          const float *charge_opt);
 /* only positions / charges changed on the host */
 int32_t psim_update_positions(psim_ctx *ctx, uint64_t n, const float *pos_xy);
 int32_t psim_update_charges(psim_ctx *ctx, uint64_t n, const float *charge);
@@ -198,6 +209,12 @@ typedef struct {
   uint32_t reserved[3];
 } psim_step_params;
 int32_t psim_step(psim_ctx *ctx, const psim_step_params *p);
+/* Device time of each phase of the last psim_step, in ms (CUDA events on the context's stream;
+ * synchronises).  Names follow the reference's profile scopes (src/profiler.rs users):
+ * [0] quadtree_build  [1] cell_list_rebuild  [2] quadtree_field (+attract)  [3] forces_lj/repulsion
+ * [4] iterate  [5] quadtree_build_domain  [6] electron_updates  [7] whole step */
+#define PSIM_NUM_PHASES 8
+int32_t psim_phase_times(psim_ctx *ctx, float *ms8);
 
 #ifdef __cplusplus
 }

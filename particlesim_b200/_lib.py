@@ -80,8 +80,11 @@ SIGNATURES = {
     "psim_sync": (_i32, [_vp]),
     "psim_stats_get": (_i32, [_vp, _vp]),
     "psim_reset_counters": (_i32, [_vp]),
+    "psim_field_counters": (_i32, [_vp, _vp]),
+    "psim_fp32_peak": (_i32, [_vp, C.POINTER(C.c_float), C.POINTER(_i32)]),
     "psim_upload_species_table": (_i32, [_vp, _vp, _u32]),
     "psim_upload_bodies": (_i32, [_vp, _u64] + [_vp] * 8),
+    "psim_update_state": (_i32, [_vp, _u64, _vp, _vp, _vp]),
     "psim_update_positions": (_i32, [_vp, _u64, _vp]),
     "psim_update_charges": (_i32, [_vp, _u64, _vp]),
     "psim_upload_electrons": (_i32, [_vp, _u64, _vp, _vp, _vp]),
@@ -103,6 +106,7 @@ SIGNATURES = {
     "psim_short_range": (_i32, [_vp, _u32]),
     "psim_iterate": (_i32, [_vp, _f, _f, _f, _f, _f, _i32]),
     "psim_step": (_i32, [_vp, _vp]),
+    "psim_phase_times": (_i32, [_vp, _vp]),
 }
 
 _LIB = None

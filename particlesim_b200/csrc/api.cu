@@ -101,6 +101,8 @@ struct psim_ctx {
 
   unsigned long long* step_counter = nullptr;
   uint64_t launches = 0;
+  cudaEvent_t ev[9] = {};
+  bool ev_ok = false, ev_recorded = false;
 };
 
 namespace {
@@ -178,6 +180,22 @@ __global__ void __launch_bounds__(256) set_charges_kernel(const float* q, uint32
     float4 p = pqr[i];
     p.z = q[i];
     pqr[i] = p;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    update_state_kernel(const float2* pos, const float2* vel, const float* q, uint32_t n, float4* pqr, float4* velz) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float4 p = pqr[i];
+    p.x = pos[i].x, p.y = pos[i].y;
+    if (q) p.z = q[i];
+    pqr[i] = p;
+    if (vel) {
+      float4 v = velz[i];
+      v.x = vel[i].x, v.y = vel[i].y;
+      velz[i] = v;
+    }
   }
 }
 
@@ -714,6 +732,9 @@ int32_t psim_create(int32_t device, uint64_t max_bodies, uint64_t max_electrons,
   cudaMemcpy(ctx->table_d, ctx->table_h, sizeof(ctx->table_h), cudaMemcpyHostToDevice);
   cudaMemset(ctx->meta, 0, sizeof(TreeMeta));
   cudaMemset(ctx->step_counter, 0, sizeof(unsigned long long));
+  ctx->ev_ok = true;
+  for (int k = 0; k < 9; ++k)
+    if (cudaEventCreate(&ctx->ev[k]) != cudaSuccess) ctx->ev_ok = false;
   *out = ctx;
   return PSIM_OK;
 }
@@ -722,6 +743,8 @@ int32_t psim_destroy(psim_ctx* ctx) {
   if (!ctx) return PSIM_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->ev_ok)
+    for (int k = 0; k < 9; ++k) cudaEventDestroy(ctx->ev[k]);
   free_all(ctx);
   delete ctx;
   return PSIM_OK;
@@ -752,6 +775,54 @@ int32_t psim_reset_counters(psim_ctx* ctx) {
   if (!ctx) return PSIM_E_ARG;
   ctx->launches = 0;
   CK(cudaMemsetAsync(ctx->step_counter, 0, sizeof(unsigned long long), ctx->stream));
+  return PSIM_OK;
+}
+
+int32_t psim_field_counters(psim_ctx* ctx, uint64_t* out4) {
+  if (!ctx || !out4) return PSIM_E_ARG;
+  if (!ctx->tree_valid) return fail(ctx, PSIM_E_STATE, "psim_field_counters: no tree");
+  out4[0] = out4[1] = out4[2] = out4[3] = 0;
+  if (ctx->n == 0) return PSIM_OK;
+  unsigned long long* d = nullptr;
+  CK(cudaMalloc(&d, 4 * sizeof(unsigned long long)));
+  cudaMemsetAsync(d, 0, 4 * sizeof(unsigned long long), ctx->stream);
+  BodyArrays& b = ctx->b[ctx->cur];
+  const uint32_t groups = (ctx->n + 31) / 32;
+  bh_count_bodies_kernel<<<grid_for(ctx, (uint64_t)groups * 32, 128, 64), 128, 0, ctx->stream>>>(
+      ctx->meta, ctx->t.nodeA, ctx->t.nodeB, b.pqr, ctx->n, field_params(ctx, 1.0f, 0.f, 0.f), d);
+  unsigned long long h[4] = {0, 0, 0, 0};
+  cudaError_t e = cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(ctx, PSIM_E_CUDA, "psim_field_counters", e);
+  for (int k = 0; k < 4; ++k) out4[k] = h[k];
+  return PSIM_OK;
+}
+
+int32_t psim_fp32_peak(psim_ctx* ctx, float* tflops, int32_t* sm_count) {
+  if (!ctx || !tflops) return PSIM_E_ARG;
+  float* d = nullptr;
+  CK(cudaMalloc(&d, sizeof(float)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0), cudaEventCreate(&e1);
+  const int blocks = ctx->sm_count * 8, iters = 4096;
+  float best = 0.0f;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, ctx->stream);
+    fp32_peak_kernel<<<blocks, 256, 0, ctx->stream>>>(d, iters, 1.0000001f, 1e-9f);
+    cudaEventRecord(e1, ctx->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 64.0 * iters * 256.0 * blocks;
+    const float tf = (float)(flops / (ms * 1e-3) / 1e12);
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0), cudaEventDestroy(e1);
+  cudaFree(d);
+  CK(cudaGetLastError());
+  *tflops = best;
+  if (sm_count) *sm_count = ctx->sm_count;
   return PSIM_OK;
 }
 
@@ -1174,21 +1245,67 @@ int32_t psim_iterate(psim_ctx* ctx, float dt, float damping_base, float hw, floa
 int32_t psim_step(psim_ctx* ctx, const psim_step_params* p) {
   if (!ctx || !p) return PSIM_E_ARG;
   int32_t rc;
+  auto mark = [&](int k) {
+    if (ctx->ev_ok) cudaEventRecord(ctx->ev[k], ctx->stream);
+  };
+  mark(0);
   if ((rc = psim_reset_acc(ctx))) return rc;
   if ((rc = build_async(ctx, PSIM_BUILD_CONTAINING, 0.f, 0.f))) return rc;
+  mark(1);
   if (p->do_short_range) {
     const float lj_cutoff = max_lj_cutoff(ctx), repulsion_cutoff = max_repulsion_cutoff(ctx);
     const float max_cutoff = fmaxf(fmaxf(3.0f * lj_cutoff, repulsion_cutoff), lj_cutoff);
     if (max_cutoff > 0.0f && (rc = cell_build_async(ctx, p->hw, p->hh, max_cutoff))) return rc;
   }
+  mark(2);
   if ((rc = field_async(ctx, p->k_e, p->bg_x, p->bg_y, 1))) return rc;
+  mark(3);
   if (p->do_short_range && (rc = short_range_async(ctx, PSIM_SR_LJ | PSIM_SR_REPULSION | PSIM_SR_STACK_PRESSURE))) return rc;
+  mark(4);
   if (p->do_iterate && (rc = iterate_async(ctx, p->dt, p->damping_base, p->hw, p->hh, p->hd, (int)p->enable_out_of_plane))) return rc;
+  mark(5);
   if (p->do_electrons) {
     if ((rc = build_async(ctx, PSIM_BUILD_DOMAIN, p->hw, p->hh))) return rc;
+    mark(6);
     if ((rc = electrons_async(ctx, p->bg_x, p->bg_y, p->dt, p->k_e))) return rc;
+  } else {
+    mark(6);
   }
+  mark(7);
+  ctx->ev_recorded = ctx->ev_ok;
   CK(cudaGetLastError());
+  return PSIM_OK;
+}
+
+int32_t psim_phase_times(psim_ctx* ctx, float* ms8) {
+  if (!ctx || !ms8) return PSIM_E_ARG;
+  for (int k = 0; k < PSIM_NUM_PHASES; ++k) ms8[k] = 0.0f;
+  if (!ctx->ev_recorded) return fail(ctx, PSIM_E_STATE, "psim_phase_times: no psim_step recorded");
+  CK(cudaEventSynchronize(ctx->ev[7]));
+  for (int k = 0; k < 7; ++k) CK(cudaEventElapsedTime(&ms8[k], ctx->ev[k], ctx->ev[k + 1]));
+  CK(cudaEventElapsedTime(&ms8[7], ctx->ev[0], ctx->ev[7]));
+  return PSIM_OK;
+}
+
+int32_t psim_update_state(psim_ctx* ctx, uint64_t n, const float* pos_xy, const float* vel_xy, const float* charge) {
+  if (!ctx || n != ctx->n || (n && !pos_xy)) return fail(ctx, PSIM_E_ARG, "psim_update_state: size mismatch");
+  if (n == 0) return PSIM_OK;
+  const size_t o_pos = 0, o_vel = align256(8 * n), o_q = o_vel + align256(8 * n), total = o_q + align256(4 * n);
+  int32_t rc = ensure_stage(ctx, total);
+  if (rc) return rc;
+  char* sb = static_cast<char*>(ctx->stage);
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(sb + o_pos, pos_xy, 8 * n, cudaMemcpyHostToDevice, st));
+  if (vel_xy) CK(cudaMemcpyAsync(sb + o_vel, vel_xy, 8 * n, cudaMemcpyHostToDevice, st));
+  if (charge) CK(cudaMemcpyAsync(sb + o_q, charge, 4 * n, cudaMemcpyHostToDevice, st));
+  BodyArrays& b = ctx->b[ctx->cur];
+  update_state_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(
+      reinterpret_cast<const float2*>(sb + o_pos), vel_xy ? reinterpret_cast<const float2*>(sb + o_vel) : nullptr,
+      charge ? reinterpret_cast<const float*>(sb + o_q) : nullptr, (uint32_t)n, b.pqr, b.velz);
+  LAUNCHED(ctx);
+  ctx->tree_valid = ctx->grid_valid = false;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
   return PSIM_OK;
 }
 

@@ -44,12 +44,15 @@ struct TraverseCounters {
 };
 
 // Shared walk.  (px, py, q, radius) are per-lane; `live` is false for tail lanes.
-template <bool PARITY>
+// COUNT adds per-lane interaction counters (cnt[0] = internal nodes this lane opened, cnt[1] =
+// monopoles accepted, cnt[2] = direct body terms): the reference visits 1 + 4 * opened nodes.
+template <bool PARITY, bool COUNT = false>
 __device__ __forceinline__ float2 bh_walk(const float4* __restrict__ nodeA,
                                           const uint4* __restrict__ nodeB,
                                           const float4* __restrict__ pqr, uint32_t M, float px,
                                           float py, float q, float radius, bool live,
-                                          const FieldParams P, uint32_t& steps_out) {
+                                          const FieldParams P, uint32_t& steps_out,
+                                          uint32_t* cnt = nullptr) {
   using A = Arith<PARITY>;
   float ax = 0.0f, ay = 0.0f;
   uint32_t skip = live ? 0u : 0xffffffffu;
@@ -74,6 +77,7 @@ __device__ __forceinline__ float2 bh_walk(const float4* __restrict__ nodeA,
         ax = A::add(ax, A::mul(dx, s));
         ay = A::add(ay, A::mul(dy, s));
         skip = nb.x;
+        if (COUNT) cnt[1]++;
       } else if (leaf) {
         for (uint32_t b = nb.y; b < nb.y + nb.z; ++b) {
           const float4 s4 = __ldg(&pqr[b]);
@@ -86,8 +90,11 @@ __device__ __forceinline__ float2 bh_walk(const float4* __restrict__ nodeA,
           const float s = fminf(A::div(A::mul(kq, s4.z), denom), 3.402823466e+38f);
           ax = A::add(ax, A::mul(bx, s));
           ay = A::add(ay, A::mul(by, s));
+          if (COUNT) cnt[2]++;
         }
         skip = nb.x;
+      } else if (COUNT) {
+        cnt[0]++;
       }
     }
     const bool descend = __any_sync(0xffffffffu, active && !accept && !leaf);
@@ -135,6 +142,56 @@ __global__ void __launch_bounds__(128)
     }
   }
   if (step_counter && lane == 0 && my_steps) atomicAdd(step_counter, my_steps);
+}
+
+// diagnostic: the interaction counters of Quadtree::field for the roofline's algorithmic flops
+__global__ void __launch_bounds__(128)
+    bh_count_bodies_kernel(const TreeMeta* __restrict__ meta, const float4* __restrict__ nodeA,
+                           const uint4* __restrict__ nodeB, const float4* __restrict__ pqr, uint32_t n,
+                           FieldParams P, unsigned long long* __restrict__ out4) {
+  const uint32_t M = meta->num_nodes;
+  const uint32_t warps_per_block = blockDim.x >> 5;
+  const uint32_t warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const uint32_t total_warps = gridDim.x * warps_per_block;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t groups = (n + 31) / 32;
+  unsigned long long opened = 0, acc = 0, pairs = 0, wsteps = 0;
+  for (uint32_t g = warp_global; g < groups; g += total_warps) {
+    const uint32_t i = g * 32 + lane;
+    const bool live = i < n;
+    float4 me = make_float4(0, 0, 0, 0);
+    if (live) me = pqr[i];
+    uint32_t steps, cnt[3] = {0, 0, 0};
+    bh_walk<true, true>(nodeA, nodeB, pqr, M, me.x, me.y, 1.0f, me.w, live, P, steps, cnt);
+    opened += cnt[0], acc += cnt[1], pairs += cnt[2];
+    if (lane == 0) wsteps += steps;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    opened += __shfl_xor_sync(0xffffffffu, opened, off);
+    acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    pairs += __shfl_xor_sync(0xffffffffu, pairs, off);
+  }
+  if (lane == 0) {
+    atomicAdd(&out4[0], opened);
+    atomicAdd(&out4[1], acc);
+    atomicAdd(&out4[2], pairs);
+    atomicAdd(&out4[3], wsteps);
+  }
+}
+
+// FP32 FMA pipe peak: 8 independent FMA chains per thread (no memory traffic)
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x0 = fmaf(x0, a, b), x1 = fmaf(x1, a, b), x2 = fmaf(x2, a, b), x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b), x5 = fmaf(x5, a, b), x6 = fmaf(x6, a, b), x7 = fmaf(x7, a, b);
+    }
+  }
+  const float r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (r == 123.456f) out[0] = r;
 }
 
 // acc_pos at arbitrary points.  q / radius may be null (1 and 0: field_at_point).
