@@ -76,6 +76,10 @@ struct psim_ctx {
   uint32_t* irank = nullptr;
   float4* bounds_partial = nullptr;
   TreeArrays t = {};
+  float4* travA = nullptr;   // traversal arrays: charged nodes only, pre-order
+  uint4* travB = nullptr;
+  uint32_t* trav_rank = nullptr;
+  uint32_t* trav_count = nullptr;
   uint32_t* perm = nullptr;
   uint32_t* inv = nullptr;
   bool tree_valid = false;
@@ -322,6 +326,7 @@ FieldParams field_params(const psim_ctx* ctx, float k_e, float bg_x, float bg_y)
   P.k_e = k_e;
   P.bg_x = bg_x;
   P.bg_y = bg_y;
+  P.inv_theta = 1.0f / ctx->cfg.theta;
   return P;
 }
 
@@ -403,6 +408,7 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
   ctx->grid_valid = false;  // the cell list indexes bodies by position in the array
   if (n == 0) {
     CK(cudaMemsetAsync(ctx->meta, 0, sizeof(TreeMeta), st));
+    CK(cudaMemsetAsync(ctx->trav_count, 0, sizeof(uint32_t), st));
     ctx->tree_valid = true;
     return PSIM_OK;
   }
@@ -454,9 +460,17 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
   // bottom-up sweeps, deepest level first; a level's node count is only known on the device, so
   // every launch is sized for the SMs and strides over the level's bucket
   for (int level = kMaxLevels - 1; level >= 0; --level) {
-    aggregate_level_kernel<<<ctx->sm_count * 4, 128, 0, st>>>(level, ctx->meta, b.pqr, b.accm, ctx->t);
+    aggregate_level_kernel<<<ctx->sm_count * 16, 128, 0, st>>>(level, ctx->meta, b.pqr, b.accm, ctx->t);
     LAUNCHED(ctx);
   }
+  // traversal arrays (charged nodes only)
+  CK(exclusive_scan_dyn(ChargedFlagFn{ctx->t.nodeB}, &ctx->meta->num_nodes, ctx->node_cap, ctx->trav_rank,
+                        ctx->scan_partials, ctx->trav_count, st));
+  ctx->launches += 3;
+  compact_traversal_kernel<<<grid_for(ctx, (uint64_t)n * 2, 256, 16), 256, 0, st>>>(
+      ctx->meta, ctx->t.nodeA, ctx->t.nodeB, ctx->trav_rank, ctx->trav_count, ctx->node_cap, ctx->travA,
+      ctx->travB);
+  LAUNCHED(ctx);
   ctx->tree_valid = true;
   ctx->perm_valid = true;
   return PSIM_OK;
@@ -518,15 +532,23 @@ int32_t field_async(psim_ctx* ctx, float k_e, float bg_x, float bg_y, int write_
   BodyArrays& b = ctx->b[ctx->cur];
   const FieldParams P = field_params(ctx, k_e, bg_x, bg_y);
   const uint32_t groups = (n + 31) / 32;
-  const int blocks = grid_for(ctx, (uint64_t)groups * 32, 128, 64);
-  if (ctx->cfg.parity_mode)
+  if (ctx->cfg.parity_mode == 2) {
+    // reference-order walk: bit-identical additions, one node per warp step, on the full tree
+    const int blocks = (int)((groups + 3) / 4);
     bh_field_bodies_kernel<true><<<blocks, 128, 0, ctx->stream>>>(
         ctx->meta, ctx->t.nodeA, ctx->t.nodeB, b.pqr, b.accm, n, P, b.efield, b.accm, write_acc,
         ctx->step_counter);
-  else
-    bh_field_bodies_kernel<false><<<blocks, 128, 0, ctx->stream>>>(
-        ctx->meta, ctx->t.nodeA, ctx->t.nodeB, b.pqr, b.accm, n, P, b.efield, b.accm, write_acc,
-        ctx->step_counter);
+  } else {
+    const int blocks = (int)((groups + 3) / 4);  // one group per warp, launched in Morton order
+    if (ctx->cfg.parity_mode)
+      bh_group_bodies_kernel<true><<<blocks, 128, 0, ctx->stream>>>(
+          ctx->travA, ctx->travB, ctx->trav_count, b.pqr, b.accm, 0, n, P, b.efield, b.accm, write_acc,
+          ctx->step_counter);
+    else
+      bh_group_bodies_kernel<false><<<blocks, 128, 0, ctx->stream>>>(
+          ctx->travA, ctx->travB, ctx->trav_count, b.pqr, b.accm, 0, n, P, b.efield, b.accm, write_acc,
+          ctx->step_counter);
+  }
   LAUNCHED(ctx);
   return PSIM_OK;
 }
@@ -538,13 +560,16 @@ int32_t points_async(psim_ctx* ctx, const float2* pts, const float* q, const flo
   BodyArrays& b = ctx->b[ctx->cur];
   const FieldParams P = field_params(ctx, k_e, 0.f, 0.f);
   const uint32_t groups = (m + 31) / 32;
-  const int blocks = grid_for(ctx, (uint64_t)groups * 32, 128, 64);
-  if (ctx->cfg.parity_mode)
+  const int blocks = (int)((groups + 3) / 4);
+  if (ctx->cfg.parity_mode == 2)
     bh_field_points_kernel<true><<<blocks, 128, 0, ctx->stream>>>(
         ctx->meta, ctx->t.nodeA, ctx->t.nodeB, b.pqr, pts, q, radius, m, P, out, ctx->step_counter);
+  else if (ctx->cfg.parity_mode)
+    bh_group_points_kernel<true><<<blocks, 128, 0, ctx->stream>>>(
+        ctx->travA, ctx->travB, ctx->trav_count, b.pqr, pts, q, radius, 0, m, P, out, ctx->step_counter);
   else
-    bh_field_points_kernel<false><<<blocks, 128, 0, ctx->stream>>>(
-        ctx->meta, ctx->t.nodeA, ctx->t.nodeB, b.pqr, pts, q, radius, m, P, out, ctx->step_counter);
+    bh_group_points_kernel<false><<<blocks, 128, 0, ctx->stream>>>(
+        ctx->travA, ctx->travB, ctx->trav_count, b.pqr, pts, q, radius, 0, m, P, out, ctx->step_counter);
   LAUNCHED(ctx);
   return PSIM_OK;
 }
@@ -639,6 +664,7 @@ void free_all(psim_ctx* c) {
   F(c->sc.hist), F(c->sc.status), F(c->sc.ticket), F(c->tree_plan), F(c->cell_plan);
   F(c->meta), F(c->le), F(c->nodebase), F(c->scan_partials), F(c->irank), F(c->bounds_partial);
   F(c->t.nodeA), F(c->t.nodeB), F(c->t.node_mass), F(c->t.parent), F(c->t.sums), F(c->t.level_nodes);
+  F(c->travA), F(c->travB), F(c->trav_rank), F(c->trav_count);
   F(c->perm), F(c->inv);
   F(c->cell_start), F(c->cell_end), F(c->order), F(c->body_cell);
   F(c->table_d), F(c->stage), F(c->qstage), F(c->step_counter);
@@ -716,6 +742,7 @@ int32_t psim_create(int32_t device, uint64_t max_bodies, uint64_t max_electrons,
   A(&ctx->irank, ctx->node_cap), A(&ctx->bounds_partial, (size_t)ctx->sm_count * 4 + 1);
   A(&ctx->t.nodeA, ctx->node_cap), A(&ctx->t.nodeB, ctx->node_cap), A(&ctx->t.node_mass, ctx->node_cap);
   A(&ctx->t.parent, ctx->node_cap), A(&ctx->t.sums, ctx->node_cap), A(&ctx->t.level_nodes, ctx->node_cap);
+  A(&ctx->travA, ctx->node_cap), A(&ctx->travB, ctx->node_cap), A(&ctx->trav_rank, ctx->node_cap), A(&ctx->trav_count, 1);
   ctx->t.node_cap = ctx->node_cap;
   A(&ctx->perm, nb), A(&ctx->inv, nb);
   A(&ctx->order, nb), A(&ctx->body_cell, nb);

@@ -23,6 +23,7 @@ constexpr int kMaxLevels = 32;  // 2 bits per level in a 64-bit key
 // Node flags kept in the low byte group of NodeB.w
 constexpr uint32_t kNodeLeaf = 1u << 8;      // no children
 constexpr uint32_t kNodeZeroAgg = 1u << 9;   // refused / thread-capacity leaf: mass = charge = pos = 0
+constexpr uint32_t kNodeCharged = 1u << 10;  // some body below the node has a non-zero charge
 constexpr uint32_t kNodeDepthMask = 0xffu;
 
 struct RootQuad {

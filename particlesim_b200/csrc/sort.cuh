@@ -413,4 +413,62 @@ cudaError_t exclusive_scan(F f, uint32_t n, uint32_t* out, uint32_t* partials, u
   return cudaGetLastError();
 }
 
+// Same, for a length that only exists on the device (*n_dev <= n_cap): the launches are sized for
+// n_cap and every kernel clips to *n_dev.
+template <typename F>
+struct ClippedFn {
+  F f;
+  const uint32_t* n_dev;
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return i < *n_dev ? f(i) : 0u; }
+};
+template <typename F>
+__global__ void __launch_bounds__(kScanThreads)
+    scan_downsweep_dyn_kernel(F f, const uint32_t* __restrict__ n_dev, const uint32_t* __restrict__ partials,
+                              uint32_t* __restrict__ out) {
+  __shared__ uint32_t s_w[kScanThreads / 32];
+  const uint32_t n = *n_dev;
+  if (blockIdx.x * kScanTile >= n) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    const uint32_t i = base + j;
+    v[j] = (i < n) ? f(i) : 0;
+    sum += v[j];
+  }
+  uint32_t incl = sum;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += t;
+  }
+  if (lane == 31) s_w[warp] = incl;
+  __syncthreads();
+  uint32_t wbase = 0;
+#pragma unroll
+  for (int w = 0; w < kScanThreads / 32; ++w)
+    if (w < warp) wbase += s_w[w];
+  uint32_t run = partials[blockIdx.x] + wbase + incl - sum;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    const uint32_t i = base + j;
+    if (i < n) out[i] = run;
+    run += v[j];
+  }
+}
+
+template <typename F>
+cudaError_t exclusive_scan_dyn(F f, const uint32_t* n_dev, uint32_t n_cap, uint32_t* out,
+                               uint32_t* partials, uint32_t* total, cudaStream_t stream) {
+  const uint32_t tiles = scan_num_tiles(n_cap);
+  if (tiles == 0) return total ? cudaMemsetAsync(total, 0, sizeof(uint32_t), stream) : cudaSuccess;
+  ClippedFn<F> cf{f, n_dev};
+  scan_reduce_kernel<ClippedFn<F>><<<tiles, kScanThreads, 0, stream>>>(cf, n_cap, partials);
+  scan_partials_kernel<<<1, 1024, 0, stream>>>(partials, tiles, total);
+  scan_downsweep_dyn_kernel<F><<<tiles, kScanThreads, 0, stream>>>(f, n_dev, partials, out);
+  return cudaGetLastError();
+}
+
 }  // namespace psim

@@ -26,6 +26,7 @@ namespace psim {
 struct FieldParams {
   float t_sq, e_sq, k_e;
   float bg_x, bg_y;
+  float inv_theta;  // 1 / theta, only used by conservative pre-tests (never decides a borderline case)
 };
 
 // PARITY = true: IEEE sqrt/div, no FMA contraction, the reference's operation order.
@@ -71,16 +72,19 @@ __device__ __forceinline__ float2 bh_walk(const float4* __restrict__ nodeA,
     const bool leaf = (nb.w & kNodeLeaf) != 0;
     if (active) {
       if (accept) {
-        const float r_eff = fmaxf(dist, A::add(radius, A::mul(na.w, 0.5f)));
-        const float denom = A::mul(A::add(A::mul(r_eff, r_eff), P.e_sq), r_eff);
-        const float s = A::div(A::mul(kq, na.z), denom);
-        ax = A::add(ax, A::mul(dx, s));
-        ay = A::add(ay, A::mul(dy, s));
+        if (na.z != 0.0f) {  // a zero-charge monopole adds exactly +-0
+          const float r_eff = fmaxf(dist, A::add(radius, A::mul(na.w, 0.5f)));
+          const float denom = A::mul(A::add(A::mul(r_eff, r_eff), P.e_sq), r_eff);
+          const float s = A::div(A::mul(kq, na.z), denom);
+          ax = A::add(ax, A::mul(dx, s));
+          ay = A::add(ay, A::mul(dy, s));
+        }
         skip = nb.x;
         if (COUNT) cnt[1]++;
       } else if (leaf) {
         for (uint32_t b = nb.y; b < nb.y + nb.z; ++b) {
           const float4 s4 = __ldg(&pqr[b]);
+          if (!COUNT && s4.z == 0.0f) continue;  // a zero-charge body adds exactly +-0
           const float ex = A::sub(s4.x, px), ey = A::sub(s4.y, py);
           if (A::add(A::mul(ex, ex), A::mul(ey, ey)) < 1e-6f) continue;  // positional self skip
           const float bx = A::sub(px, s4.x), by = A::sub(py, s4.y);
@@ -225,6 +229,245 @@ __global__ void __launch_bounds__(128)
     if (live) out[i] = e;
   }
   if (step_counter && lane == 0 && my_steps) atomicAdd(step_counter, my_steps);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Group walk: the warp's 32 targets share one walk of the tree.  Lanes classify 32 tree nodes per
+// round (one node per lane) against the group's bounding box; a node is
+//   - accepted by every target   -> monopole term for all (shared interaction entry),
+//   - rejected by every target   -> opened (children pushed) or, for a leaf, direct-summed by all,
+//   - otherwise                  -> the node is broadcast and every lane evaluates the reference's opening
+//                                   test EXACTLY for its own target; accepting targets take the monopole,
+//                                   the rest carry on below the node (per-target mask).
+// The box tests are conservative (2e-5 margin, far above the worst-case rounding of the exact test)
+// and never decide a borderline case, so every target sums exactly the reference's interaction set
+// with the reference's per-term arithmetic; only the order of the additions differs from acc_pos.
+// Pending nodes live in a per-warp ring buffer in shared memory: entry = (node, end of the parent's
+// subtree, mask of targets that reach the node).
+constexpr int kStackCap = 416;
+struct WarpShared {
+  uint32_t st_node[kStackCap], st_pend[kStackCap], st_mask[kStackCap];
+};
+
+template <bool PARITY>
+__device__ __forceinline__ float2 bh_group_walk(const float4* __restrict__ nodeA,
+                                                const uint4* __restrict__ nodeB,
+                                                const float4* __restrict__ pqr, uint32_t M, float px,
+                                                float py, float q, float radius, bool live,
+                                                const FieldParams P, WarpShared& ws,
+                                                uint32_t& nodes_out) {
+  using A = Arith<PARITY>;
+  const uint32_t FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const uint32_t lt = (1u << lane) - 1u;
+  float ax = 0.0f, ay = 0.0f;
+  nodes_out = 0;
+  const uint32_t live_mask = __ballot_sync(FULL, live);
+  if (live_mask == 0 || M == 0) return make_float2(0.f, 0.f);
+  // bounding box and radius range of the live targets
+  const float INF = __int_as_float(0x7f800000);
+  float bx0 = live ? px : INF, bx1 = live ? px : -INF, by0 = live ? py : INF, by1 = live ? py : -INF;
+  float rmin = live ? radius : INF, rmax = live ? radius : -INF;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    bx0 = fminf(bx0, __shfl_xor_sync(FULL, bx0, off));
+    bx1 = fmaxf(bx1, __shfl_xor_sync(FULL, bx1, off));
+    by0 = fminf(by0, __shfl_xor_sync(FULL, by0, off));
+    by1 = fmaxf(by1, __shfl_xor_sync(FULL, by1, off));
+    rmin = fminf(rmin, __shfl_xor_sync(FULL, rmin, off));
+    rmax = fmaxf(rmax, __shfl_xor_sync(FULL, rmax, off));
+  }
+  // a target with a NaN / infinite coordinate or radius makes every box test meaningless: such a
+  // group takes the exact test everywhere
+  const bool finite_me = !live || (fabsf(px) < INF && fabsf(py) < INF && fabsf(radius) < INF);
+  const bool box_ok = __all_sync(FULL, finite_me);
+  const float kq = A::mul(P.k_e, q);
+  const float my_lim_r = radius;
+  if (lane == 0) ws.st_node[0] = 0, ws.st_pend[0] = M, ws.st_mask[0] = live_mask;
+  __syncwarp();
+  // pending nodes: a ring buffer served first-in-first-out (wide rounds); when it is nearly full the
+  // walk switches to last-in-first-out, one node per round, which bounds the growth by the depth
+  int head = 0, size = 1;
+  uint32_t visited = 0;
+  while (size > 0) {
+    const bool lifo = size > kStackCap - 104;
+    const int k = lifo ? 1 : (size < 32 ? size : 32);
+    const bool has = lane < k;
+    uint32_t node = 0, pend = 0, mask = 0;
+    if (has) {
+      int idx = lifo ? head + size - 1 : head + lane;
+      if (idx >= kStackCap) idx -= kStackCap;
+      node = ws.st_node[idx], pend = ws.st_pend[idx], mask = ws.st_mask[idx];
+    }
+    __syncwarp();
+    if (!lifo) {
+      head += k;
+      if (head >= kStackCap) head -= kStackCap;
+    }
+    size -= k;
+    visited += k;
+    float4 na = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint4 nb = make_uint4(0, 0, 0, 0);
+    bool leaf = false;
+    int cls = 2;  // 0 ambiguous, 1 every target accepts, 2 every target rejects
+    if (has) {
+      na = __ldg(&nodeA[node]);
+      nb = __ldg(&nodeB[node]);
+      leaf = (nb.w & kNodeLeaf) != 0;
+      cls = 0;
+      if (box_ok) {
+        const float s_t = na.w * P.inv_theta;
+        const float ddx = fmaxf(fmaxf(bx0 - na.x, na.x - bx1), 0.0f);
+        const float ddy = fmaxf(fmaxf(by0 - na.y, na.y - by1), 0.0f);
+        const float fx = fmaxf(na.x - bx0, bx1 - na.x), fy = fmaxf(na.y - by0, by1 - na.y);
+        const float dmin2 = ddx * ddx + ddy * ddy, dmax2 = fx * fx + fy * fy;
+        const float la = s_t + rmax, lr = s_t + rmin;
+        if (dmin2 > la * la * 1.00002f) cls = 1;
+        else if (dmax2 < lr * lr * 0.99998f) cls = 2;
+      }
+    }
+    // every node that some target may accept: each lane applies the reference's opening test with its
+    // own position and radius (quadtree.rs:361-371) and, if it accepts, adds the monopole (:372-375)
+    uint32_t acc_mask = (has && cls == 1 && na.z == 0.0f) ? mask : 0u;  // charge 0: adds exactly +-0
+    uint32_t todo = __ballot_sync(FULL, has && cls != 2 && !(cls == 1 && na.z == 0.0f));
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const float nx = __shfl_sync(FULL, na.x, src), ny = __shfl_sync(FULL, na.y, src);
+      const float nq = __shfl_sync(FULL, na.z, src), ns = __shfl_sync(FULL, na.w, src);
+      const uint32_t m = __shfl_sync(FULL, mask, src);
+      const int c = __shfl_sync(FULL, cls, src);
+      const float dx = A::sub(px, nx), dy = A::sub(py, ny);
+      const float d_sq = A::add(A::mul(dx, dx), A::mul(dy, dy));
+      bool acc = ((m >> lane) & 1u) != 0;
+      float dist = 0.0f;
+      bool have_dist = false;
+      if (c != 1 && acc) {
+        const float lim = ns * P.inv_theta + my_lim_r;
+        const float lim2 = lim * lim;
+        if (d_sq > lim2 * 1.00002f) {
+          acc = true;
+        } else if (d_sq < lim2 * 0.99998f) {
+          acc = false;
+        } else {
+          dist = A::sqrt(d_sq);
+          have_dist = true;
+          const float dist_adj = fmaxf(A::sub(dist, radius), 0.0f);
+          acc = A::mul(ns, ns) < A::mul(A::mul(dist_adj, dist_adj), P.t_sq);
+        }
+      }
+      const uint32_t am = __ballot_sync(FULL, acc);
+      if (lane == src) acc_mask = am;
+      if (acc && nq != 0.0f) {
+        if (!have_dist) dist = A::sqrt(d_sq);
+        const float r_eff = fmaxf(dist, A::add(radius, A::mul(ns, 0.5f)));
+        const float denom = A::mul(A::add(A::mul(r_eff, r_eff), P.e_sq), r_eff);
+        const float s = A::div(A::mul(kq, nq), denom);
+        ax = A::add(ax, A::mul(dx, s));
+        ay = A::add(ay, A::mul(dy, s));
+      }
+    }
+    const uint32_t rem = mask & ~acc_mask;
+    const bool push_sib = has && nb.x < pend;
+    const bool push_child = has && rem != 0 && !leaf;
+    const uint32_t bs = __ballot_sync(FULL, push_sib), bc = __ballot_sync(FULL, push_child);
+    int off = head + size + __popc(bs & lt) + __popc(bc & lt);
+    if (off >= kStackCap) off -= kStackCap;
+    if (push_sib) ws.st_node[off] = nb.x, ws.st_pend[off] = pend, ws.st_mask[off] = mask;
+    if (push_child) {
+      int o2 = off + (push_sib ? 1 : 0);
+      if (o2 >= kStackCap) o2 -= kStackCap;
+      ws.st_node[o2] = node + 1, ws.st_pend[o2] = nb.x, ws.st_mask[o2] = rem;
+    }
+    size += __popc(bs) + __popc(bc);
+    __syncwarp();
+    // direct terms of this round (quadtree.rs:381-395)
+    uint32_t nm = __ballot_sync(FULL, has && rem != 0 && leaf);
+    while (nm) {
+      const int src = __ffs(nm) - 1;
+      nm &= nm - 1;
+      const uint32_t b0 = __shfl_sync(FULL, nb.y, src), bn = __shfl_sync(FULL, nb.z, src);
+      const uint32_t m = __shfl_sync(FULL, rem, src);
+      if ((m >> lane) & 1u) {
+        for (uint32_t b = b0; b < b0 + bn; ++b) {
+          const float4 s4 = __ldg(&pqr[b]);
+          if (s4.z == 0.0f) continue;  // adds exactly +-0
+          const float ex = A::sub(s4.x, px), ey = A::sub(s4.y, py);
+          if (A::add(A::mul(ex, ex), A::mul(ey, ey)) < 1e-6f) continue;  // positional self skip
+          const float bx = A::sub(px, s4.x), by = A::sub(py, s4.y);
+          const float bd = A::sqrt(A::add(A::mul(bx, bx), A::mul(by, by)));
+          const float r_eff = fmaxf(bd, A::add(radius, s4.w));
+          const float denom = A::mul(A::add(A::mul(r_eff, r_eff), P.e_sq), r_eff);
+          const float s = fminf(A::div(A::mul(kq, s4.z), denom), 3.402823466e+38f);
+          ax = A::add(ax, A::mul(bx, s));
+          ay = A::add(ay, A::mul(by, s));
+        }
+      }
+    }
+  }
+  nodes_out = visited;
+  return make_float2(ax, ay);
+}
+
+template <bool PARITY>
+__global__ void __launch_bounds__(128)
+    bh_group_bodies_kernel(const float4* __restrict__ nodeA, const uint4* __restrict__ nodeB,
+                           const uint32_t* __restrict__ num_nodes, const float4* __restrict__ pqr,
+                           const float4* __restrict__ acc_mass, uint32_t first, uint32_t n,
+                           FieldParams P, float2* __restrict__ e_field,
+                           float4* __restrict__ acc_mass_out, int write_acc,
+                           unsigned long long* __restrict__ step_counter) {
+  __shared__ WarpShared ws[4];
+  const uint32_t M = *num_nodes;
+  const uint32_t g = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t i = first + g * 32 + lane;
+  const bool live = g * 32 + lane < n;
+  float4 me = make_float4(0, 0, 0, 0);
+  if (live) me = pqr[i];
+  uint32_t visited;
+  float2 e = bh_group_walk<PARITY>(nodeA, nodeB, pqr, M, me.x, me.y, 1.0f, me.w, live, P,
+                                   ws[threadIdx.x >> 5], visited);
+  if (live) {
+    e.x = __fadd_rn(e.x, P.bg_x);
+    e.y = __fadd_rn(e.y, P.bg_y);
+    e_field[i] = e;
+    if (write_acc) {
+      float4 am = acc_mass[i];
+      am.x = __fdiv_rn(__fmul_rn(me.z, e.x), am.w);
+      am.y = __fdiv_rn(__fmul_rn(me.z, e.y), am.w);
+      acc_mass_out[i] = am;
+    }
+  }
+  if (step_counter && lane == 0 && visited) atomicAdd(step_counter, (unsigned long long)visited);
+}
+
+template <bool PARITY>
+__global__ void __launch_bounds__(128)
+    bh_group_points_kernel(const float4* __restrict__ nodeA, const uint4* __restrict__ nodeB,
+                           const uint32_t* __restrict__ num_nodes, const float4* __restrict__ pqr,
+                           const float2* __restrict__ pts, const float* __restrict__ q,
+                           const float* __restrict__ radius, uint32_t first, uint32_t m, FieldParams P,
+                           float2* __restrict__ out, unsigned long long* __restrict__ step_counter) {
+  __shared__ WarpShared ws[4];
+  const uint32_t M = *num_nodes;
+  const uint32_t g = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t i = first + g * 32 + lane;
+  const bool live = g * 32 + lane < m;
+  float2 p = make_float2(0, 0);
+  float qq = 1.0f, rr = 0.0f;
+  if (live) {
+    p = pts[i];
+    if (q) qq = q[i];
+    if (radius) rr = radius[i];
+  }
+  uint32_t visited;
+  const float2 e = bh_group_walk<PARITY>(nodeA, nodeB, pqr, M, p.x, p.y, qq, rr, live, P,
+                                         ws[threadIdx.x >> 5], visited);
+  if (live) out[i] = e;
+  if (step_counter && lane == 0 && visited) atomicAdd(step_counter, (unsigned long long)visited);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -186,6 +186,35 @@ __global__ void __launch_bounds__(128)
     aggregate_node(t.level_nodes[k], root_size, pqr, accm, t);
 }
 
+// Traversal arrays: the nodes that can contribute to a field sum, i.e. those with a charged body
+// below them, compacted in pre-order (skip pointers remapped).  A node without charge adds exactly
+// +-0 to every acc_pos sum whatever the opening test says, so the reference's result is unchanged.
+struct ChargedFlagFn {
+  const uint4* nodeB;
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
+    return (nodeB[i].w & kNodeCharged) ? 1u : 0u;
+  }
+};
+
+__global__ void __launch_bounds__(256)
+    compact_traversal_kernel(const TreeMeta* __restrict__ meta, const float4* __restrict__ nodeA,
+                             const uint4* __restrict__ nodeB, const uint32_t* __restrict__ rank,
+                             const uint32_t* __restrict__ total, uint32_t node_cap,
+                             float4* __restrict__ travA, uint4* __restrict__ travB) {
+  const uint32_t M = meta->num_nodes;
+  if (M > node_cap) return;
+  const uint32_t T = *total;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < M; n += stride) {
+    uint4 nb = nodeB[n];
+    if (!(nb.w & kNodeCharged)) continue;
+    const uint32_t r = rank[n];
+    nb.x = nb.x < M ? rank[nb.x] : T;
+    travA[r] = nodeA[n];
+    travB[r] = nb;
+  }
+}
+
 struct InternalFlagFn {
   const uint4* nodeB;
   __device__ __forceinline__ uint32_t operator()(uint32_t i) const {

@@ -148,6 +148,8 @@ PSIM_HD void emit_nodes_for_body(const uint64_t* keys, uint32_t n, uint32_t i, u
     if (d == ell) {
       const bool agg = leaf_is_aggregated(count, leaf_capacity, thread_capacity);
       float tm = 0.0f, tq = 0.0f, wx = 0.0f, wy = 0.0f;
+      bool charged = false;
+      for (uint32_t b = i; b < j; ++b) charged = charged || (pqr[b].z != 0.0f);
       if (agg) {
         for (uint32_t b = i; b < j; ++b) {
           const float4 p = pqr[b];
@@ -166,7 +168,8 @@ PSIM_HD void emit_nodes_for_body(const uint64_t* keys, uint32_t n, uint32_t i, u
       if (count > 1 && d == dcap) sink.cap_leaf();
       t.nodeA[node] = make_float4(wx, wy, tq, size);
       t.node_mass[node] = tm;
-      t.nodeB[node] = make_uint4(next, i, count, (uint32_t)d | kNodeLeaf | (agg ? 0u : kNodeZeroAgg));
+      t.nodeB[node] = make_uint4(next, i, count, (uint32_t)d | kNodeLeaf | (agg ? 0u : kNodeZeroAgg) |
+                                                     (charged ? kNodeCharged : 0u));
     } else {
       t.nodeB[node] = make_uint4(next, i, count, (uint32_t)d);
       t.level_nodes[sink.level_slot(d)] = node;
@@ -207,6 +210,7 @@ PSIM_HD void aggregate_node(uint32_t node, float root_size, const float4* pqr, c
     c = cb.x;
   }
   t.sums[node] = s;
+  if (s.aq > 0.0) t.nodeB[node].w = nb.w | kNodeCharged;
   float px, py;
   if (s.aq > (double)1e-6f) {
     px = (float)(s.aqx / s.aq), py = (float)(s.aqy / s.aq);

@@ -171,3 +171,52 @@ def test_attract_epilogue(cuda_device):
     assert rel_l2(sim.bodies.e_field, ob["e_field"]) <= TOL
     assert rel_l2(sim.bodies.acc, ob["acc"]) <= TOL
     sim.close()
+
+
+def test_reference_order_mode_is_bit_identical(cuda_device):
+    """parity_mode 2: one-node-per-step walk that adds every term in acc_pos's order: bit-identical to
+    the f64-centre oracle and to the reference-order oracle traversing the device's centres"""
+    for gen, mode, theta in [(lambda: uniform_pm1(30_000), 0, 0.5), (lambda: electrolyte(30_000), 1, 1.0)]:
+        bodies = gen()
+        sim = make_sim(bodies, theta=theta, parity_mode=2)
+        if mode == 0:
+            sim.quadtree.build(sim.bodies)
+        else:
+            sim.quadtree.build_with_domain(sim.bodies, bodies["hw"], bodies["hh"])
+        sim.quadtree.field(sim.bodies, KE)
+        o = oracle_for(bodies, theta=theta, variant="hp")
+        o.build() if mode == 0 else o.build_with_domain(bodies["hw"], bodies["hh"])
+        e, _ = o.field(KE)
+        assert np.array_equal(sim.bodies.e_field, e)
+        s = oracle_for(bodies, theta=theta)
+        s.build() if mode == 0 else s.build_with_domain(bodies["hw"], bodies["hh"])
+        s.set_canonical_pos(canonical_from_nodes(sim.quadtree.nodes)["pos"])
+        e2, _ = s.field(KE)
+        assert np.array_equal(sim.bodies.e_field, e2)
+        sim.close()
+
+
+def test_fast_math_mode_within_tolerance(cuda_device):
+    bodies = electrolyte(40_000)
+    sim = make_sim(bodies, parity_mode=0)
+    sim.quadtree.build(sim.bodies)
+    sim.quadtree.field(sim.bodies, KE)
+    o = oracle_for(bodies, variant="hp")
+    o.build()
+    e, _ = o.field(KE)
+    assert rel_l2(sim.bodies.e_field, e) <= TOL
+    sim.close()
+
+
+def test_nonfinite_target_does_not_hang(cuda_device):
+    bodies = electrolyte(5_000)
+    sim = make_sim(bodies)
+    sim.quadtree.build(sim.bodies)
+    pts = np.array([[np.nan, 0.0], [np.inf, 1.0], [0.0, 0.0]], np.float32)
+    f = sim.quadtree.field_at_point(sim.bodies, pts, KE)
+    o = oracle_for(bodies, variant="hp")
+    o.build()
+    fo, _ = o.acc_points(pts, k_e=KE)
+    assert np.allclose(f[2], fo[2], rtol=1e-5, atol=1e-9)
+    assert not np.all(np.isfinite(f[0]))
+    sim.close()
