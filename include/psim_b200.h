@@ -147,6 +147,10 @@ int32_t psim_download_electrons(psim_ctx *ctx, uint32_t *body, float *rel_xy, fl
 /* Quadtree::build (mode 0) / build_with_domain(hw, hh) (mode 1): quadtree.rs:153-195.
  * Morton keys -> onesweep sort -> tree construction -> bottom-up aggregation.  Permutes bodies. */
 int32_t psim_build(psim_ctx *ctx, int32_t mode, float hw, float hh);
+/* same launches without the final host synchronisation / arena-overflow check (psim_stats_get or
+ * psim_sync + psim_build_status report it later); for callers that chain phases on the stream */
+int32_t psim_build_async(psim_ctx *ctx, int32_t mode, float hw, float hh);
+int32_t psim_build_status(psim_ctx *ctx);
 /* out[i] = position, before the last psim_build, of the body now at i */
 int32_t psim_get_permutation(psim_ctx *ctx, uint32_t *out);
 /* 32-level quadrant keys of the bodies in current (sorted) order */
@@ -215,6 +219,22 @@ int32_t psim_step(psim_ctx *ctx, const psim_step_params *p);
  * [4] iterate  [5] quadtree_build_domain  [6] electron_updates  [7] whole step */
 #define PSIM_NUM_PHASES 8
 int32_t psim_phase_times(psim_ctx *ctx, float *ms8);
+
+/* ---- multi-GPU (one context per rank) ----------------------------------------------------------
+ * Every rank holds the whole body set and builds the same tree (deterministic sort => identical
+ * order on every rank); rank r OWNS a contiguous range of the sorted (Morton) order and computes
+ * field / short-range / integrator only for it, and a contiguous range of the electrons.  After the
+ * integrator and after the electron update the owned slices are exchanged with an NCCL all-gather
+ * issued by the caller (particlesim_b200/parallel.py) directly on the device arrays below. */
+int32_t psim_set_target_range(psim_ctx *ctx, uint64_t first, uint64_t count);
+int32_t psim_set_electron_range(psim_ctx *ctx, uint64_t first, uint64_t count);
+/* out[0..5] = device addresses of the CURRENT body / electron arrays (they swap at every psim_build):
+ * pos_charge_radius (float4 per body: x, y, charge, radius), vel_z_vz (float4), acc_mass (float4),
+ * e_field (float2), electron rel_pos (float2), electron vel (float2); out[6] = body capacity,
+ * out[7] = electron capacity */
+int32_t psim_device_ptrs(psim_ctx *ctx, uint64_t *out8);
+/* the caller wrote positions into the device arrays (e.g. an all-gather): tree and grid are stale */
+int32_t psim_mark_positions_changed(psim_ctx *ctx);
 
 #ifdef __cplusplus
 }

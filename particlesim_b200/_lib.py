@@ -91,6 +91,8 @@ SIGNATURES = {
     "psim_download_bodies": (_i32, [_vp] + [_vp] * 12),
     "psim_download_electrons": (_i32, [_vp, _vp, _vp, _vp]),
     "psim_build": (_i32, [_vp, _i32, _f, _f]),
+    "psim_build_async": (_i32, [_vp, _i32, _f, _f]),
+    "psim_build_status": (_i32, [_vp]),
     "psim_get_permutation": (_i32, [_vp, _vp]),
     "psim_get_keys": (_i32, [_vp, _vp]),
     "psim_download_nodes": (_i32, [_vp, _vp, _u64, C.POINTER(_u64)]),
@@ -107,6 +109,10 @@ SIGNATURES = {
     "psim_iterate": (_i32, [_vp, _f, _f, _f, _f, _f, _i32]),
     "psim_step": (_i32, [_vp, _vp]),
     "psim_phase_times": (_i32, [_vp, _vp]),
+    "psim_set_target_range": (_i32, [_vp, _u64, _u64]),
+    "psim_set_electron_range": (_i32, [_vp, _u64, _u64]),
+    "psim_device_ptrs": (_i32, [_vp, _vp]),
+    "psim_mark_positions_changed": (_i32, [_vp]),
 }
 
 _LIB = None

@@ -105,6 +105,9 @@ struct psim_ctx {
 
   unsigned long long* step_counter = nullptr;
   uint64_t launches = 0;
+  // multi-GPU: the slice of bodies / electrons this rank computes (default: everything)
+  bool tgt_set = false, etgt_set = false;
+  uint32_t tgt_first = 0, tgt_count = 0, e_first = 0, e_count = 0;
   cudaEvent_t ev[9] = {};
   bool ev_ok = false, ev_recorded = false;
 };
@@ -319,6 +322,21 @@ int32_t ensure_qstage(psim_ctx* ctx, size_t bytes) {
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+void body_range(const psim_ctx* ctx, uint32_t& first, uint32_t& count) {
+  first = 0, count = ctx->n;
+  if (ctx->tgt_set) {
+    first = ctx->tgt_first < ctx->n ? ctx->tgt_first : ctx->n;
+    count = ctx->tgt_count < ctx->n - first ? ctx->tgt_count : ctx->n - first;
+  }
+}
+void electron_range(const psim_ctx* ctx, uint32_t& first, uint32_t& count) {
+  first = 0, count = ctx->m;
+  if (ctx->etgt_set) {
+    first = ctx->e_first < ctx->m ? ctx->e_first : ctx->m;
+    count = ctx->e_count < ctx->m - first ? ctx->e_count : ctx->m - first;
+  }
+}
+
 FieldParams field_params(const psim_ctx* ctx, float k_e, float bg_x, float bg_y) {
   FieldParams P;
   P.t_sq = ctx->cfg.theta * ctx->cfg.theta;      // Quadtree::new, quadtree.rs:26-27
@@ -531,7 +549,10 @@ int32_t field_async(psim_ctx* ctx, float k_e, float bg_x, float bg_y, int write_
   if (n == 0) return PSIM_OK;
   BodyArrays& b = ctx->b[ctx->cur];
   const FieldParams P = field_params(ctx, k_e, bg_x, bg_y);
-  const uint32_t groups = (n + 31) / 32;
+  uint32_t first, count;
+  body_range(ctx, first, count);
+  if (count == 0) return PSIM_OK;
+  const uint32_t groups = ((ctx->cfg.parity_mode == 2 ? n : count) + 31) / 32;
   if (ctx->cfg.parity_mode == 2) {
     // reference-order walk: bit-identical additions, one node per warp step, on the full tree
     const int blocks = (int)((groups + 3) / 4);
@@ -542,11 +563,11 @@ int32_t field_async(psim_ctx* ctx, float k_e, float bg_x, float bg_y, int write_
     const int blocks = (int)((groups + 3) / 4);  // one group per warp, launched in Morton order
     if (ctx->cfg.parity_mode)
       bh_group_bodies_kernel<true><<<blocks, 128, 0, ctx->stream>>>(
-          ctx->travA, ctx->travB, ctx->trav_count, b.pqr, b.accm, 0, n, P, b.efield, b.accm, write_acc,
+          ctx->travA, ctx->travB, ctx->trav_count, b.pqr, b.accm, first, count, P, b.efield, b.accm, write_acc,
           ctx->step_counter);
     else
       bh_group_bodies_kernel<false><<<blocks, 128, 0, ctx->stream>>>(
-          ctx->travA, ctx->travB, ctx->trav_count, b.pqr, b.accm, 0, n, P, b.efield, b.accm, write_acc,
+          ctx->travA, ctx->travB, ctx->trav_count, b.pqr, b.accm, first, count, P, b.efield, b.accm, write_acc,
           ctx->step_counter);
   }
   LAUNCHED(ctx);
@@ -554,7 +575,7 @@ int32_t field_async(psim_ctx* ctx, float k_e, float bg_x, float bg_y, int write_
 }
 
 int32_t points_async(psim_ctx* ctx, const float2* pts, const float* q, const float* radius, uint32_t m,
-                     float k_e, float2* out) {
+                     float k_e, float2* out, uint32_t first = 0) {
   if (!ctx->tree_valid) return fail(ctx, PSIM_E_STATE, "acc_pos: no tree (call psim_build first)");
   if (m == 0) return PSIM_OK;
   BodyArrays& b = ctx->b[ctx->cur];
@@ -563,31 +584,35 @@ int32_t points_async(psim_ctx* ctx, const float2* pts, const float* q, const flo
   const int blocks = (int)((groups + 3) / 4);
   if (ctx->cfg.parity_mode == 2)
     bh_field_points_kernel<true><<<blocks, 128, 0, ctx->stream>>>(
-        ctx->meta, ctx->t.nodeA, ctx->t.nodeB, b.pqr, pts, q, radius, m, P, out, ctx->step_counter);
+        ctx->meta, ctx->t.nodeA, ctx->t.nodeB, b.pqr, pts + first, q ? q + first : nullptr,
+        radius ? radius + first : nullptr, m, P, out + first, ctx->step_counter);
   else if (ctx->cfg.parity_mode)
     bh_group_points_kernel<true><<<blocks, 128, 0, ctx->stream>>>(
-        ctx->travA, ctx->travB, ctx->trav_count, b.pqr, pts, q, radius, 0, m, P, out, ctx->step_counter);
+        ctx->travA, ctx->travB, ctx->trav_count, b.pqr, pts, q, radius, first, m, P, out, ctx->step_counter);
   else
     bh_group_points_kernel<false><<<blocks, 128, 0, ctx->stream>>>(
-        ctx->travA, ctx->travB, ctx->trav_count, b.pqr, pts, q, radius, 0, m, P, out, ctx->step_counter);
+        ctx->travA, ctx->travB, ctx->trav_count, b.pqr, pts, q, radius, first, m, P, out, ctx->step_counter);
   LAUNCHED(ctx);
   return PSIM_OK;
 }
 
 int32_t electrons_async(psim_ctx* ctx, float bg_x, float bg_y, float dt, float k_e) {
-  const uint32_t m = ctx->m;
-  if (m == 0) return PSIM_OK;
+  if (ctx->m == 0) return PSIM_OK;
   if (!ctx->tree_valid) return fail(ctx, PSIM_E_STATE, "psim_update_electrons: no tree");
+  uint32_t first, m;
+  electron_range(ctx, first, m);
+  if (m == 0) return PSIM_OK;
   BodyArrays& b = ctx->b[ctx->cur];
   const int e = ctx->ecur;
-  electron_points_kernel<<<grid_for(ctx, m, 256, 16), 256, 0, ctx->stream>>>(b.pqr, ctx->ebody[e], ctx->erel[e], m, ctx->epts);
+  electron_points_kernel<<<grid_for(ctx, m, 256, 16), 256, 0, ctx->stream>>>(
+      b.pqr, ctx->ebody[e] + first, ctx->erel[e] + first, m, ctx->epts + first);
   LAUNCHED(ctx);
-  int32_t rc = points_async(ctx, ctx->epts, nullptr, nullptr, m, k_e, ctx->efld);
+  int32_t rc = points_async(ctx, ctx->epts, nullptr, nullptr, m, k_e, ctx->efld, first);
   if (rc) return rc;
   // config.rs:6-9,27-35: electron_spring_k() is 5.0 for every species; config.rs:49
   electron_drift_kernel<<<grid_for(ctx, m, 256, 16), 256, 0, ctx->stream>>>(
-      b.pqr, b.species, ctx->table_d, ctx->ebody[e], ctx->erel[e], ctx->evel[e], ctx->efld, m, bg_x,
-      bg_y, dt, 5.0f, 10.2f);
+      b.pqr, b.species, ctx->table_d, ctx->ebody[e] + first, ctx->erel[e] + first, ctx->evel[e] + first,
+      ctx->efld + first, m, bg_x, bg_y, dt, 5.0f, 10.2f);
   LAUNCHED(ctx);
   return PSIM_OK;
 }
@@ -614,9 +639,12 @@ int32_t short_range_async(psim_ctx* ctx, uint32_t flags) {
   P.range = (P.do_lj || P.do_rep) ? (int)ceilf(reach / ctx->grid.cell_size) : 0;
   if (P.range < 0) P.range = 0;
   BodyArrays& b = ctx->b[ctx->cur];
-  short_range_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(
-      b.pqr, b.species, ctx->table_d, n, ctx->cell_start, ctx->cell_end, ctx->order, ctx->body_cell, P,
-      b.accm);
+  uint32_t first, count;
+  body_range(ctx, first, count);
+  if (count == 0) return PSIM_OK;
+  short_range_kernel<<<(count + 127) / 128, 128, 0, ctx->stream>>>(
+      b.pqr, b.species, ctx->table_d, first, first + count, ctx->cell_start, ctx->cell_end, ctx->order,
+      ctx->body_cell, P, b.accm);
   LAUNCHED(ctx);
   return PSIM_OK;
 }
@@ -629,7 +657,11 @@ int32_t iterate_async(psim_ctx* ctx, float dt, float damping_base, float hw, flo
   P.base_damping = powf(damping_base, dt / 0.01f);  // simulation.rs:1441
   P.hw = hw, P.hh = hh, P.hd = hd, P.enable_z = enable_z;
   BodyArrays& b = ctx->b[ctx->cur];
-  iterate_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, ctx->stream>>>(b.pqr, b.velz, b.accm, b.species, ctx->table_d, n, P);
+  uint32_t first, count;
+  body_range(ctx, first, count);
+  if (count)
+    iterate_kernel<<<grid_for(ctx, count, 256, 16), 256, 0, ctx->stream>>>(
+        b.pqr + first, b.velz + first, b.accm + first, b.species + first, ctx->table_d, count, P);
   LAUNCHED(ctx);
   // positions moved: tree and grid no longer describe them
   ctx->tree_valid = false;
@@ -897,6 +929,7 @@ int32_t psim_upload_bodies(psim_ctx* ctx, uint64_t n, const float* pos_xy, const
   cudaStream_t st = ctx->stream;
   ctx->n = (uint32_t)n;
   ctx->m = 0;
+  ctx->tgt_set = ctx->etgt_set = false;
   ctx->tree_valid = ctx->grid_valid = ctx->perm_valid = false;
   if (n == 0) return PSIM_OK;
   // layout of the staging buffer: pos | vel | z | vz | mass | radius | charge | species
@@ -1049,6 +1082,20 @@ int32_t psim_build(psim_ctx* ctx, int32_t mode, float hw, float hh) {
   int32_t rc = build_async(ctx, mode, hw, hh);
   if (rc) return rc;
   CK(cudaGetLastError());
+  return check_build(ctx);
+}
+
+int32_t psim_build_async(psim_ctx* ctx, int32_t mode, float hw, float hh) {
+  if (!ctx) return PSIM_E_ARG;
+  if (mode != PSIM_BUILD_CONTAINING && mode != PSIM_BUILD_DOMAIN) return fail(ctx, PSIM_E_ARG, "psim_build: mode");
+  int32_t rc = build_async(ctx, mode, hw, hh);
+  if (rc) return rc;
+  CK(cudaGetLastError());
+  return PSIM_OK;
+}
+
+int32_t psim_build_status(psim_ctx* ctx) {
+  if (!ctx) return PSIM_E_ARG;
   return check_build(ctx);
 }
 
@@ -1301,6 +1348,31 @@ int32_t psim_step(psim_ctx* ctx, const psim_step_params* p) {
   mark(7);
   ctx->ev_recorded = ctx->ev_ok;
   CK(cudaGetLastError());
+  return PSIM_OK;
+}
+
+int32_t psim_set_target_range(psim_ctx* ctx, uint64_t first, uint64_t count) {
+  if (!ctx || first > ctx->n || count > ctx->n - first) return fail(ctx, PSIM_E_ARG, "psim_set_target_range: out of range");
+  ctx->tgt_set = true, ctx->tgt_first = (uint32_t)first, ctx->tgt_count = (uint32_t)count;
+  return PSIM_OK;
+}
+int32_t psim_set_electron_range(psim_ctx* ctx, uint64_t first, uint64_t count) {
+  if (!ctx || first > ctx->m || count > ctx->m - first) return fail(ctx, PSIM_E_ARG, "psim_set_electron_range: out of range");
+  ctx->etgt_set = true, ctx->e_first = (uint32_t)first, ctx->e_count = (uint32_t)count;
+  return PSIM_OK;
+}
+int32_t psim_device_ptrs(psim_ctx* ctx, uint64_t* out8) {
+  if (!ctx || !out8) return PSIM_E_ARG;
+  BodyArrays& b = ctx->b[ctx->cur];
+  out8[0] = (uint64_t)(uintptr_t)b.pqr, out8[1] = (uint64_t)(uintptr_t)b.velz, out8[2] = (uint64_t)(uintptr_t)b.accm;
+  out8[3] = (uint64_t)(uintptr_t)b.efield;
+  out8[4] = (uint64_t)(uintptr_t)ctx->erel[ctx->ecur], out8[5] = (uint64_t)(uintptr_t)ctx->evel[ctx->ecur];
+  out8[6] = ctx->cap_bodies, out8[7] = ctx->cap_elec;
+  return PSIM_OK;
+}
+int32_t psim_mark_positions_changed(psim_ctx* ctx) {
+  if (!ctx) return PSIM_E_ARG;
+  ctx->tree_valid = ctx->grid_valid = false;
   return PSIM_OK;
 }
 

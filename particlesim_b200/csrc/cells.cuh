@@ -143,7 +143,7 @@ __device__ __forceinline__ void rep_pair(const SpeciesRow& sa, const SpeciesRow&
 // that are in the same CTA (the common case for a compact patch) are read from there.
 __global__ void __launch_bounds__(128)
     short_range_kernel(const float4* __restrict__ pqr, const uint8_t* __restrict__ species,
-                       const SpeciesRow* __restrict__ table_g, uint32_t n,
+                       const SpeciesRow* __restrict__ table_g, uint32_t first, uint32_t n,
                        const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end,
                        const uint32_t* __restrict__ order, const uint32_t* __restrict__ body_cell,
                        ShortRangeParams P, float4* __restrict__ acc_mass) {
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(128)
   __shared__ uint8_t s_sp[128];
   for (int k = threadIdx.x; k < kMaxSpecies * (int)(sizeof(SpeciesRow) / 4); k += blockDim.x)
     reinterpret_cast<uint32_t*>(table)[k] = reinterpret_cast<const uint32_t*>(table_g)[k];
-  const uint32_t block_first = blockIdx.x * blockDim.x;
+  const uint32_t block_first = first + blockIdx.x * blockDim.x;  // bodies [first, n) of this rank
   const uint32_t i = block_first + threadIdx.x;
   float4 me = make_float4(0, 0, 0, 0);
   uint8_t my_sp = 0;

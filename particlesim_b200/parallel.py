@@ -1,0 +1,107 @@
+"""Multi-GPU hot path: one process per GPU (torch.distributed, NCCL over NVLink / NVSwitch).
+
+Every rank holds the whole body set and builds the same tree (the sort is deterministic, so all
+ranks see the same Morton order); rank r owns a CONTIGUOUS RANGE OF THE MORTON ORDER and computes
+field / short-range forces / integrator only for those targets, plus an equal slice of the bound
+electrons.  Two exchanges per step, both all-gathers issued straight on the library's device arrays:
+  after the integrator      positions+charges+radii and velocities of the owned range
+  after the electron update  electron offsets and velocities of the owned slice
+No force reduction is needed: a target's field depends only on the (replicated) source tree.
+The replicated build is the scaling limit of this scheme; a per-rank local build with a
+locally-essential-tree exchange replaces it next (multi-GPU).
+
+The partition helpers are pure functions so the plumbing is testable with the gloo backend on CPU.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+from .simulation import Simulation
+
+
+def shard_width(n: int, world: int) -> int:
+    """bodies per rank (the last rank may own fewer); arrays are padded to world * width"""
+    return (n + world - 1) // world if n else 0
+
+
+def shard_range(n: int, world: int, rank: int) -> tuple[int, int]:
+    """(first, count) of the slice of [0, n) that `rank` owns"""
+    w = shard_width(n, world)
+    first = min(rank * w, n)
+    return first, min(w, n - first)
+
+
+def all_gather_slices(full, width: int, rank: int, world: int, dist, scratch=None):
+    """In-place all-gather of equal slices of a (world * width, ...) tensor: rank r contributes rows
+    [r * width, (r + 1) * width).  Works for CUDA tensors over NCCL and CPU tensors over gloo."""
+    mine = full[rank * width:(rank + 1) * width]
+    if scratch is None:
+        scratch = mine.clone()
+    else:
+        scratch.copy_(mine)
+    dist.all_gather_into_tensor(full[:world * width], scratch)
+    return full
+
+
+class _DevArray:
+    """zero-copy view of library-owned device memory for torch (CUDA array interface v2)"""
+
+    def __init__(self, ptr: int, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class ShardedSimulation(Simulation):
+    def __init__(self, bodies, domain_width, domain_height, *, rank: int, world: int, **kw):
+        n, m = len(bodies), len(bodies.ebody)
+        self.rank, self.world = rank, world
+        self.wb, self.we = shard_width(n, world), shard_width(m, world)
+        kw["max_bodies"] = max(self.wb * world, 1)
+        kw["max_electrons"] = max(self.we * world, 1)
+        super().__init__(bodies, domain_width, domain_height, **kw)
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self._scratch_b = torch.empty((self.wb, 4), dtype=torch.float32, device="cuda")
+        self._scratch_e = torch.empty((self.we, 2), dtype=torch.float32, device="cuda")
+        f, c = shard_range(n, world, rank)
+        self._call("psim_set_target_range", f, c)
+        if m:
+            f, c = shard_range(m, world, rank)
+            self._call("psim_set_electron_range", f, c)
+
+    def _views(self):
+        p = np.zeros(8, np.uint64)
+        self._call("psim_device_ptrs", p.ctypes.data)
+        t = self.torch
+        nb, ne = self.wb * self.world, self.we * self.world
+        mk = lambda ptr, rows, cols: t.as_tensor(_DevArray(ptr, (rows, cols)), device="cuda")
+        return dict(pqr=mk(p[0], nb, 4), velz=mk(p[1], nb, 4), erel=mk(p[4], ne, 2) if ne else None,
+                    evel=mk(p[5], ne, 2) if ne else None)
+
+    def step_device(self, params=None):
+        """Simulation::step's hot path (simulation.rs:1000-1196), sharded"""
+        p = params or self.step_params()
+        C = self._call
+        C("psim_reset_acc")
+        C("psim_build_async", _lib.BUILD_CONTAINING, 0.0, 0.0)
+        cell = self.force_cell_size()
+        if p.do_short_range and cell > 0.0:
+            C("psim_cell_build", p.hw, p.hh, cell)
+        C("psim_field", p.k_e, p.bg_x, p.bg_y, 1, None, None)
+        if p.do_short_range:
+            C("psim_short_range", _lib.SR_LJ | _lib.SR_REPULSION | _lib.SR_STACK_PRESSURE)
+        if p.do_iterate:
+            C("psim_iterate", p.dt, p.damping_base, p.hw, p.hh, p.hd, int(p.enable_out_of_plane))
+            v = self._views()
+            all_gather_slices(v["pqr"], self.wb, self.rank, self.world, self.dist, self._scratch_b)
+            all_gather_slices(v["velz"], self.wb, self.rank, self.world, self.dist, self._scratch_b)
+            C("psim_mark_positions_changed")
+        if p.do_electrons:
+            C("psim_build_async", _lib.BUILD_DOMAIN, p.hw, p.hh)
+            C("psim_update_electrons", p.bg_x, p.bg_y, p.dt, p.k_e)
+            if self.we:
+                v = self._views()
+                all_gather_slices(v["erel"], self.we, self.rank, self.world, self.dist, self._scratch_e)
+                all_gather_slices(v["evel"], self.we, self.rank, self.world, self.dist, self._scratch_e)

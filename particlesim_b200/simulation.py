@@ -179,7 +179,8 @@ class Simulation:
 
     def __init__(self, bodies: Bodies, domain_width, domain_height, domain_depth=1.0, dt=5.0,
                  theta=1.0, epsilon=2.0, leaf_capacity=1, thread_capacity=1024, config: SimConfig | None = None,
-                 device=0, parity_mode=True, node_factor=4.0, species_table=None, max_bodies=None, stream=0):
+                 device=0, parity_mode=True, node_factor=4.0, species_table=None, max_bodies=None,
+                 max_electrons=None, stream=0):
         self.lib = _lib.load()
         self.bodies = bodies
         self.domain_width, self.domain_height, self.domain_depth = float(domain_width), float(domain_height), float(domain_depth)
@@ -199,7 +200,7 @@ class Simulation:
         self._cfg = cfg
         h = C.c_void_p()
         nmax = max(int(max_bodies or 0), len(bodies), 1)
-        emax = max(len(bodies.ebody), 1)
+        emax = max(int(max_electrons or 0), len(bodies.ebody), 1)
         rc = self.lib.psim_create(device, nmax, emax, C.byref(cfg), C.byref(h))
         if rc != 0:
             raise PsimError(rc, "psim_create failed (no CUDA device or out of memory); there is no CPU fallback")
@@ -277,6 +278,18 @@ class Simulation:
             self._call("psim_neighbors_within", m, _p(q), np.float32(cutoff), int(metals_only), _p(off), _p(ind),
                        tot.value, C.byref(tot))
         return [ind[off[k]:off[k + 1]].astype(np.int64) for k in range(m)]
+
+    def force_cell_size(self) -> float:
+        """forces.rs:17-22: max(3 * max_lj_cutoff, max_repulsion_cutoff, max_lj_cutoff)"""
+        t = self.species_table
+        lj = np.float32(0.0)
+        rep = np.float32(0.0)
+        for r in t:
+            if r["lj_enabled"]:
+                lj = max(lj, np.float32(r["lj_cutoff"]) * np.float32(r["lj_sigma"]))
+            if r["repulsion_enabled"]:
+                rep = max(rep, np.float32(r["repulsion_cutoff"]))
+        return float(max(np.float32(3.0) * lj, rep, lj))
 
     def stats(self) -> dict:
         st = _lib.Stats()

@@ -1,0 +1,61 @@
+"""torchrun --nproc-per-node G tools/check_sharded.py: the sharded step must give the single-GPU result."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from helpers import KE, electrolyte  # noqa: E402
+from particlesim_b200 import Bodies, Simulation  # noqa: E402
+from particlesim_b200.parallel import ShardedSimulation  # noqa: E402
+
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 200_001
+bd = electrolyte(n)
+bd["species"][: n // 10] = 1  # some LJ bodies
+
+
+def mk(cls, **kw):
+    b = Bodies(bd["pos"], vel=bd["vel"], mass=bd["mass"], radius=bd["radius"], charge=bd["charge"],
+               species=bd["species"], ebody=bd["ebody"], erel=bd["erel"])
+    s = cls(b, bd["hw"], bd["hh"], device=lr, stream=torch.cuda.current_stream().cuda_stream, **kw)
+    s.config.coulomb_constant = float(KE)
+    return s
+
+
+def state(sim):
+    nb, m = len(sim.bodies), len(sim.bodies.ebody)
+    pos, vel = np.zeros((nb, 2), np.float32), np.zeros((nb, 2), np.float32)
+    orig = np.zeros(nb, np.uint32)
+    sim._call("psim_download_bodies", pos.ctypes.data, None, vel.ctypes.data, None, None, None, None, None, None,
+              None, None, orig.ctypes.data)
+    eb, er, ev = np.zeros(m, np.uint32), np.zeros((m, 2), np.float32), np.zeros((m, 2), np.float32)
+    sim._call("psim_download_electrons", eb.ctypes.data, er.ctypes.data, ev.ctypes.data)
+    return pos, vel, orig, eb, er, ev
+
+
+sh = mk(ShardedSimulation, rank=rank, world=world)
+for _ in range(3):
+    sh.step_device()
+torch.cuda.synchronize()
+a = state(sh)
+if rank == 0:
+    one = mk(Simulation)
+    for _ in range(3):
+        one.step_device()
+    b = state(one)
+    names = ["pos", "vel", "orig", "ebody", "erel", "evel"]
+    ok = True
+    for nm, x, y in zip(names, a, b):
+        same = np.array_equal(x, y)
+        ok &= same
+        print(f"{nm}: identical={same}")
+    print("SHARDED == SINGLE:", ok, flush=True)
+dist.barrier()
+dist.destroy_process_group()
