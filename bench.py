@@ -6,7 +6,7 @@ A "step" = one pass of the hot path over the whole body set, in Simulation::step
 attract, LJ / repulsion / stack pressure, integrator, domain-bounded quadtree build, electron field
 sampling + drift.  Metric: Mparticles/s = bodies / step time (BASELINE.json).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--n BODIES] [--theta T]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--bodies BODIES] [--theta T]
   python bench.py --impl reference ...    # the C++ restatement of the reference's rayon path on the host cores
 
 Workload at N=1: BASELINE.json configs[3], "N=16M uniform electrolyte with electron polarization
@@ -234,9 +234,13 @@ def run_ours(args):
     acc = np.zeros(8, np.float64)
     reps = min(args.steps, 5)
     for _ in range(reps):
-        sim.step_device(params)
-        sim._call("psim_phase_times", ph.ctypes.data)
-        acc += ph
+        if world > 1:
+            sim.step_device(params, record=True)
+            acc += np.array(sim.phase_ms())
+        else:
+            sim.step_device(params)
+            sim._call("psim_phase_times", ph.ctypes.data)
+            acc += ph
     phase = {nm: float(v / reps) for nm, v in zip(PHASES, acc)}
 
     line = None
@@ -343,7 +347,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=16_000_000)
+    ap.add_argument("--bodies", dest="n", type=int, default=16_000_000)
     ap.add_argument("--theta", type=float, default=1.0)
     ap.add_argument("--fast", type=int, default=0, help="1: fast-math traversal instead of the reference-exact one")
     ap.add_argument("--cpu-n", type=int, default=1_000_000, help="bodies in the CPU-baseline sample")

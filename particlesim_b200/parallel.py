@@ -80,28 +80,57 @@ class ShardedSimulation(Simulation):
         return dict(pqr=mk(p[0], nb, 4), velz=mk(p[1], nb, 4), erel=mk(p[4], ne, 2) if ne else None,
                     evel=mk(p[5], ne, 2) if ne else None)
 
-    def step_device(self, params=None):
-        """Simulation::step's hot path (simulation.rs:1000-1196), sharded"""
+    def step_device(self, params=None, record=False):
+        """Simulation::step's hot path (simulation.rs:1000-1196), sharded.  record=True keeps CUDA events
+        at the phase boundaries (see phase_ms)."""
         p = params or self.step_params()
         C = self._call
+        ev = []
+
+        def mark():
+            if record:
+                e = self.torch.cuda.Event(enable_timing=True)
+                e.record()
+                ev.append(e)
+
+        mark()
         C("psim_reset_acc")
         C("psim_build_async", _lib.BUILD_CONTAINING, 0.0, 0.0)
+        mark()
         cell = self.force_cell_size()
         if p.do_short_range and cell > 0.0:
             C("psim_cell_build", p.hw, p.hh, cell)
+        mark()
         C("psim_field", p.k_e, p.bg_x, p.bg_y, 1, None, None)
+        mark()
         if p.do_short_range:
             C("psim_short_range", _lib.SR_LJ | _lib.SR_REPULSION | _lib.SR_STACK_PRESSURE)
+        mark()
         if p.do_iterate:
             C("psim_iterate", p.dt, p.damping_base, p.hw, p.hh, p.hd, int(p.enable_out_of_plane))
             v = self._views()
             all_gather_slices(v["pqr"], self.wb, self.rank, self.world, self.dist, self._scratch_b)
             all_gather_slices(v["velz"], self.wb, self.rank, self.world, self.dist, self._scratch_b)
             C("psim_mark_positions_changed")
+        mark()
         if p.do_electrons:
             C("psim_build_async", _lib.BUILD_DOMAIN, p.hw, p.hh)
+            mark()
             C("psim_update_electrons", p.bg_x, p.bg_y, p.dt, p.k_e)
             if self.we:
                 v = self._views()
                 all_gather_slices(v["erel"], self.we, self.rank, self.world, self.dist, self._scratch_e)
                 all_gather_slices(v["evel"], self.we, self.rank, self.world, self.dist, self._scratch_e)
+        else:
+            mark()
+        mark()
+        self._events = ev
+
+    def phase_ms(self):
+        """device ms of the phases of the last recorded step (same order as psim_phase_times; the two
+        exchanges are inside `iterate` and `electron_updates`)"""
+        ev = self._events
+        self.torch.cuda.synchronize()
+        out = [ev[k].elapsed_time(ev[k + 1]) for k in range(7)]
+        out.append(ev[0].elapsed_time(ev[7]))
+        return out
