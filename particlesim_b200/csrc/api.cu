@@ -478,11 +478,13 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
   // bottom-up sweeps, deepest level first; a level's node count is only known on the device, so
   // every launch is sized for the SMs and strides over the level's bucket
   for (int level = kMaxLevels - 1; level >= 0; --level) {
-    aggregate_level_kernel<<<ctx->sm_count * 16, 128, 0, st>>>(level, ctx->meta, b.pqr, b.accm, ctx->t);
+    aggregate_level_kernel<<<ctx->sm_count * 16, 128, 0, st>>>(level, ctx->meta, ctx->t);
     LAUNCHED(ctx);
   }
+  finalize_nodes_kernel<<<grid_for(ctx, (uint64_t)n * 2, 256, 16), 256, 0, st>>>(ctx->meta, b.pqr, b.accm, ctx->t);
+  LAUNCHED(ctx);
   // traversal arrays (charged nodes only)
-  CK(exclusive_scan_dyn(ChargedFlagFn{ctx->t.nodeB}, &ctx->meta->num_nodes, ctx->node_cap, ctx->trav_rank,
+  CK(exclusive_scan_dyn(ChargedFlagFn{ctx->t.rec}, &ctx->meta->num_nodes, ctx->node_cap, ctx->trav_rank,
                         ctx->scan_partials, ctx->trav_count, st));
   ctx->launches += 3;
   compact_traversal_kernel<<<grid_for(ctx, (uint64_t)n * 2, 256, 16), 256, 0, st>>>(
@@ -696,6 +698,7 @@ void free_all(psim_ctx* c) {
   F(c->sc.hist), F(c->sc.status), F(c->sc.ticket), F(c->tree_plan), F(c->cell_plan);
   F(c->meta), F(c->le), F(c->nodebase), F(c->scan_partials), F(c->irank), F(c->bounds_partial);
   F(c->t.nodeA), F(c->t.nodeB), F(c->t.node_mass), F(c->t.parent), F(c->t.sums), F(c->t.level_nodes);
+  F(c->t.rec), F(c->t.ndepth);
   F(c->travA), F(c->travB), F(c->trav_rank), F(c->trav_count);
   F(c->perm), F(c->inv);
   F(c->cell_start), F(c->cell_end), F(c->order), F(c->body_cell);
@@ -774,6 +777,7 @@ int32_t psim_create(int32_t device, uint64_t max_bodies, uint64_t max_electrons,
   A(&ctx->irank, ctx->node_cap), A(&ctx->bounds_partial, (size_t)ctx->sm_count * 4 + 1);
   A(&ctx->t.nodeA, ctx->node_cap), A(&ctx->t.nodeB, ctx->node_cap), A(&ctx->t.node_mass, ctx->node_cap);
   A(&ctx->t.parent, ctx->node_cap), A(&ctx->t.sums, ctx->node_cap), A(&ctx->t.level_nodes, ctx->node_cap);
+  A(&ctx->t.rec, ctx->node_cap), A(&ctx->t.ndepth, ctx->node_cap);
   A(&ctx->travA, ctx->node_cap), A(&ctx->travB, ctx->node_cap), A(&ctx->trav_rank, ctx->node_cap), A(&ctx->trav_count, 1);
   ctx->t.node_cap = ctx->node_cap;
   A(&ctx->perm, nb), A(&ctx->inv, nb);
@@ -1130,6 +1134,16 @@ int32_t psim_download_nodes(psim_ctx* ctx, psim_node* out, uint64_t cap, uint64_
   if (count) *count = total;
   if (!out || cap == 0) return PSIM_OK;
   cudaStream_t st = ctx->stream;
+  {
+    // export sweep: parent links, node masses, body counts, centres of chargeless nodes
+    BodyArrays& b = ctx->b[ctx->cur];
+    export_root_leaf_kernel<<<1, 32, 0, st>>>(ctx->meta, b.accm, ctx->t);
+    LAUNCHED(ctx);
+    for (int level = kMaxLevels - 1; level >= 0; --level) {
+      export_level_kernel<<<ctx->sm_count * 8, 128, 0, st>>>(level, ctx->meta, b.pqr, b.accm, ctx->t);
+      LAUNCHED(ctx);
+    }
+  }
   CK(exclusive_scan(InternalFlagFn{ctx->t.nodeB}, M, ctx->irank, ctx->scan_partials, nullptr, st));
   ctx->launches += 3;
   const uint64_t ncopy = total < cap ? total : cap;

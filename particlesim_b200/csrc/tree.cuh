@@ -172,11 +172,33 @@ __global__ void __launch_bounds__(128)
                         root_size, dcap, t, sink);
 }
 
-// one level of the bottom-up sweep (deepest level first)
+// one level of the build's bottom-up sweep (deepest level first)
 __global__ void __launch_bounds__(128)
-    aggregate_level_kernel(int level, const TreeMeta* __restrict__ meta,
-                           const float4* __restrict__ pqr, const float4* __restrict__ accm,
-                           TreeArrays t) {
+    aggregate_level_kernel(int level, const TreeMeta* __restrict__ meta, TreeArrays t) {
+  const uint32_t M = meta->num_nodes;
+  if (M > t.node_cap) return;
+  const uint32_t begin = meta->level_start[level], end = meta->level_start[level + 1];
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t k = begin + blockIdx.x * blockDim.x + threadIdx.x; k < end; k += stride)
+    aggregate_node_lean(t.level_nodes[k], level, M, t);
+}
+
+__global__ void __launch_bounds__(256)
+    finalize_nodes_kernel(const TreeMeta* __restrict__ meta, const float4* __restrict__ pqr,
+                          const float4* __restrict__ accm, TreeArrays t) {
+  const uint32_t M = meta->num_nodes;
+  if (M > t.node_cap) return;
+  const float root_size = meta->root.size;
+  const uint32_t n_bodies = meta->n;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t node = blockIdx.x * blockDim.x + threadIdx.x; node < M; node += stride)
+    finalize_node(node, M, n_bodies, root_size, pqr, accm, t);
+}
+
+// one level of the export sweep (psim_download_nodes only)
+__global__ void __launch_bounds__(128)
+    export_level_kernel(int level, const TreeMeta* __restrict__ meta, const float4* __restrict__ pqr,
+                        const float4* __restrict__ accm, TreeArrays t) {
   const uint32_t M = meta->num_nodes;
   if (M > t.node_cap) return;
   const uint32_t begin = meta->level_start[level], end = meta->level_start[level + 1];
@@ -186,14 +208,26 @@ __global__ void __launch_bounds__(128)
     aggregate_node(t.level_nodes[k], root_size, pqr, accm, t);
 }
 
+// leaf masses for a tree that is a single leaf (no internal node ever visits it)
+__global__ void export_root_leaf_kernel(const TreeMeta* __restrict__ meta, const float4* __restrict__ accm,
+                                        TreeArrays t) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (meta->num_nodes == 0 || meta->num_nodes > t.node_cap) return;
+  const uint4 nb = t.nodeB[0];
+  if (!(nb.w & kNodeLeaf)) return;
+  float lm = 0.0f;
+  if (!(nb.w & kNodeZeroAgg))
+    for (uint32_t b = nb.y; b < nb.y + nb.z; ++b) lm = f_add(lm, accm[b].w);
+  t.node_mass[0] = lm;
+  t.parent[0] = 0xffffffffu;
+}
+
 // Traversal arrays: the nodes that can contribute to a field sum, i.e. those with a charged body
 // below them, compacted in pre-order (skip pointers remapped).  A node without charge adds exactly
 // +-0 to every acc_pos sum whatever the opening test says, so the reference's result is unchanged.
 struct ChargedFlagFn {
-  const uint4* nodeB;
-  __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
-    return (nodeB[i].w & kNodeCharged) ? 1u : 0u;
-  }
+  const NodeRec* rec;
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return rec[i].aq > 0.0 ? 1u : 0u; }
 };
 
 __global__ void __launch_bounds__(256)

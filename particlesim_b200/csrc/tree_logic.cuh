@@ -35,12 +35,24 @@ struct NodeSums {  // per internal node: running sums over its body range
   double x, y;          // Σx, Σy
 };
 
+// What the bottom-up sweep of the build carries per node: one 32-byte sector.
+struct NodeRec {
+  double aq, aqx, aqy;  // Σ|q|, Σ|q|x, Σ|q|y over the node's bodies
+  float charge;         // node charge in the reference's child order
+  uint32_t next;        // skip pointer | kLastSibling if the node is its parent's last non-empty child
+};
+constexpr uint32_t kLastSibling = 1u << 31;
+constexpr uint32_t kNextMask = ~kLastSibling;
+
 struct TreeArrays {
   float4* nodeA;      // {pos.x, pos.y, charge, quad.size}
-  uint4* nodeB;       // {next, body_start, body_count, depth | flags}
-  float* node_mass;
-  uint32_t* parent;   // compact index of the parent (root: 0xffffffff)
-  NodeSums* sums;
+  uint4* nodeB;       // {next, body_start, body_count, depth | flags}; internal body_count is
+                      // filled by the export sweep only (the traversal never reads it)
+  NodeRec* rec;
+  uint8_t* ndepth;
+  float* node_mass;   // export sweep only
+  uint32_t* parent;   // export sweep only: compact index of the parent (root: 0xffffffff)
+  NodeSums* sums;     // export sweep only
   uint32_t* level_nodes;  // internal nodes bucketed by depth
   uint32_t node_cap;
 };
@@ -128,102 +140,168 @@ PSIM_HD void level_scan(TreeMeta* meta, uint32_t node_cap) {
 }
 
 // All nodes whose first body is i: the leaf at depth ℓ_i and the internal cells above it down to
-// depth λ_i + 1.  Leaf aggregation follows quadtree.rs:281-306.  `sink` hands out level-bucket
-// slots and counts diagnostics (atomics on the device, plain counters in the emulation).
+// depth λ_i + 1.  The leaf is finished here (range end by galloping search, aggregates per
+// quadtree.rs:281-306, Σ|q| sums for its ancestors); internal cells only get their depth and first
+// body — their skip pointer and sums come from the bottom-up sweep, which reaches the end of a
+// node's subtree through its children.  `sink` hands out level-bucket slots and counts diagnostics
+// (atomics on the device, plain counters in the emulation).
 template <class Sink>
 PSIM_HD void emit_nodes_for_body(const uint64_t* keys, uint32_t n, uint32_t i, uint16_t lev,
                                  const uint32_t* nodebase, uint32_t M, const float4* pqr,
                                  const float4* accm, uint32_t leaf_capacity, uint32_t thread_capacity,
                                  float root_size, int dcap, const TreeArrays& t, Sink& sink) {
+  (void)accm;
   const int lam = le_lambda(lev), ell = le_ell(lev);
   if (!(lam < ell)) return;
   const uint32_t base = nodebase[i];
-  uint32_t j = i + 1;
-  for (int d = ell; d > lam; --d) {
-    j = run_end(keys, n, i, j, d);
+  {
+    const int d = ell;
+    const uint32_t j = run_end(keys, n, i, i + 1, d);
     const uint32_t node = base + (uint32_t)(d - lam - 1);
     const uint32_t next = (j < n) ? nodebase[j] : M;
     const uint32_t count = j - i;
     const float size = ldexpf(root_size, -d);  // size *= 0.5 per level, exact
-    if (d == ell) {
-      const bool agg = leaf_is_aggregated(count, leaf_capacity, thread_capacity);
-      float tm = 0.0f, tq = 0.0f, wx = 0.0f, wy = 0.0f;
-      bool charged = false;
-      for (uint32_t b = i; b < j; ++b) charged = charged || (pqr[b].z != 0.0f);
+    const bool agg = leaf_is_aggregated(count, leaf_capacity, thread_capacity);
+    float tq = 0.0f, wx = 0.0f, wy = 0.0f;
+    double aq = 0.0, aqx = 0.0, aqy = 0.0;
+    for (uint32_t b = i; b < j; ++b) {
+      const float4 p = pqr[b];
+      const double a = fabs((double)p.z);
+      aq += a, aqx += a * (double)p.x, aqy += a * (double)p.y;
       if (agg) {
-        for (uint32_t b = i; b < j; ++b) {
-          const float4 p = pqr[b];
-          tm = f_add(tm, accm[b].w);
-          wx = f_add(wx, f_mul(p.x, p.z));
-          wy = f_add(wy, f_mul(p.y, p.z));
-          tq = f_add(tq, p.z);
-        }
-        if (fabsf(tq) > 1e-6f) {
-          wx = f_div(wx, tq);
-          wy = f_div(wy, tq);
-        }
-      } else {
-        sink.zero_leaf();
+        wx = f_add(wx, f_mul(p.x, p.z));
+        wy = f_add(wy, f_mul(p.y, p.z));
+        tq = f_add(tq, p.z);
       }
-      if (count > 1 && d == dcap) sink.cap_leaf();
-      t.nodeA[node] = make_float4(wx, wy, tq, size);
-      t.node_mass[node] = tm;
-      t.nodeB[node] = make_uint4(next, i, count, (uint32_t)d | kNodeLeaf | (agg ? 0u : kNodeZeroAgg) |
-                                                     (charged ? kNodeCharged : 0u));
-    } else {
-      t.nodeB[node] = make_uint4(next, i, count, (uint32_t)d);
-      t.level_nodes[sink.level_slot(d)] = node;
     }
-    if (d == 0) t.parent[node] = 0xffffffffu;
+    if (agg) {
+      if (fabsf(tq) > 1e-6f) {
+        wx = f_div(wx, tq);
+        wy = f_div(wy, tq);
+      }
+    } else {
+      sink.zero_leaf();
+    }
+    if (count > 1 && d == dcap) sink.cap_leaf();
+    t.nodeA[node] = make_float4(wx, wy, tq, size);
+    t.nodeB[node] = make_uint4(next, i, count, (uint32_t)d | kNodeLeaf | (agg ? 0u : kNodeZeroAgg) |
+                                                   (aq > 0.0 ? kNodeCharged : 0u));
+    const bool last = (j >= n) || lcp_levels(keys[i], keys[j]) < d - 1;
+    NodeRec r;
+    r.aq = aq, r.aqx = aqx, r.aqy = aqy, r.charge = tq, r.next = next | (last ? kLastSibling : 0u);
+    t.rec[node] = r;
+    t.ndepth[node] = (uint8_t)d;
+  }
+  for (int d = ell - 1; d > lam; --d) {
+    const uint32_t node = base + (uint32_t)(d - lam - 1);
+    t.nodeB[node] = make_uint4(0u, i, 0u, (uint32_t)d);
+    t.ndepth[node] = (uint8_t)d;
+    t.level_nodes[sink.level_slot(d)] = node;
   }
 }
 
-// One internal node of the bottom-up sweep: quadtree.rs:103-151.
-// mass/charge: the reference's ((c0 + c1) + c2) + c3 over the 4 children; absent (empty) children
-// are +0.0 terms.  Centre: |q|-weighted, else mass-weighted, else centroid, from sums
-// carried up in double (the reference runs one f32 running sum over the node's whole range).
+// One internal node of the build's bottom-up sweep (quadtree.rs:103-151): charge in the reference's
+// ((c0 + c1) + c2) + c3 order (absent children are +0.0 terms), Σ|q| sums in f64 for the centre (the
+// reference runs one f32 running sum over the node's whole range), skip pointer = where the last
+// child's subtree ends.  It touches one 32-byte record per child and writes one; centres and the
+// topology records are finished by the streaming finalize pass.
+PSIM_HD void aggregate_node_lean(uint32_t node, int depth, uint32_t M, const TreeArrays& t) {
+  double aq = 0.0, aqx = 0.0, aqy = 0.0;
+  float charge = 0.0f;
+  uint32_t c = node + 1;
+  while (true) {
+    const NodeRec r = t.rec[c];
+    charge = f_add(charge, r.charge);
+    aq += r.aq, aqx += r.aqx, aqy += r.aqy;
+    c = r.next & kNextMask;
+    if (r.next & kLastSibling) break;
+  }
+  // the node that follows my subtree is my sibling iff it sits at my depth
+  const bool last = (c >= M) || ((int)t.ndepth[c] != depth);
+  NodeRec out;
+  out.aq = aq, out.aqx = aqx, out.aqy = aqy, out.charge = charge, out.next = c | (last ? kLastSibling : 0u);
+  t.rec[node] = out;
+}
+
+// Streaming pass over all nodes in pre-order after the sweep: topology record and centre of every
+// internal node from its sums.  A node whose Σ|q| is <= 1e-6 takes the reference's mass / centroid
+// fall-back by a direct pass over its bodies; for Σ|q| == 0 (no charge below: the node
+// can never contribute to a field sum) that is left to the export sweep.
+PSIM_HD void finalize_node(uint32_t node, uint32_t M, uint32_t n_bodies, float root_size,
+                           const float4* pqr, const float4* accm, const TreeArrays& t) {
+  uint4 nb = t.nodeB[node];
+  if (nb.w & kNodeLeaf) return;
+  const NodeRec r = t.rec[node];
+  const uint32_t c = r.next & kNextMask;
+  nb.x = c;
+  if (r.aq > 0.0) nb.w |= kNodeCharged;
+  t.nodeB[node] = nb;
+  float px = 0.0f, py = 0.0f;
+  if (r.aq > (double)1e-6f) {
+    px = (float)(r.aqx / r.aq), py = (float)(r.aqy / r.aq);
+  } else if (r.aq > 0.0) {
+    const uint32_t b0 = nb.y, b1 = (c < M) ? t.nodeB[c].y : n_bodies;
+    double m = 0.0, mx = 0.0, my = 0.0, x = 0.0, y = 0.0;
+    for (uint32_t b = b0; b < b1; ++b) {
+      const float4 p = pqr[b];
+      const double w = (double)accm[b].w;
+      m += w, mx += w * (double)p.x, my += w * (double)p.y, x += (double)p.x, y += (double)p.y;
+    }
+    if (m > (double)1e-6f) px = (float)(mx / m), py = (float)(my / m);
+    else if (b1 > b0) px = (float)(x / (double)(b1 - b0)), py = (float)(y / (double)(b1 - b0));
+  }
+  t.nodeA[node] = make_float4(px, py, r.charge, ldexpf(root_size, -(int)(nb.w & kNodeDepthMask)));
+}
+
+// Export sweep (psim_download_nodes only), one internal node, deepest level first: parent links,
+// node mass in the reference's child order, body counts, and the mass-weighted / centroid centre of
+// nodes without charge (quadtree.rs:127-139), which the build leaves at (0, 0).
 PSIM_HD void aggregate_node(uint32_t node, float root_size, const float4* pqr, const float4* accm,
                             const TreeArrays& t) {
+  (void)root_size;
   const uint4 nb = t.nodeB[node];
   NodeSums s = {0, 0, 0, 0, 0, 0, 0, 0};
-  float charge = 0.0f, msum = 0.0f;
+  float msum = 0.0f;
+  uint32_t count = 0;
   uint32_t c = node + 1;
   while (c < nb.x) {
     const uint4 cb = t.nodeB[c];
-    charge = f_add(charge, t.nodeA[c].z);
-    msum = f_add(msum, t.node_mass[c]);
     t.parent[c] = node;
     if (cb.w & kNodeLeaf) {
+      float lm = 0.0f;
+      const bool agg = !(cb.w & kNodeZeroAgg);
       for (uint32_t b = cb.y; b < cb.y + cb.z; ++b) {
         const float4 p = pqr[b];
-        const double aq = fabs((double)p.z), m = (double)accm[b].w;
-        s.aq += aq, s.aqx += aq * (double)p.x, s.aqy += aq * (double)p.y;
+        const double m = (double)accm[b].w;
         s.m += m, s.mx += m * (double)p.x, s.my += m * (double)p.y;
         s.x += (double)p.x, s.y += (double)p.y;
+        if (agg) lm = f_add(lm, accm[b].w);
       }
+      t.node_mass[c] = lm;
+      msum = f_add(msum, lm);
     } else {
       const NodeSums cs = t.sums[c];
-      s.aq += cs.aq, s.aqx += cs.aqx, s.aqy += cs.aqy;
       s.m += cs.m, s.mx += cs.mx, s.my += cs.my;
       s.x += cs.x, s.y += cs.y;
+      msum = f_add(msum, t.node_mass[c]);
     }
+    count += t.nodeB[c].z;
     c = cb.x;
   }
   t.sums[node] = s;
-  if (s.aq > 0.0) t.nodeB[node].w = nb.w | kNodeCharged;
-  float px, py;
-  if (s.aq > (double)1e-6f) {
-    px = (float)(s.aqx / s.aq), py = (float)(s.aqy / s.aq);
-  } else if (s.m > (double)1e-6f) {
-    px = (float)(s.mx / s.m), py = (float)(s.my / s.m);
-  } else if (nb.z > 0) {
-    px = (float)(s.x / (double)nb.z), py = (float)(s.y / (double)nb.z);
-  } else {
-    px = 0.0f, py = 0.0f;
-  }
-  const float size = ldexpf(root_size, -(int)(nb.w & kNodeDepthMask));
-  t.nodeA[node] = make_float4(px, py, charge, size);
   t.node_mass[node] = msum;
+  t.nodeB[node].z = count;
+  if (!(t.rec[node].aq > 0.0)) {
+    float px = 0.0f, py = 0.0f;
+    if (s.m > (double)1e-6f) {
+      px = (float)(s.mx / s.m), py = (float)(s.my / s.m);
+    } else if (count > 0) {
+      px = (float)(s.x / (double)count), py = (float)(s.y / (double)count);
+    }
+    float4 a = t.nodeA[node];
+    a.x = px, a.y = py;
+    t.nodeA[node] = a;
+  }
 }
 
 // ---- export in the reference's shape (node.rs:6-14): ROOT = 0, the 4 children of the r-th

@@ -35,6 +35,8 @@ struct Emu {
   std::vector<float> node_mass;
   std::vector<uint32_t> parent, level_nodes, irank;
   std::vector<NodeSums> sums;
+  std::vector<NodeRec> rec;
+  std::vector<uint8_t> ndepth;
   TreeArrays t;
   float t_sq = 1, e_sq = 4;
 };
@@ -109,12 +111,25 @@ uint32_t emu_build(void* h, uint32_t n, const float* pos_xy, const float* mass, 
   e.parent.assign(M, 0);
   e.level_nodes.assign(M, 0);
   e.sums.assign(M, NodeSums{0, 0, 0, 0, 0, 0, 0, 0});
-  e.t = TreeArrays{e.nodeA.data(), e.nodeB.data(), e.node_mass.data(), e.parent.data(), e.sums.data(),
-                   e.level_nodes.data(), M};
+  e.rec.assign(M, NodeRec{0, 0, 0, 0.f, 0});
+  e.ndepth.assign(M, 0);
+  e.t = TreeArrays{e.nodeA.data(), e.nodeB.data(), e.rec.data(), e.ndepth.data(), e.node_mass.data(),
+                   e.parent.data(), e.sums.data(), e.level_nodes.data(), M};
   HostSink sink{&e.meta};
   for (uint32_t i = 0; i < n; ++i)
     emit_nodes_for_body(e.keys.data(), n, i, le[i], nodebase.data(), M, e.pqr.data(), e.accm.data(),
                         leaf_capacity, thread_capacity, r.size, dcap, e.t, sink);
+  // build sweep, then the export sweep (parents, masses, counts, chargeless centres)
+  for (int level = kMaxLevels - 1; level >= 0; --level)
+    for (uint32_t k = e.meta.level_start[level]; k < e.meta.level_start[level + 1]; ++k)
+      aggregate_node_lean(e.level_nodes[k], level, M, e.t);
+  for (uint32_t node = 0; node < M; ++node) finalize_node(node, M, n, r.size, e.pqr.data(), e.accm.data(), e.t);
+  if (M && (e.nodeB[0].w & kNodeLeaf)) {
+    float lm = 0.f;
+    if (!(e.nodeB[0].w & kNodeZeroAgg))
+      for (uint32_t b = e.nodeB[0].y; b < e.nodeB[0].y + e.nodeB[0].z; ++b) lm += e.accm[b].w;
+    e.node_mass[0] = lm;
+  }
   for (int level = kMaxLevels - 1; level >= 0; --level)
     for (uint32_t k = e.meta.level_start[level]; k < e.meta.level_start[level + 1]; ++k)
       aggregate_node(e.level_nodes[k], r.size, e.pqr.data(), e.accm.data(), e.t);
