@@ -248,6 +248,10 @@ __global__ void __launch_bounds__(128)
 constexpr int kStackCap = 416;
 struct WarpShared {
   uint32_t st_node[kStackCap], st_pend[kStackCap], st_mask[kStackCap];
+  // the round's nodes that some target may accept, staged for broadcast reads
+  float4 l_node[32];  // {centre.x, centre.y, charge, size}
+  uint2 l_mc[32];     // {mask of targets that reach the node, 1 if every target accepts}
+  uint32_t l_acc[32]; // result: mask of targets that accepted
 };
 
 template <bool PARITY>
@@ -327,24 +331,29 @@ __device__ __forceinline__ float2 bh_group_walk(const float4* __restrict__ nodeA
         else if (dmax2 < lr * lr * 0.99998f) cls = 2;
       }
     }
-    // every node that some target may accept: each lane applies the reference's opening test with its
-    // own position and radius (quadtree.rs:361-371) and, if it accepts, adds the monopole (:372-375)
+    // every node that some target may accept is staged in shared memory; then each lane applies the
+    // reference's opening test with its own position and radius (quadtree.rs:361-371) to every staged
+    // node (broadcast reads) and, if it accepts, adds the monopole (:372-375)
     uint32_t acc_mask = (has && cls == 1 && na.z == 0.0f) ? mask : 0u;  // charge 0: adds exactly +-0
-    uint32_t todo = __ballot_sync(FULL, has && cls != 2 && !(cls == 1 && na.z == 0.0f));
-    while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const float nx = __shfl_sync(FULL, na.x, src), ny = __shfl_sync(FULL, na.y, src);
-      const float nq = __shfl_sync(FULL, na.z, src), ns = __shfl_sync(FULL, na.w, src);
-      const uint32_t m = __shfl_sync(FULL, mask, src);
-      const int c = __shfl_sync(FULL, cls, src);
-      const float dx = A::sub(px, nx), dy = A::sub(py, ny);
+    const bool in_list = has && cls != 2 && !(cls == 1 && na.z == 0.0f);
+    const uint32_t lm = __ballot_sync(FULL, in_list);
+    const int cnt = __popc(lm);
+    const int my_slot = __popc(lm & lt);
+    if (in_list) {
+      ws.l_node[my_slot] = na;
+      ws.l_mc[my_slot] = make_uint2(mask, cls == 1 ? 1u : 0u);
+    }
+    __syncwarp();
+    for (int it = 0; it < cnt; ++it) {
+      const float4 nd = ws.l_node[it];
+      const uint2 mc = ws.l_mc[it];
+      const float dx = A::sub(px, nd.x), dy = A::sub(py, nd.y);
       const float d_sq = A::add(A::mul(dx, dx), A::mul(dy, dy));
-      bool acc = ((m >> lane) & 1u) != 0;
+      bool acc = ((mc.x >> lane) & 1u) != 0;
       float dist = 0.0f;
       bool have_dist = false;
-      if (c != 1 && acc) {
-        const float lim = ns * P.inv_theta + my_lim_r;
+      if (mc.y == 0u && acc) {
+        const float lim = nd.w * P.inv_theta + my_lim_r;
         const float lim2 = lim * lim;
         if (d_sq > lim2 * 1.00002f) {
           acc = true;
@@ -354,20 +363,22 @@ __device__ __forceinline__ float2 bh_group_walk(const float4* __restrict__ nodeA
           dist = A::sqrt(d_sq);
           have_dist = true;
           const float dist_adj = fmaxf(A::sub(dist, radius), 0.0f);
-          acc = A::mul(ns, ns) < A::mul(A::mul(dist_adj, dist_adj), P.t_sq);
+          acc = A::mul(nd.w, nd.w) < A::mul(A::mul(dist_adj, dist_adj), P.t_sq);
         }
       }
       const uint32_t am = __ballot_sync(FULL, acc);
-      if (lane == src) acc_mask = am;
-      if (acc && nq != 0.0f) {
+      if (lane == 0) ws.l_acc[it] = am;
+      if (acc && nd.z != 0.0f) {
         if (!have_dist) dist = A::sqrt(d_sq);
-        const float r_eff = fmaxf(dist, A::add(radius, A::mul(ns, 0.5f)));
+        const float r_eff = fmaxf(dist, A::add(radius, A::mul(nd.w, 0.5f)));
         const float denom = A::mul(A::add(A::mul(r_eff, r_eff), P.e_sq), r_eff);
-        const float s = A::div(A::mul(kq, nq), denom);
-        ax = A::add(ax, A::mul(dx, s));
-        ay = A::add(ay, A::mul(dy, s));
+        const float sc = A::div(A::mul(kq, nd.z), denom);
+        ax = A::add(ax, A::mul(dx, sc));
+        ay = A::add(ay, A::mul(dy, sc));
       }
     }
+    __syncwarp();
+    if (in_list) acc_mask = ws.l_acc[my_slot];
     const uint32_t rem = mask & ~acc_mask;
     const bool push_sib = has && nb.x < pend;
     const bool push_child = has && rem != 0 && !leaf;

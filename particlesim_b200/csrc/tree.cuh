@@ -136,19 +136,13 @@ __global__ void level_scan_kernel(TreeMeta* __restrict__ meta, uint32_t node_cap
   level_scan(meta, node_cap);
 }
 
-// level-bucket slots: one atomic per group of lanes that are at the same depth
+// level-bucket slots.  A CTA first counts, from the packed (λ, ℓ) bytes alone, how many internal nodes
+// of each depth its bodies start, reserves one contiguous range per depth with a single global atomic,
+// and then hands slots out of shared-memory counters while it emits.
 struct DeviceSink {
   TreeMeta* meta;
-  __device__ __forceinline__ uint32_t level_slot(int d) {
-    const unsigned act = __activemask();
-    const unsigned peers = __match_any_sync(act, d);
-    const int leader = __ffs(peers) - 1;
-    const int lane = threadIdx.x & 31;
-    uint32_t slot = 0;
-    if (lane == leader) slot = atomicAdd(&meta->level_cursor[d], (uint32_t)__popc(peers));
-    slot = __shfl_sync(peers, slot, leader);
-    return meta->level_start[d] + slot + __popc(peers & ((1u << lane) - 1u));
-  }
+  uint32_t* s_cursor;  // [kLevels] next free slot per depth (absolute index into level_nodes)
+  __device__ __forceinline__ uint32_t level_slot(int d) { return atomicAdd(&s_cursor[d], 1u); }
   __device__ __forceinline__ void zero_leaf() { atomicAdd(&meta->num_zero_leaves, 1u); }
   __device__ __forceinline__ void cap_leaf() { atomicAdd(&meta->num_cap_leaves, 1u); }
 };
@@ -163,11 +157,30 @@ __global__ void __launch_bounds__(128)
   const uint64_t* __restrict__ keys = plan->src[npass] ? keys1 : keys0;
   const uint32_t M = meta->num_nodes;
   if (M > t.node_cap) return;  // arena overflow, flagged by level_scan_kernel
+  __shared__ uint32_t s_cnt[kLevels];
+  __shared__ uint32_t s_cursor[kLevels];
+  if (threadIdx.x < kLevels) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  // each CTA owns a contiguous slab of bodies (keeps its nodes, and the level buckets, local)
+  const uint32_t per_block = (n + gridDim.x - 1) / gridDim.x;
+  const uint32_t lo = blockIdx.x * per_block;
+  const uint32_t hi = (lo + per_block < n) ? lo + per_block : n;
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const uint16_t lev = le[i];
+    const int lam = le_lambda(lev), ell = le_ell(lev);
+    for (int d = lam + 1; d < ell; ++d) atomicAdd(&s_cnt[d], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < kLevels) {
+    const uint32_t c = s_cnt[threadIdx.x];
+    s_cursor[threadIdx.x] =
+        meta->level_start[threadIdx.x] + (c ? atomicAdd(&meta->level_cursor[threadIdx.x], c) : 0u);
+  }
+  __syncthreads();
   const float root_size = meta->root.size;
   const int dcap = (int)meta->dcap;
-  DeviceSink sink{meta};
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  DeviceSink sink{meta, s_cursor};
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
     emit_nodes_for_body(keys, n, i, le[i], nodebase, M, pqr, accm, leaf_capacity, thread_capacity,
                         root_size, dcap, t, sink);
 }
