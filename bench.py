@@ -45,6 +45,18 @@ def measured_peaks():
         return {}
 
 
+def ncu_traffic(n):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the committed
+    ncu --set full capture of the same workload (profiles/); null for other sizes"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if int(t["n_bodies"]) == int(n):
+            return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -268,7 +280,7 @@ def run_ours(args):
         line["roofline"] = {
             "kernel": "bh_field_bodies_kernel", "bound": "fp32",
             "achieved": achieved, "peak": float(tf.value), "unit": "TFLOP/s", "frac": achieved / float(tf.value),
-            "traffic": None,
+            "traffic": ncu_traffic(n),
             "peak_source": "measured live: FP32 FMA microbenchmark on this GPU (MEASURED_PEAKS.json holds HBM and bf16 "
                            "tensor peaks only; the traversal is FP32-pipe bound and uses no tensor cores, SURVEY.md 8d)",
             "algorithmic": {"node_visits_per_body": visits / n, "monopoles_per_body": accepted / n,
@@ -276,6 +288,7 @@ def run_ours(args):
                             "rule": "12 flops per opening test + 14 per monopole or direct term (SURVEY.md 8d)",
                             "warp_steps_per_32_bodies": wsteps / ((n + 31) // 32)},
             "avg_launch_ms": phase["quadtree_field"],
+            "algorithmic_bytes": int(st["compact_nodes"] * 0 + n * (16 + 8 + 16)),
         }
         # HBM roofline of the build pipeline (keys, sort, gather, nodes, aggregation), for the explanation
         peaks = measured_peaks()
