@@ -1,0 +1,30 @@
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / synccheck)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from helpers import KE, clustered, electrolyte  # noqa: E402
+from particlesim_b200 import Bodies, Simulation  # noqa: E402
+
+for gen, n in ((electrolyte, 30_011), (clustered, 20_003)):
+    bd = gen(n)
+    if gen is electrolyte:
+        bd["species"][:2000] = 1
+    b = Bodies(bd["pos"], vel=bd.get("vel"), mass=bd["mass"], radius=bd["radius"], charge=bd["charge"],
+               species=bd["species"], ebody=bd.get("ebody"), erel=bd.get("erel"))
+    for mode in (1, 2, 0):
+        sim = Simulation(b, bd["hw"], bd["hh"], parity_mode=mode)
+        sim.config.coulomb_constant = float(KE)
+        for _ in range(2):
+            sim.step_device()
+        sim.sync()
+        nodes = sim.quadtree.nodes
+        sim._call("psim_cell_build", bd["hw"], bd["hh"], 11.88)
+        sim._neighbors(np.arange(0, n, 97), 3.96, False)
+        print(gen.__name__, mode, len(nodes), sim.stats()["max_depth"], flush=True)
+        sim.close()
+print("sanitize run done")
