@@ -243,11 +243,14 @@ __global__ void __launch_bounds__(128)
 // The box tests are conservative (2e-5 margin, far above the worst-case rounding of the exact test)
 // and never decide a borderline case, so every target sums exactly the reference's interaction set
 // with the reference's per-term arithmetic; only the order of the additions differs from acc_pos.
-// Pending nodes live in a per-warp ring buffer in shared memory: entry = (node, end of the parent's
-// subtree, mask of targets that reach the node).
-constexpr int kStackCap = 416;
+// Pending nodes live in a per-warp ring buffer in shared memory: entry = (node, mask of targets that
+// reach the node).  A lane that opens a node finds all its children at once (child k+1 is the skip
+// pointer of child k, until it equals the parent's), so the frontier widens by the branching factor
+// every round and a walk takes about as many rounds as the tree is deep.
+constexpr int kStackCap = 640;
+constexpr int kLifoAbove = kStackCap - 288;  // see the capacity argument in bh_group_walk
 struct WarpShared {
-  uint32_t st_node[kStackCap], st_pend[kStackCap], st_mask[kStackCap];
+  uint32_t st_node[kStackCap], st_mask[kStackCap];
   // the round's nodes that some target may accept, staged for broadcast reads
   float4 l_node[32];  // {centre.x, centre.y, charge, size}
   uint2 l_mc[32];     // {mask of targets that reach the node, 1 if every target accepts}
@@ -288,21 +291,23 @@ __device__ __forceinline__ float2 bh_group_walk(const float4* __restrict__ nodeA
   const bool box_ok = __all_sync(FULL, finite_me);
   const float kq = A::mul(P.k_e, q);
   const float my_lim_r = radius;
-  if (lane == 0) ws.st_node[0] = 0, ws.st_pend[0] = M, ws.st_mask[0] = live_mask;
+  if (lane == 0) ws.st_node[0] = 0, ws.st_mask[0] = live_mask;
   __syncwarp();
-  // pending nodes: a ring buffer served first-in-first-out (wide rounds); when it is nearly full the
-  // walk switches to last-in-first-out, one node per round, which bounds the growth by the depth
+  // Ring buffer served first-in-first-out (wide rounds).  Capacity: a FIFO round pops k <= 32 entries
+  // and pushes <= 4k, so starting at size <= kLifoAbove it ends at <= kLifoAbove + 96; above that the
+  // walk goes last-in-first-out one node per round, where at most 3 siblings per level stay pending
+  // (<= 96 more for 32 levels): kLifoAbove + 96 + 96 <= kStackCap.
   int head = 0, size = 1;
   uint32_t visited = 0;
   while (size > 0) {
-    const bool lifo = size > kStackCap - 104;
+    const bool lifo = size > kLifoAbove;
     const int k = lifo ? 1 : (size < 32 ? size : 32);
     const bool has = lane < k;
-    uint32_t node = 0, pend = 0, mask = 0;
+    uint32_t node = 0, mask = 0;
     if (has) {
       int idx = lifo ? head + size - 1 : head + lane;
       if (idx >= kStackCap) idx -= kStackCap;
-      node = ws.st_node[idx], pend = ws.st_pend[idx], mask = ws.st_mask[idx];
+      node = ws.st_node[idx], mask = ws.st_mask[idx];
     }
     __syncwarp();
     if (!lifo) {
@@ -380,18 +385,37 @@ __device__ __forceinline__ float2 bh_group_walk(const float4* __restrict__ nodeA
     __syncwarp();
     if (in_list) acc_mask = ws.l_acc[my_slot];
     const uint32_t rem = mask & ~acc_mask;
-    const bool push_sib = has && nb.x < pend;
-    const bool push_child = has && rem != 0 && !leaf;
-    const uint32_t bs = __ballot_sync(FULL, push_sib), bc = __ballot_sync(FULL, push_child);
-    int off = head + size + __popc(bs & lt) + __popc(bc & lt);
-    if (off >= kStackCap) off -= kStackCap;
-    if (push_sib) ws.st_node[off] = nb.x, ws.st_pend[off] = pend, ws.st_mask[off] = mask;
-    if (push_child) {
-      int o2 = off + (push_sib ? 1 : 0);
-      if (o2 >= kStackCap) o2 -= kStackCap;
-      ws.st_node[o2] = node + 1, ws.st_pend[o2] = nb.x, ws.st_mask[o2] = rem;
+    // a node some target still has to look below: all its children go onto the buffer
+    uint32_t kid[4] = {0u, 0u, 0u, 0u};
+    int nk = 0;
+    if (has && rem != 0 && !leaf) {
+      uint32_t c = node + 1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        kid[j] = c;
+        nk = j + 1;
+        const uint32_t cn = __ldg(&nodeB[c].x);
+        if (cn == nb.x) break;  // c was the last child: its skip pointer is the parent's
+        c = cn;
+      }
     }
-    size += __popc(bs) + __popc(bc);
+    int incl = nk;  // inclusive prefix of the child counts over the lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int off = incl - nk;
+    const int total = __shfl_sync(FULL, incl, 31);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j < nk) {
+        int o2 = head + size + off + j;
+        if (o2 >= kStackCap) o2 -= kStackCap;
+        ws.st_node[o2] = kid[j], ws.st_mask[o2] = rem;
+      }
+    }
+    size += total;
     __syncwarp();
     // direct terms of this round (quadtree.rs:381-395)
     uint32_t nm = __ballot_sync(FULL, has && rem != 0 && leaf);
