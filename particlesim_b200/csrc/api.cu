@@ -87,6 +87,7 @@ struct psim_ctx {
 
   // cells
   uint32_t *cell_start = nullptr, *cell_end = nullptr, *order = nullptr, *body_cell = nullptr;
+  float4* cpos = nullptr;
   uint64_t cell_cap = 0;
   GridDims grid = {0, 0, 1.0f, 0.0f, 0.0f};
   int cell_passes = 0;
@@ -539,7 +540,7 @@ int32_t cell_build_async(psim_ctx* ctx, float hw, float hh, float cell_size) {
   ctx->launches += 2 + npass;
   cell_ranges_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(
       ctx->ckeys[0], ctx->ckeys[1], ctx->cidx[0], ctx->cidx[1], ctx->cell_plan, npass, n,
-      ctx->cell_start, ctx->cell_end, ctx->order, ctx->body_cell);
+      ctx->cell_start, ctx->cell_end, ctx->order, ctx->body_cell, b.pqr, b.species, ctx->cpos);
   LAUNCHED(ctx);
   ctx->grid_valid = true;
   return PSIM_OK;
@@ -645,7 +646,7 @@ int32_t short_range_async(psim_ctx* ctx, uint32_t flags) {
   body_range(ctx, first, count);
   if (count == 0) return PSIM_OK;
   short_range_kernel<<<(count + 127) / 128, 128, 0, ctx->stream>>>(
-      b.pqr, b.species, ctx->table_d, first, first + count, ctx->cell_start, ctx->cell_end, ctx->order,
+      b.pqr, b.species, ctx->table_d, first, first + count, ctx->cell_start, ctx->cell_end, ctx->cpos,
       ctx->body_cell, P, b.accm);
   LAUNCHED(ctx);
   return PSIM_OK;
@@ -701,7 +702,7 @@ void free_all(psim_ctx* c) {
   F(c->t.rec), F(c->t.ndepth);
   F(c->travA), F(c->travB), F(c->trav_rank), F(c->trav_count);
   F(c->perm), F(c->inv);
-  F(c->cell_start), F(c->cell_end), F(c->order), F(c->body_cell);
+  F(c->cell_start), F(c->cell_end), F(c->order), F(c->body_cell), F(c->cpos);
   F(c->table_d), F(c->stage), F(c->qstage), F(c->step_counter);
 }
 
@@ -781,7 +782,7 @@ int32_t psim_create(int32_t device, uint64_t max_bodies, uint64_t max_electrons,
   A(&ctx->travA, ctx->node_cap), A(&ctx->travB, ctx->node_cap), A(&ctx->trav_rank, ctx->node_cap), A(&ctx->trav_count, 1);
   ctx->t.node_cap = ctx->node_cap;
   A(&ctx->perm, nb), A(&ctx->inv, nb);
-  A(&ctx->order, nb), A(&ctx->body_cell, nb);
+  A(&ctx->order, nb), A(&ctx->body_cell, nb), A(&ctx->cpos, nb);
   A(&ctx->table_d, kMaxSpecies), A(&ctx->step_counter, 1);
   if (!ok) {
     cudaGetLastError();
@@ -1341,9 +1342,12 @@ int32_t psim_step(psim_ctx* ctx, const psim_step_params* p) {
   if ((rc = build_async(ctx, PSIM_BUILD_CONTAINING, 0.f, 0.f))) return rc;
   mark(1);
   if (p->do_short_range) {
+    // The reference sizes its grid for the polar pass too (3 x the LJ cutoff, forces.rs:17-22).  The
+    // pair sets of the LJ / repulsion passes do not depend on the cell size, so the fused step bins at
+    // the largest cutoff those passes use: 9x fewer candidates per body than at 3 x cutoff.
     const float lj_cutoff = max_lj_cutoff(ctx), repulsion_cutoff = max_repulsion_cutoff(ctx);
-    const float max_cutoff = fmaxf(fmaxf(3.0f * lj_cutoff, repulsion_cutoff), lj_cutoff);
-    if (max_cutoff > 0.0f && (rc = cell_build_async(ctx, p->hw, p->hh, max_cutoff))) return rc;
+    const float cell = fmaxf(repulsion_cutoff, lj_cutoff);
+    if (cell > 0.0f && (rc = cell_build_async(ctx, p->hw, p->hh, cell))) return rc;
   }
   mark(2);
   if ((rc = field_async(ctx, p->k_e, p->bg_x, p->bg_y, 1))) return rc;

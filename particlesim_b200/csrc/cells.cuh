@@ -53,7 +53,9 @@ __global__ void __launch_bounds__(256)
                        const uint32_t* __restrict__ idx0, const uint32_t* __restrict__ idx1,
                        const SortPlan* __restrict__ plan, int npass, uint32_t n,
                        uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_end,
-                       uint32_t* __restrict__ order, uint32_t* __restrict__ body_cell) {
+                       uint32_t* __restrict__ order, uint32_t* __restrict__ body_cell,
+                       const float4* __restrict__ pqr, const uint8_t* __restrict__ species,
+                       float4* __restrict__ cpos) {
   const uint32_t* __restrict__ cell = plan->src[npass] ? cell1 : cell0;
   const uint32_t* __restrict__ idx = plan->src[npass] ? idx1 : idx0;
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -62,6 +64,10 @@ __global__ void __launch_bounds__(256)
     const uint32_t b = idx[k];
     order[k] = b;
     body_cell[b] = c;
+    // neighbour data laid out in cell order: {x, y, species, body index}, so a cell's bodies are one
+    // contiguous run of 16-byte records
+    const float4 p = pqr[b];
+    cpos[k] = make_float4(p.x, p.y, __uint_as_float((uint32_t)species[b]), __uint_as_float(b));
     if (k == 0 || cell[k - 1] != c) cell_start[c] = k;
     if (k + 1 == n || cell[k + 1] != c) cell_end[c] = k + 1;
   }
@@ -137,19 +143,16 @@ __device__ __forceinline__ void rep_pair(const SpeciesRow& sa, const SpeciesRow&
 }
 
 // Gather form of the reference's serial pair loops: each body sums the terms of every pair it is
-// in.  One CTA handles a run of consecutive bodies (Morton order => a compact patch); the bodies of
-// the patch's neighbouring cells are the L1/L2-resident working set.
-// Tile staging: the CTA first copies its own bodies' (pos, species) into shared memory; partners
-// that are in the same CTA (the common case for a compact patch) are read from there.
+// in.  One CTA handles a run of consecutive bodies (Morton order => a compact patch); partner data
+// is read from `cpos`, the cell-ordered copy of {x, y, species, index}, so each neighbouring cell is
+// one contiguous run of 16-byte records that the patch's threads share through L1.
 __global__ void __launch_bounds__(128)
     short_range_kernel(const float4* __restrict__ pqr, const uint8_t* __restrict__ species,
                        const SpeciesRow* __restrict__ table_g, uint32_t first, uint32_t n,
                        const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end,
-                       const uint32_t* __restrict__ order, const uint32_t* __restrict__ body_cell,
+                       const float4* __restrict__ cpos, const uint32_t* __restrict__ body_cell,
                        ShortRangeParams P, float4* __restrict__ acc_mass) {
   __shared__ SpeciesRow table[kMaxSpecies];
-  __shared__ float2 s_pos[128];
-  __shared__ uint8_t s_sp[128];
   for (int k = threadIdx.x; k < kMaxSpecies * (int)(sizeof(SpeciesRow) / 4); k += blockDim.x)
     reinterpret_cast<uint32_t*>(table)[k] = reinterpret_cast<const uint32_t*>(table_g)[k];
   const uint32_t block_first = first + blockIdx.x * blockDim.x;  // bodies [first, n) of this rank
@@ -160,8 +163,6 @@ __global__ void __launch_bounds__(128)
     me = pqr[i];
     my_sp = species[i] < kMaxSpecies ? species[i] : 0;
   }
-  s_pos[threadIdx.x] = make_float2(me.x, me.y);
-  s_sp[threadIdx.x] = my_sp;
   __syncthreads();
   if (i >= n) return;
   const SpeciesRow si = table[my_sp];
@@ -182,19 +183,12 @@ __global__ void __launch_bounds__(128)
         const uint32_t cc = (uint32_t)x + (uint32_t)y * P.g.gx;
         const uint32_t e = cell_end[cc];
         for (uint32_t k = cell_start[cc]; k < e; ++k) {
-          const uint32_t j = order[k];
+          const float4 cj = __ldg(&cpos[k]);
+          const uint32_t j = __float_as_uint(cj.w);
           if (j == i) continue;
-          float jx, jy;
-          uint8_t jsp;
-          const uint32_t local = j - block_first;  // wraps for j < block_first
-          if (local < blockDim.x) {
-            jx = s_pos[local].x, jy = s_pos[local].y, jsp = s_sp[local];
-          } else {
-            const float4 pj = __ldg(&pqr[j]);
-            jx = pj.x, jy = pj.y;
-            jsp = __ldg(&species[j]);
-            if (jsp >= kMaxSpecies) jsp = 0;
-          }
+          const float jx = cj.x, jy = cj.y;
+          uint32_t jsp = __float_as_uint(cj.z);
+          if (jsp >= kMaxSpecies) jsp = 0;
           const SpeciesRow& sj = table[jsp];
           const bool me_is_a = i < j;
           const float ax = me_is_a ? me.x : jx, ay = me_is_a ? me.y : jy;
