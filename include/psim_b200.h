@@ -57,7 +57,11 @@ typedef struct {
   float stack_pressure_decay;
   uint32_t parity_mode;     /* 1: IEEE sqrt/div, reference operation order (default); 0: fast math */
   float node_factor;        /* node arena = node_factor * max_bodies + 1024 compact nodes (default 4) */
-  uint32_t reserved[5];
+  uint32_t strict_centres;  /* 1: recompute every internal node's centre with the reference's serial f32
+                               running sums over its body range (quadtree.rs:114-139) - bit-identical to the
+                               reference for leaf_capacity 1, O(N depth) with one thread per node, so slow
+                               for large N; 0 (default): f64 sums carried up the tree */
+  uint32_t reserved[4];
 } psim_config;
 
 /* one row per Species (body/types.rs:12-36), the SpeciesProps columns the path reads (species.rs:7-24) */

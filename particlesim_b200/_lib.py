@@ -31,7 +31,7 @@ class Config(C.Structure):
         ("thread_capacity", C.c_uint32), ("lj_force_max", C.c_float), ("collision_passes", C.c_uint32),
         ("stack_pressure_enabled", C.c_uint32), ("stack_pressure", C.c_float),
         ("stack_pressure_decay", C.c_float), ("parity_mode", C.c_uint32), ("node_factor", C.c_float),
-        ("reserved", C.c_uint32 * 5),
+        ("strict_centres", C.c_uint32), ("reserved", C.c_uint32 * 4),
     ]
 
 

@@ -484,6 +484,10 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
   }
   finalize_nodes_kernel<<<grid_for(ctx, (uint64_t)n * 2, 256, 16), 256, 0, st>>>(ctx->meta, b.pqr, b.accm, ctx->t);
   LAUNCHED(ctx);
+  if (ctx->cfg.strict_centres) {
+    strict_centres_kernel<<<grid_for(ctx, n, 128, 16), 128, 0, st>>>(ctx->meta, b.pqr, b.accm, ctx->t);
+    LAUNCHED(ctx);
+  }
   // traversal arrays (charged nodes only)
   CK(exclusive_scan_dyn(ChargedFlagFn{ctx->t.rec}, &ctx->meta->num_nodes, ctx->node_cap, ctx->trav_rank,
                         ctx->scan_partials, ctx->trav_count, st));
@@ -1141,7 +1145,8 @@ int32_t psim_download_nodes(psim_ctx* ctx, psim_node* out, uint64_t cap, uint64_
     export_root_leaf_kernel<<<1, 32, 0, st>>>(ctx->meta, b.accm, ctx->t);
     LAUNCHED(ctx);
     for (int level = kMaxLevels - 1; level >= 0; --level) {
-      export_level_kernel<<<ctx->sm_count * 8, 128, 0, st>>>(level, ctx->meta, b.pqr, b.accm, ctx->t);
+      export_level_kernel<<<ctx->sm_count * 8, 128, 0, st>>>(level, ctx->meta, b.pqr, b.accm, ctx->t,
+                                                              !ctx->cfg.strict_centres);
       LAUNCHED(ctx);
     }
   }

@@ -211,14 +211,14 @@ __global__ void __launch_bounds__(256)
 // one level of the export sweep (psim_download_nodes only)
 __global__ void __launch_bounds__(128)
     export_level_kernel(int level, const TreeMeta* __restrict__ meta, const float4* __restrict__ pqr,
-                        const float4* __restrict__ accm, TreeArrays t) {
+                        const float4* __restrict__ accm, TreeArrays t, bool write_chargeless_centres) {
   const uint32_t M = meta->num_nodes;
   if (M > t.node_cap) return;
   const uint32_t begin = meta->level_start[level], end = meta->level_start[level + 1];
   const float root_size = meta->root.size;
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t k = begin + blockIdx.x * blockDim.x + threadIdx.x; k < end; k += stride)
-    aggregate_node(t.level_nodes[k], root_size, pqr, accm, t);
+    aggregate_node(t.level_nodes[k], root_size, pqr, accm, t, write_chargeless_centres);
 }
 
 // leaf masses for a tree that is a single leaf (no internal node ever visits it)
@@ -233,6 +233,46 @@ __global__ void export_root_leaf_kernel(const TreeMeta* __restrict__ meta, const
     for (uint32_t b = nb.y; b < nb.y + nb.z; ++b) lm = f_add(lm, accm[b].w);
   t.node_mass[0] = lm;
   t.parent[0] = 0xffffffffu;
+}
+
+// psim_config.strict_centres: the reference's own arithmetic for internal centres - three serial f32
+// running sums over the node's body range in sorted order (quadtree.rs:114-139).  One thread per node.
+__global__ void __launch_bounds__(128)
+    strict_centres_kernel(const TreeMeta* __restrict__ meta, const float4* __restrict__ pqr,
+                          const float4* __restrict__ accm, TreeArrays t) {
+  const uint32_t M = meta->num_nodes;
+  if (M > t.node_cap) return;
+  const uint32_t count = meta->num_internal, n_bodies = meta->n;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) {
+    const uint32_t node = t.level_nodes[k];
+    const uint4 nb = t.nodeB[node];
+    const uint32_t b0 = nb.y, b1 = nb.x < M ? t.nodeB[nb.x].y : n_bodies;
+    float total_mass = 0.0f, total_abs = 0.0f;
+    for (uint32_t b = b0; b < b1; ++b) total_mass = f_add(total_mass, accm[b].w);
+    for (uint32_t b = b0; b < b1; ++b) total_abs = f_add(total_abs, fabsf(pqr[b].z));
+    float wx = 0.0f, wy = 0.0f;
+    if (total_abs > 1e-6f) {
+      for (uint32_t b = b0; b < b1; ++b) {
+        const float4 p = pqr[b];
+        wx = f_add(wx, f_mul(p.x, fabsf(p.z))), wy = f_add(wy, f_mul(p.y, fabsf(p.z)));
+      }
+      wx = f_div(wx, total_abs), wy = f_div(wy, total_abs);
+    } else if (total_mass > 1e-6f) {
+      for (uint32_t b = b0; b < b1; ++b) {
+        const float4 p = pqr[b];
+        const float m = accm[b].w;
+        wx = f_add(wx, f_mul(p.x, m)), wy = f_add(wy, f_mul(p.y, m));
+      }
+      wx = f_div(wx, total_mass), wy = f_div(wy, total_mass);
+    } else if (b1 > b0) {
+      for (uint32_t b = b0; b < b1; ++b) wx = f_add(wx, pqr[b].x), wy = f_add(wy, pqr[b].y);
+      wx = f_div(wx, (float)(b1 - b0)), wy = f_div(wy, (float)(b1 - b0));
+    }
+    float4 a = t.nodeA[node];
+    a.x = wx, a.y = wy;
+    t.nodeA[node] = a;
+  }
 }
 
 // Traversal arrays: the nodes that can contribute to a field sum, i.e. those with a charged body

@@ -257,7 +257,7 @@ PSIM_HD void finalize_node(uint32_t node, uint32_t M, uint32_t n_bodies, float r
 // node mass in the reference's child order, body counts, and the mass-weighted / centroid centre of
 // nodes without charge (quadtree.rs:127-139), which the build leaves at (0, 0).
 PSIM_HD void aggregate_node(uint32_t node, float root_size, const float4* pqr, const float4* accm,
-                            const TreeArrays& t) {
+                            const TreeArrays& t, bool write_chargeless_centres = true) {
   (void)root_size;
   const uint4 nb = t.nodeB[node];
   NodeSums s = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -291,7 +291,7 @@ PSIM_HD void aggregate_node(uint32_t node, float root_size, const float4* pqr, c
   t.sums[node] = s;
   t.node_mass[node] = msum;
   t.nodeB[node].z = count;
-  if (!(t.rec[node].aq > 0.0)) {
+  if (write_chargeless_centres && !(t.rec[node].aq > 0.0)) {
     float px = 0.0f, py = 0.0f;
     if (s.m > (double)1e-6f) {
       px = (float)(s.mx / s.m), py = (float)(s.my / s.m);

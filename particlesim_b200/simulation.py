@@ -180,7 +180,7 @@ class Simulation:
     def __init__(self, bodies: Bodies, domain_width, domain_height, domain_depth=1.0, dt=5.0,
                  theta=1.0, epsilon=2.0, leaf_capacity=1, thread_capacity=1024, config: SimConfig | None = None,
                  device=0, parity_mode=True, node_factor=4.0, species_table=None, max_bodies=None,
-                 max_electrons=None, stream=0):
+                 max_electrons=None, stream=0, strict_centres=False):
         self.lib = _lib.load()
         self.bodies = bodies
         self.domain_width, self.domain_height, self.domain_depth = float(domain_width), float(domain_height), float(domain_depth)
@@ -193,7 +193,7 @@ class Simulation:
         self.cell_list._sim = self
         cfg = _lib.default_config(theta=theta, epsilon=epsilon, leaf_capacity=leaf_capacity,
                                   thread_capacity=thread_capacity, parity_mode=int(parity_mode),
-                                  node_factor=node_factor,
+                                  node_factor=node_factor, strict_centres=int(strict_centres),
                                   stack_pressure_enabled=int(self.config.stack_pressure_enabled),
                                   stack_pressure=self.config.stack_pressure,
                                   stack_pressure_decay=self.config.stack_pressure_decay)

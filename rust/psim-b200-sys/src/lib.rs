@@ -24,7 +24,8 @@ pub struct psim_config {
     pub stack_pressure_decay: f32,
     pub parity_mode: u32,
     pub node_factor: f32,
-    pub reserved: [u32; 5],
+    pub strict_centres: u32,
+    pub reserved: [u32; 4],
 }
 
 #[repr(C)]

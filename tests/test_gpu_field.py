@@ -220,3 +220,35 @@ def test_nonfinite_target_does_not_hang(cuda_device):
     assert np.allclose(f[2], fo[2], rtol=1e-5, atol=1e-9)
     assert not np.all(np.isfinite(f[0]))
     sim.close()
+
+
+@pytest.mark.parametrize("name,gen,mode,theta", [
+    ("uniform_50k", lambda: uniform_pm1(50_000), 0, 1.0),
+    ("electrolyte_50k", lambda: electrolyte(50_000), 1, 0.5),
+    ("clustered_60k", lambda: clustered(60_000), 0, 1.0),
+])
+def test_strict_centres_reproduce_the_reference_bit_for_bit(cuda_device, name, gen, mode, theta):
+    """psim_config.strict_centres + parity_mode 2: node centres by the reference's serial f32 running sums,
+    additions in acc_pos order => every node field and every body's field equals the STRICT oracle's bits"""
+    bodies = gen()
+    sim = make_sim(bodies, theta=theta, parity_mode=2, strict_centres=True)
+    o = oracle_for(bodies, theta=theta)
+    if mode == 0:
+        sim.quadtree.build(sim.bodies)
+        o.build()
+    else:
+        sim.quadtree.build_with_domain(sim.bodies, bodies["hw"], bodies["hh"])
+        o.build_with_domain(bodies["hw"], bodies["hh"])
+    dc, oc = canonical_from_nodes(sim.quadtree.nodes), o.canonical()
+    charged = np.abs(oc["charge"]) >= 0  # every node
+    assert np.array_equal(dc["pos"][charged], oc["pos"][charged]), "node centres differ from the reference's"
+    sim.quadtree.field(sim.bodies, KE)
+    e, _ = o.field(KE)
+    assert np.array_equal(sim.bodies.e_field, e)
+    # the default traversal on the same centres: same interaction sets, different addition order
+    sim2 = make_sim(bodies, theta=theta, parity_mode=1, strict_centres=True)
+    sim2.quadtree.build(sim2.bodies) if mode == 0 else sim2.quadtree.build_with_domain(sim2.bodies, bodies["hw"], bodies["hh"])
+    sim2.quadtree.field(sim2.bodies, KE)
+    assert rel_l2(sim2.bodies.e_field, e) <= TOL
+    sim.close()
+    sim2.close()
