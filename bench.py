@@ -307,8 +307,8 @@ def run_ours(args):
         h_pos, h_vel, h_q = pin(bd["pos"]), pin(bd["vel"]), pin(bd["charge"])
         o_pos, o_vel = torch.empty_like(h_pos).pin_memory(), torch.empty_like(h_vel).pin_memory()
         o_ef = torch.empty_like(h_pos).pin_memory()
-        assert all(t.is_pinned() for t in (h_pos, h_vel, h_q, o_pos, o_vel, o_ef, o_orig))
         o_orig = torch.empty(n, dtype=torch.int32).pin_memory()
+        assert all(t.is_pinned() for t in (h_pos, h_vel, h_q, o_pos, o_vel, o_ef, o_orig))
         ksteps = max(3, min(args.steps, 5))
         ts = []
         for k in range(ksteps + 1):
