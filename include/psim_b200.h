@@ -197,6 +197,10 @@ int32_t psim_prepare_spatial_structures(psim_ctx *ctx, float hw, float hh, float
 /* apply_lj_forces / apply_repulsive_forces / apply_stack_pressure accumulated into acc.
  * Needs a cell grid whose cell_size >= the largest cutoff in use. */
 int32_t psim_short_range(psim_ctx *ctx, uint32_t flags);
+/* forces::apply_polar_forces (forces.rs:52-175), accumulated into acc: EC / DMC bodies with a bound
+ * electron against their neighbours within 3 * radius.  dipole_model 0 = SingleOffset, 1 = ConjugatePair
+ * (the default, config.rs:278-281).  Needs a cell grid (any cell size) built after the last psim_build. */
+int32_t psim_apply_polar_forces(psim_ctx *ctx, float k_e, int32_t dipole_model);
 /* Simulation::iterate (simulation.rs:1437-1486); base damping = damping_base ^ (dt / 0.01) */
 int32_t psim_iterate(psim_ctx *ctx, float dt, float damping_base, float hw, float hh, float hd,
                      int32_t enable_out_of_plane);
@@ -214,7 +218,9 @@ typedef struct {
   uint32_t do_short_range;  /* 0: Coulomb only (config 2) */
   uint32_t do_electrons;    /* second build + electron field sampling + drift */
   uint32_t do_iterate;
-  uint32_t reserved[3];
+  uint32_t do_polar;        /* 1: apply_polar_forces (ConjugatePair) between attract and the LJ pass, on a
+                               grid of the reference's size max(3 * lj, repulsion, lj) (forces.rs:17-22) */
+  uint32_t reserved[2];
 } psim_step_params;
 int32_t psim_step(psim_ctx *ctx, const psim_step_params *p);
 /* Device time of each phase of the last psim_step, in ms (CUDA events on the context's stream;

@@ -325,6 +325,10 @@ inline void attract(Simulation& sim) {  // forces.rs:33-44
                        1, nullptr, nullptr));
   sim.download_fields(false, true, true);
 }
+inline void apply_polar_forces(Simulation& sim, int dipole_model = 1) {  // forces.rs:52-175
+  sim.check(psim_apply_polar_forces(sim.raw(), sim.config.coulomb_constant, dipole_model));
+  sim.download_fields(false, true, false);
+}
 inline void apply_lj_forces(Simulation& sim) {  // forces.rs:182-231
   sim.check(psim_short_range(sim.raw(), PSIM_SR_LJ));
   sim.download_fields(false, true, false);

@@ -991,6 +991,58 @@ void orc_attract(OrcSim *s, float k_e, float bg_x, float bg_y, int threads) {
   for (Body &b : s->bodies) b.acc = (b.charge * b.e_field) / b.mass;
 }
 
+// forces.rs:52-175 (serial).  dipole_model 0 = SingleOffset, 1 = ConjugatePair (the default,
+// config.rs:278-281).  epsilon is config::QUADTREE_EPSILON (config.rs:214), not the tree's.
+void orc_apply_polar_forces(OrcSim *s, int use_cell, float k_e, int dipole_model) {
+  std::vector<Body> &bodies = s->bodies;
+  if (bodies.empty()) return;
+  const float epsilon_sq = 2.0f * 2.0f;
+  std::vector<size_t> neighbors;
+  auto field_from_source = [&](V2 point, float point_radius, V2 src_pos, float src_radius, float src_charge) -> V2 {
+    if (fabsf(src_charge) < FLT_EPSILON) return v2(0, 0);
+    V2 d = point - src_pos;
+    float dist = mag(d);
+    float min_sep = point_radius + src_radius;
+    float r_eff = rmax(dist, min_sep);
+    float denom = (r_eff * r_eff + epsilon_sq) * r_eff;
+    return d * (k_e * src_charge / denom);
+  };
+  for (size_t i = 0; i < bodies.size(); ++i) {
+    if (!(bodies[i].species == 4 || bodies[i].species == 5)) continue;  // EC | DMC
+    if (bodies[i].n_electrons == 0) continue;
+    V2 e_pos = bodies[i].pos + bodies[i].electrons[0].rel_pos;
+    float cutoff = 3.0f * bodies[i].radius;
+    neighbors_of(s, use_cell, i, cutoff, neighbors);
+    for (size_t j : neighbors) {
+      V2 i_nuc_pos = bodies[i].pos;
+      float i_nuc_rad = bodies[i].radius;
+      V2 i_ele_pos = e_pos;
+      V2 j_pos = bodies[j].pos;
+      float j_rad = bodies[j].radius;
+      float j_q = bodies[j].charge;
+      bool j_has_dipole = (bodies[j].species == 4 || bodies[j].species == 5) && bodies[j].n_electrons != 0;
+      V2 j_e_pos = j_has_dipole ? j_pos + bodies[j].electrons[0].rel_pos : j_pos;
+      float j_q_eff = j_has_dipole ? sp(s, bodies[j].species).polar_charge : 0.0f;
+      V2 fnuc = v2(0, 0), fele = v2(0, 0);
+      fnuc = fnuc + field_from_source(i_nuc_pos, i_nuc_rad, j_pos, j_rad, j_q);
+      fele = fele + field_from_source(i_ele_pos, 0.0f, j_pos, j_rad, j_q);
+      if (dipole_model == 1 && j_has_dipole) {
+        fnuc = fnuc + field_from_source(i_nuc_pos, i_nuc_rad, j_pos, j_rad, j_q_eff);
+        fnuc = fnuc - field_from_source(i_nuc_pos, i_nuc_rad, j_e_pos, 0.0f, j_q_eff);
+        fele = fele + field_from_source(i_ele_pos, 0.0f, j_pos, j_rad, j_q_eff);
+        fele = fele - field_from_source(i_ele_pos, 0.0f, j_e_pos, 0.0f, j_q_eff);
+      }
+      if (is_zero(fnuc) && is_zero(fele)) continue;
+      float q_eff_i = sp(s, bodies[i].species).polar_charge;
+      V2 force = (fnuc - fele) * q_eff_i;
+      Body &a = bodies[i];
+      Body &b = bodies[j];
+      a.acc = a.acc + force / a.mass;
+      b.acc = b.acc - force / b.mass;
+    }
+  }
+}
+
 // forces.rs:182-231 (serial)
 void orc_apply_lj_forces(OrcSim *s, int use_cell, float lj_force_max, uint32_t collision_passes) {
   float max_cutoff = max_lj_cutoff(s);

@@ -135,6 +135,8 @@ void orc_reset_acc(OrcSim *);
 void orc_prepare_spatial_structures(OrcSim *, float hw, float hh, float density_threshold,
                                     int threads);
 void orc_attract(OrcSim *, float k_e, float bg_x, float bg_y, int threads);
+/* forces.rs:52-175; dipole_model 0 = SingleOffset, 1 = ConjugatePair (default) */
+void orc_apply_polar_forces(OrcSim *, int use_cell, float k_e, int dipole_model);
 void orc_apply_lj_forces(OrcSim *, int use_cell, float lj_force_max, uint32_t collision_passes);
 void orc_apply_repulsive_forces(OrcSim *, int use_cell);
 void orc_apply_stack_pressure(OrcSim *, int enabled, float pressure, float decay, float hw);

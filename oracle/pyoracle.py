@@ -112,6 +112,7 @@ def load(variant: str = "") -> C.CDLL:
         "orc_reset_acc": (None, [vp]),
         "orc_prepare_spatial_structures": (None, [vp, f, f, f, i]),
         "orc_attract": (None, [vp, f, f, f, i]),
+        "orc_apply_polar_forces": (None, [vp, i, f, i]),
         "orc_apply_lj_forces": (None, [vp, i, f, u32]),
         "orc_apply_repulsive_forces": (None, [vp, i]),
         "orc_apply_stack_pressure": (None, [vp, i, f, f, f]),
@@ -297,6 +298,9 @@ class OracleSim:
 
     def attract(self, k_e, bg=(0.0, 0.0), threads=0):
         self.lib.orc_attract(self.h, k_e, bg[0], bg[1], threads)
+
+    def apply_polar_forces(self, k_e, use_cell=True, dipole_model=1):
+        self.lib.orc_apply_polar_forces(self.h, int(use_cell), k_e, dipole_model)
 
     def apply_lj_forces(self, use_cell=True, lj_force_max=200.0, collision_passes=7):
         self.lib.orc_apply_lj_forces(self.h, int(use_cell), lj_force_max, collision_passes)

@@ -51,7 +51,7 @@ class StepParams(C.Structure):
         ("damping_base", C.c_float), ("k_e", C.c_float), ("bg_x", C.c_float), ("bg_y", C.c_float),
         ("density_threshold", C.c_float), ("enable_out_of_plane", C.c_uint32),
         ("do_short_range", C.c_uint32), ("do_electrons", C.c_uint32), ("do_iterate", C.c_uint32),
-        ("reserved", C.c_uint32 * 3),
+        ("do_polar", C.c_uint32), ("reserved", C.c_uint32 * 2),
     ]
 
 
@@ -106,6 +106,7 @@ SIGNATURES = {
     "psim_use_cell_list": (_i32, [_vp, _f, _f, _f]),
     "psim_prepare_spatial_structures": (_i32, [_vp, _f, _f, _f]),
     "psim_short_range": (_i32, [_vp, _u32]),
+    "psim_apply_polar_forces": (_i32, [_vp, _f, _i32]),
     "psim_iterate": (_i32, [_vp, _f, _f, _f, _f, _f, _i32]),
     "psim_step": (_i32, [_vp, _vp]),
     "psim_phase_times": (_i32, [_vp, _vp]),

@@ -12,6 +12,7 @@
 
 #include "../../include/psim_b200.h"
 #include "cells.cuh"
+#include "polar.cuh"
 #include "sort.cuh"
 #include "traverse.cuh"
 #include "tree.cuh"
@@ -88,6 +89,8 @@ struct psim_ctx {
   // cells
   uint32_t *cell_start = nullptr, *cell_end = nullptr, *order = nullptr, *body_cell = nullptr;
   float4* cpos = nullptr;
+  float4* polarB = nullptr;          // cell-ordered {species | flags, index, electron rel_pos}
+  uint32_t* polar_cutoff = nullptr;  // max 3 * radius over polar bodies with an electron (float bits)
   uint64_t cell_cap = 0;
   GridDims grid = {0, 0, 1.0f, 0.0f, 0.0f};
   int cell_passes = 0;
@@ -656,6 +659,39 @@ int32_t short_range_async(psim_ctx* ctx, uint32_t flags) {
   return PSIM_OK;
 }
 
+int32_t polar_async(psim_ctx* ctx, float k_e, int dipole_model) {
+  const uint32_t n = ctx->n;
+  if (n == 0) return PSIM_OK;
+  if (!ctx->grid_valid)
+    return fail(ctx, PSIM_E_STATE, "psim_apply_polar_forces: no cell grid (call psim_cell_build after the last psim_build)");
+  cudaStream_t st = ctx->stream;
+  BodyArrays& b = ctx->b[ctx->cur];
+  const int e = ctx->ecur;
+  CK(cudaMemsetAsync(ctx->polar_cutoff, 0, sizeof(uint32_t), st));
+  // cell-ordered records; record A reuses the staging area of the short-range pass layout (x, y, charge, radius)
+  int32_t rc = ensure_stage(ctx, (size_t)n * sizeof(float4));
+  if (rc) return rc;
+  float4* recA = static_cast<float4*>(ctx->stage);
+  polar_records_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(ctx->order, n, b.pqr, b.species, b.ecount,
+                                                                ctx->eoff[e], ctx->erel[e], recA, ctx->polarB,
+                                                                ctx->polar_cutoff);
+  LAUNCHED(ctx);
+  PolarParams P;
+  P.g = ctx->grid;
+  P.k_e = k_e;
+  P.epsilon_sq = 2.0f * 2.0f;  // config::QUADTREE_EPSILON squared (forces.rs:60), not the tree's epsilon
+  P.dipole_model = dipole_model;
+  uint32_t first, count;
+  body_range(ctx, first, count);
+  if (count == 0) return PSIM_OK;
+  polar_forces_kernel<<<(count + 127) / 128, 128, 0, st>>>(b.pqr, b.species, b.ecount, ctx->eoff[e], ctx->erel[e],
+                                                           ctx->table_d, first, first + count, ctx->cell_start,
+                                                           ctx->cell_end, recA, ctx->polarB, ctx->body_cell,
+                                                           ctx->polar_cutoff, P, b.accm);
+  LAUNCHED(ctx);
+  return PSIM_OK;
+}
+
 int32_t iterate_async(psim_ctx* ctx, float dt, float damping_base, float hw, float hh, float hd, int enable_z) {
   const uint32_t n = ctx->n;
   if (n == 0) return PSIM_OK;
@@ -706,7 +742,7 @@ void free_all(psim_ctx* c) {
   F(c->t.rec), F(c->t.ndepth);
   F(c->travA), F(c->travB), F(c->trav_rank), F(c->trav_count);
   F(c->perm), F(c->inv);
-  F(c->cell_start), F(c->cell_end), F(c->order), F(c->body_cell), F(c->cpos);
+  F(c->cell_start), F(c->cell_end), F(c->order), F(c->body_cell), F(c->cpos), F(c->polarB), F(c->polar_cutoff);
   F(c->table_d), F(c->stage), F(c->qstage), F(c->step_counter);
 }
 
@@ -787,6 +823,7 @@ int32_t psim_create(int32_t device, uint64_t max_bodies, uint64_t max_electrons,
   ctx->t.node_cap = ctx->node_cap;
   A(&ctx->perm, nb), A(&ctx->inv, nb);
   A(&ctx->order, nb), A(&ctx->body_cell, nb), A(&ctx->cpos, nb);
+  A(&ctx->polarB, nb), A(&ctx->polar_cutoff, 1);
   A(&ctx->table_d, kMaxSpecies), A(&ctx->step_counter, 1);
   if (!ok) {
     cudaGetLastError();
@@ -1328,6 +1365,15 @@ int32_t psim_short_range(psim_ctx* ctx, uint32_t flags) {
   return PSIM_OK;
 }
 
+int32_t psim_apply_polar_forces(psim_ctx* ctx, float k_e, int32_t dipole_model) {
+  if (!ctx) return PSIM_E_ARG;
+  if (dipole_model != 0 && dipole_model != 1) return fail(ctx, PSIM_E_ARG, "psim_apply_polar_forces: dipole_model");
+  int32_t rc = polar_async(ctx, k_e, dipole_model);
+  if (rc) return rc;
+  CK(cudaGetLastError());
+  return PSIM_OK;
+}
+
 int32_t psim_iterate(psim_ctx* ctx, float dt, float damping_base, float hw, float hh, float hd, int32_t enable_z) {
   if (!ctx) return PSIM_E_ARG;
   int32_t rc = iterate_async(ctx, dt, damping_base, hw, hh, hd, enable_z);
@@ -1351,11 +1397,13 @@ int32_t psim_step(psim_ctx* ctx, const psim_step_params* p) {
     // pair sets of the LJ / repulsion passes do not depend on the cell size, so the fused step bins at
     // the largest cutoff those passes use: 9x fewer candidates per body than at 3 x cutoff.
     const float lj_cutoff = max_lj_cutoff(ctx), repulsion_cutoff = max_repulsion_cutoff(ctx);
-    const float cell = fmaxf(repulsion_cutoff, lj_cutoff);
+    const float cell = p->do_polar ? fmaxf(fmaxf(3.0f * lj_cutoff, repulsion_cutoff), lj_cutoff)
+                                   : fmaxf(repulsion_cutoff, lj_cutoff);
     if (cell > 0.0f && (rc = cell_build_async(ctx, p->hw, p->hh, cell))) return rc;
   }
   mark(2);
   if ((rc = field_async(ctx, p->k_e, p->bg_x, p->bg_y, 1))) return rc;
+  if (p->do_polar && p->do_short_range && (rc = polar_async(ctx, p->k_e, 1))) return rc;
   mark(3);
   if (p->do_short_range && (rc = short_range_async(ctx, PSIM_SR_LJ | PSIM_SR_REPULSION | PSIM_SR_STACK_PRESSURE))) return rc;
   mark(4);

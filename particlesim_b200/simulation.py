@@ -325,7 +325,7 @@ class Simulation:
                    self.config.coulomb_constant)
         self.download_electrons()
 
-    def step_params(self, do_short_range=True, do_electrons=True, do_iterate=True) -> "_lib.StepParams":
+    def step_params(self, do_short_range=True, do_electrons=True, do_iterate=True, do_polar=False) -> "_lib.StepParams":
         p = _lib.StepParams()
         p.hw, p.hh, p.hd = self.domain_width, self.domain_height, self.domain_depth
         p.dt, p.damping_base = self.dt, self.config.damping_base
@@ -334,6 +334,7 @@ class Simulation:
         p.density_threshold = self.config.cell_list_density_threshold
         p.enable_out_of_plane = int(self.config.enable_out_of_plane)
         p.do_short_range, p.do_electrons, p.do_iterate = int(do_short_range), int(do_electrons), int(do_iterate)
+        p.do_polar = int(do_polar)
         return p
 
     def step_device(self, params=None):
@@ -357,6 +358,12 @@ class forces:
     def attract(sim: Simulation):
         bg = sim.background_e_field
         sim._call("psim_field", sim.config.coulomb_constant, bg[0], bg[1], 1, _p(sim.bodies.e_field), _p(sim.bodies.acc))
+
+    @staticmethod
+    def apply_polar_forces(sim: Simulation, dipole_model=1):
+        """forces.rs:52-175 (ConjugatePair by default, config.rs:278-281)"""
+        sim._call("psim_apply_polar_forces", sim.config.coulomb_constant, int(dipole_model))
+        sim.download(("acc",))
 
     @staticmethod
     def apply_lj_forces(sim: Simulation):

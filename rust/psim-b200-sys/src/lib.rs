@@ -77,7 +77,8 @@ pub struct psim_step_params {
     pub do_short_range: u32,
     pub do_electrons: u32,
     pub do_iterate: u32,
-    pub reserved: [u32; 3],
+    pub do_polar: u32,
+    pub reserved: [u32; 2],
 }
 
 pub const PSIM_BUILD_CONTAINING: i32 = 0;
@@ -113,6 +114,7 @@ extern "C" {
     pub fn psim_reset_acc(ctx: *mut psim_ctx) -> i32;
     pub fn psim_prepare_spatial_structures(ctx: *mut psim_ctx, hw: f32, hh: f32, density_threshold: f32) -> i32;
     pub fn psim_short_range(ctx: *mut psim_ctx, flags: u32) -> i32;
+    pub fn psim_apply_polar_forces(ctx: *mut psim_ctx, k_e: f32, dipole_model: i32) -> i32;
     pub fn psim_iterate(ctx: *mut psim_ctx, dt: f32, damping_base: f32, hw: f32, hh: f32, hd: f32, enable_out_of_plane: i32) -> i32;
     pub fn psim_step(ctx: *mut psim_ctx, p: *const psim_step_params) -> i32;
     pub fn psim_sync(ctx: *mut psim_ctx) -> i32;

@@ -86,6 +86,7 @@ static void force_phase_in_step_order() {
   sim.reset_acc();
   forces::prepare_spatial_structures(sim);
   forces::attract(sim);
+  forces::apply_polar_forces(sim);
   forces::apply_lj_forces(sim);
   forces::apply_repulsive_forces(sim);
   forces::apply_stack_pressure(sim);

@@ -215,3 +215,56 @@ def test_fused_step_matches_the_call_sequence(cuda_device):
     assert np.array_equal(sb, ebody)
     assert rel_l2(sr, erel) <= TOL and rel_l2(sv, evel) <= TOL
     sim.close()
+
+
+@pytest.mark.parametrize("dipole_model", [1, 0])
+def test_polar_forces(cuda_device, dipole_model):
+    """forces.rs:52-175 (the pass between attract and LJ in Simulation::step), gather form vs the serial loop"""
+    from particlesim_b200 import forces
+    bodies = electrolyte(30_000)
+    hw, hh = bodies["hw"], bodies["hh"]
+    sim = make_sim(bodies)
+    o = oracle_for(bodies, variant="hp")
+    sim.reset_acc()
+    forces.prepare_spatial_structures(sim)
+    forces.attract(sim)
+    before = sim.bodies.acc.copy()
+    forces.apply_polar_forces(sim, dipole_model)
+    o.reset_acc()
+    o.prepare_spatial_structures(hw, hh)
+    o.attract(KE)
+    base = o.get_bodies()["acc"].copy()
+    o.apply_polar_forces(KE, True, dipole_model)
+    ob = o.get_bodies()
+    assert np.array_equal(ob["id"], sim.bodies.id)
+    d_dev, d_ref = sim.bodies.acc - before, ob["acc"] - base
+    assert np.abs(d_ref).max() > 0
+    assert rel_l2(d_dev, d_ref) <= 1e-4  # the increment alone (differences of nearly equal fields)
+    assert rel_l2(sim.bodies.acc, ob["acc"]) <= TOL
+    sim.close()
+
+
+def test_fused_step_with_polar_forces(cuda_device):
+    bodies = electrolyte(30_000)
+    hw, hh = bodies["hw"], bodies["hh"]
+    sim = make_sim(bodies)
+    sim.step_device(sim.step_params(do_polar=True))
+    sim.download(("pos", "vel", "acc"))
+    orig = np.zeros(len(sim.bodies), np.uint32)
+    sim._call("psim_download_bodies", *([None] * 11), orig.ctypes.data)
+    o = oracle_for(bodies, variant="hp")
+    o.reset_acc()
+    o.prepare_spatial_structures(hw, hh)
+    o.attract(KE)
+    o.apply_polar_forces(KE, True, 1)
+    o.apply_lj_forces(True)
+    o.apply_repulsive_forces(True)
+    o.iterate(5.0, 1.0, hw, hh, 1.0, False)
+    o.build_with_domain(hw, hh)
+    o.update_electrons((0.0, 0.0), 5.0, KE, threads=0)
+    ob = o.get_bodies()
+    assert np.array_equal(ob["id"], orig.astype(np.uint64))
+    assert rel_l2(sim.bodies.acc, ob["acc"]) <= TOL
+    assert rel_l2(sim.bodies.vel, ob["vel"]) <= TOL
+    assert rel_l2(sim.bodies.pos, ob["pos"]) <= 1e-6
+    sim.close()
