@@ -1037,6 +1037,7 @@ int32_t psim_update_charges(psim_ctx* ctx, uint64_t n, const float* charge) {
 
 int32_t psim_upload_electrons(psim_ctx* ctx, uint64_t m, const uint32_t* body, const float* rel_xy, const float* vel_xy) {
   if (!ctx) return PSIM_E_ARG;
+  CK(cudaStreamSynchronize(ctx->stream));  // the copies below are synchronous and must not overtake queued work
   if (m > ctx->cap_elec) return fail(ctx, PSIM_E_ARG, "psim_upload_electrons: m exceeds max_electrons");
   if (m && (!body || !rel_xy)) return fail(ctx, PSIM_E_ARG, "psim_upload_electrons: null array");
   const uint32_t n = ctx->n;

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(128)
                            FieldParams P, float2* __restrict__ e_field,
                            float4* __restrict__ acc_mass_out, int write_acc,
                            unsigned long long* __restrict__ step_counter) {
-  const uint32_t M = meta->num_nodes;
+  const uint32_t M = meta->err ? 0u : meta->num_nodes;  // arena overflow: walk nothing
   const uint32_t warps_per_block = blockDim.x >> 5;
   const uint32_t warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const uint32_t total_warps = gridDim.x * warps_per_block;
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(128)
     bh_count_bodies_kernel(const TreeMeta* __restrict__ meta, const float4* __restrict__ nodeA,
                            const uint4* __restrict__ nodeB, const float4* __restrict__ pqr, uint32_t n,
                            FieldParams P, unsigned long long* __restrict__ out4) {
-  const uint32_t M = meta->num_nodes;
+  const uint32_t M = meta->err ? 0u : meta->num_nodes;  // arena overflow: walk nothing
   const uint32_t warps_per_block = blockDim.x >> 5;
   const uint32_t warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const uint32_t total_warps = gridDim.x * warps_per_block;
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(128)
                            const float2* __restrict__ pts, const float* __restrict__ q,
                            const float* __restrict__ radius, uint32_t m, FieldParams P,
                            float2* __restrict__ out, unsigned long long* __restrict__ step_counter) {
-  const uint32_t M = meta->num_nodes;
+  const uint32_t M = meta->err ? 0u : meta->num_nodes;  // arena overflow: walk nothing
   const uint32_t warps_per_block = blockDim.x >> 5;
   const uint32_t warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const uint32_t total_warps = gridDim.x * warps_per_block;

@@ -286,10 +286,15 @@ struct ChargedFlagFn {
 __global__ void __launch_bounds__(256)
     compact_traversal_kernel(const TreeMeta* __restrict__ meta, const float4* __restrict__ nodeA,
                              const uint4* __restrict__ nodeB, const uint32_t* __restrict__ rank,
-                             const uint32_t* __restrict__ total, uint32_t node_cap,
+                             uint32_t* __restrict__ total, uint32_t node_cap,
                              float4* __restrict__ travA, uint4* __restrict__ travB) {
   const uint32_t M = meta->num_nodes;
-  if (M > node_cap) return;
+  if (M > node_cap) {
+    // arena overflow (flagged in meta->err): leave an empty traversal tree so that a chained field
+    // pass walks nothing instead of walking stale records
+    if (blockIdx.x == 0 && threadIdx.x == 0) *total = 0;
+    return;
+  }
   const uint32_t T = *total;
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < M; n += stride) {

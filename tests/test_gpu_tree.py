@@ -167,3 +167,18 @@ def test_node_arena_overflow_is_an_error(cuda_device):
         # node_factor 1.0 => arena of n + 1024 nodes < 1.7 n
         sim.quadtree.build(sim.bodies)
     assert e.value.code == -4
+
+
+def test_fused_step_survives_arena_overflow(cuda_device):
+    """psim_step does not synchronise: on an arena overflow the field passes must walk nothing (not stale
+    records) and the error must be reported by the next status call"""
+    from particlesim_b200 import PsimError
+    bodies = clustered(5000)
+    for mode in (1, 2):
+        sim = make_sim(bodies, node_factor=1.0, parity_mode=mode)
+        sim.step_device(sim.step_params(do_electrons=False))
+        sim.sync()
+        with pytest.raises(PsimError) as e:
+            sim._call("psim_build_status")
+        assert e.value.code == -4
+        sim.close()
