@@ -223,6 +223,25 @@ typedef struct {
   uint32_t reserved[2];
 } psim_step_params;
 int32_t psim_step(psim_ctx *ctx, const psim_step_params *p);
+/* The same step for a caller whose Vec<Body> lives in host memory (the reference's Simulation owns its
+ * bodies on the host, simulation.rs:40-60): psim_update_state + psim_step + the read-back of the
+ * results in one call, with the transfers pipelined against the device work.
+ *   in : positions are copied first; charges and velocities follow on a copy stream while the keys are
+ *        generated and sorted, and are applied where the step first needs them;
+ *   out: each result leaves on a second copy stream as soon as it is final (original indices after the
+ *        first build, fields after the traversal, positions and velocities after the integrator),
+ *        underneath the second build and the electron field sampling.
+ * Row order: the outputs are in the body order of the step's first build (the order quadtree.build
+ * leaves in Vec<Body>, simulation.rs:1004), out_orig_index[i] = the upload index of row i.  The inputs
+ * of the next psim_step_host call are in the order of these outputs (the first call: the order the
+ * device holds, i.e. the upload order or the last downloaded order); the context keeps the extra
+ * permutation of the electron pass to itself.  Any other call that reads or writes bodies sees the
+ * device order: follow it with psim_download_bodies before mixing the two styles.
+ * Host arrays should be page-locked (cudaHostAlloc / cudaHostRegister) or the copies serialise.
+ * Optional arrays may be NULL.  Synchronises, and returns the build status (PSIM_E_NODE_OVERFLOW ...). */
+int32_t psim_step_host(psim_ctx *ctx, const psim_step_params *p, uint64_t n, const float *pos_xy,
+                       const float *vel_xy_opt, const float *charge_opt, float *out_pos_xy_opt,
+                       float *out_vel_xy_opt, float *out_e_field_xy_opt, uint32_t *out_orig_index_opt);
 /* Device time of each phase of the last psim_step, in ms (CUDA events on the context's stream;
  * synchronises).  Names follow the reference's profile scopes (src/profiler.rs users):
  * [0] quadtree_build  [1] cell_list_rebuild  [2] quadtree_field (+attract)  [3] forces_lj/repulsion

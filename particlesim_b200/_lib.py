@@ -109,6 +109,7 @@ SIGNATURES = {
     "psim_apply_polar_forces": (_i32, [_vp, _f, _i32]),
     "psim_iterate": (_i32, [_vp, _f, _f, _f, _f, _f, _i32]),
     "psim_step": (_i32, [_vp, _vp]),
+    "psim_step_host": (_i32, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "psim_phase_times": (_i32, [_vp, _vp]),
     "psim_set_target_range": (_i32, [_vp, _u64, _u64]),
     "psim_set_electron_range": (_i32, [_vp, _u64, _u64]),

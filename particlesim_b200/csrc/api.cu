@@ -89,6 +89,9 @@ struct psim_ctx {
   // cells
   uint32_t *cell_start = nullptr, *cell_end = nullptr, *order = nullptr, *body_cell = nullptr;
   float4* cpos = nullptr;
+  uint32_t* cell_off = nullptr;      // monotone per-cell offsets (ncells + 1), built on demand
+  bool cell_off_valid = false;
+  uint32_t species_present = 0;      // bit s: some uploaded body has species s
   float4* polarB = nullptr;          // cell-ordered {species | flags, index, electron rel_pos}
   uint32_t* polar_cutoff = nullptr;  // max 3 * radius over polar bodies with an electron (float bits)
   uint64_t cell_cap = 0;
@@ -114,6 +117,25 @@ struct psim_ctx {
   uint32_t tgt_first = 0, tgt_count = 0, e_first = 0, e_count = 0;
   cudaEvent_t ev[9] = {};
   bool ev_ok = false, ev_recorded = false;
+  // psim_step_host: copy streams, their events, a private staging area and the plan of the call in flight
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_q = nullptr, ev_vel = nullptr, ev_mid = nullptr, ev_out = nullptr;
+  void* hstage = nullptr;
+  size_t hstage_bytes = 0;
+  // row of the caller's arrays (the order of the previous call's outputs) that device row i holds;
+  // valid from a call whose electron pass re-sorted the bodies until the next build
+  uint32_t* host_map = nullptr;
+  bool host_map_valid = false;
+  struct HostedStep {
+    bool active = false;
+    const float* late_q = nullptr;      // staged charges, applied before the first gather
+    const float2* late_vel = nullptr;   // staged velocities, applied before the integrator
+    const float* vel_src = nullptr;     // host velocities whose copy has not been queued yet
+    const uint32_t* map = nullptr;      // host_map while the inputs are applied (null: identity)
+    float2 *s_pos = nullptr, *s_vel = nullptr;  // device staging of the unpacked outputs
+    float *out_pos = nullptr, *out_vel = nullptr, *out_ef = nullptr;
+    uint32_t* out_orig = nullptr;
+  } hosted;
 };
 
 namespace {
@@ -207,6 +229,39 @@ __global__ void __launch_bounds__(256)
       v.x = vel[i].x, v.y = vel[i].y;
       velz[i] = v;
     }
+  }
+}
+
+// psim_step_host: the pieces of a pipelined state refresh.  `map` (may be null) is the caller's row of
+// each device row; velocities arrive after the first gather, so they also go through its permutation.
+__global__ void __launch_bounds__(256)
+    hosted_positions_kernel(const float2* pos, const uint32_t* map, uint32_t n, float4* pqr) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float2 p = pos[map ? map[i] : i];
+    pqr[i].x = p.x, pqr[i].y = p.y;
+  }
+}
+__global__ void __launch_bounds__(256)
+    hosted_charges_kernel(const float* q, const uint32_t* map, uint32_t n, float4* pqr) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) pqr[i].z = q[map ? map[i] : i];
+}
+__global__ void __launch_bounds__(256)
+    hosted_velocities_kernel(const float2* vel, const uint32_t* perm, const uint32_t* map, uint32_t n, float4* velz) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t s = perm[i];
+    const float2 v = vel[map ? map[s] : s];
+    velz[i].x = v.x, velz[i].y = v.y;
+  }
+}
+__global__ void __launch_bounds__(256)
+    hosted_unpack_kernel(const float4* pqr, const float4* velz, uint32_t n, float2* pos, float2* vel) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (pos) pos[i] = make_float2(pqr[i].x, pqr[i].y);
+    if (vel) vel[i] = make_float2(velz[i].x, velz[i].y);
   }
 }
 
@@ -427,6 +482,7 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
   cudaStream_t st = ctx->stream;
   ctx->tree_valid = false;
   ctx->perm_valid = false;
+  ctx->host_map_valid = false;
   ctx->grid_valid = false;  // the cell list indexes bodies by position in the array
   if (n == 0) {
     CK(cudaMemsetAsync(ctx->meta, 0, sizeof(TreeMeta), st));
@@ -450,6 +506,22 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
   CK(onesweep_sort<uint64_t>(ctx->keys[0], ctx->keys[1], ctx->idx[0], ctx->idx[1], n, 0, kTreePasses,
                              ctx->sc, ctx->sm_count, st));
   ctx->launches += 2 + kTreePasses;
+  if (ctx->hosted.active && ctx->hosted.late_q) {  // psim_step_host: the charges arrived during the sort
+    CK(cudaStreamWaitEvent(st, ctx->ev_q, 0));
+    hosted_charges_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(ctx->hosted.late_q, ctx->hosted.map, n, in.pqr);
+    LAUNCHED(ctx);
+    ctx->hosted.late_q = nullptr;
+  }
+  if (ctx->hosted.active && ctx->hosted.vel_src) {
+    // the velocities are not needed before the integrator: their copy starts here, so that it neither
+    // shares the link with the positions and charges nor delays their completion event
+    CK(cudaEventRecord(ctx->ev_start, st));
+    CK(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_start, 0));
+    CK(cudaMemcpyAsync(const_cast<float2*>(ctx->hosted.late_vel), ctx->hosted.vel_src, 8 * (size_t)n,
+                       cudaMemcpyHostToDevice, ctx->copy_in));
+    CK(cudaEventRecord(ctx->ev_vel, ctx->copy_in));
+    ctx->hosted.vel_src = nullptr;
+  }
   gather_bodies_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(
       ctx->idx[0], ctx->idx[1], ctx->tree_plan, kTreePasses, n, in, out, ctx->perm, ctx->inv);
   LAUNCHED(ctx);
@@ -507,6 +579,7 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
 int32_t cell_build_async(psim_ctx* ctx, float hw, float hh, float cell_size) {
   cudaStream_t st = ctx->stream;
   ctx->grid_valid = false;
+  ctx->cell_off_valid = false;
   // cell_list.rs:28-29
   const float fx = ceilf((2.0f * hw) / cell_size), fy = ceilf((2.0f * hh) / cell_size);
   if (!(fx >= 0.0f) || !(fy >= 0.0f) || !(cell_size > 0.0f)) return fail(ctx, PSIM_E_ARG, "cell grid: bad domain or cell size");
@@ -517,9 +590,11 @@ int32_t cell_build_async(psim_ctx* ctx, float hw, float hh, float cell_size) {
     const uint64_t need = (uint64_t)(gxd * gyd);
     if (ctx->cell_start) cudaFree(ctx->cell_start);
     if (ctx->cell_end) cudaFree(ctx->cell_end);
-    ctx->cell_start = ctx->cell_end = nullptr;
+    if (ctx->cell_off) cudaFree(ctx->cell_off);
+    ctx->cell_start = ctx->cell_end = ctx->cell_off = nullptr;
     ctx->cell_cap = 0;
     cudaError_t e1 = dalloc(&ctx->cell_start, need + 1), e2 = dalloc(&ctx->cell_end, need + 1);
+    if (e1 == cudaSuccess) e1 = dalloc(&ctx->cell_off, need + 2);
     if (e1 != cudaSuccess || e2 != cudaSuccess) return fail(ctx, PSIM_E_OOM, "cell arrays", e1 != cudaSuccess ? e1 : e2);
     ctx->cell_cap = need;
   }
@@ -632,29 +707,47 @@ int32_t short_range_async(psim_ctx* ctx, uint32_t flags) {
   if (n == 0) return PSIM_OK;
   ShortRangeParams P;
   memset(&P, 0, sizeof(P));
+  // cutoffs over the species table (species.rs:412-479); a pass is a no-op when no uploaded body
+  // belongs to a species it applies to (apply_lj_forces / apply_repulsive_forces skip such bodies)
   const float lj_cut = max_lj_cutoff(ctx), rep_cut = max_repulsion_cutoff(ctx);
-  P.do_lj = (flags & PSIM_SR_LJ) && lj_cut > 0.0f;
-  P.do_rep = (flags & PSIM_SR_REPULSION) && rep_cut > 0.0f;  // forces.rs:252-255
+  bool lj_present = false, rep_present = false;
+  for (uint32_t sp = 0; sp < ctx->nspecies; ++sp) {
+    if (!(ctx->species_present >> sp & 1u)) continue;
+    lj_present |= ctx->table_h[sp].lj_enabled != 0;
+    rep_present |= ctx->table_h[sp].repulsion_enabled != 0;
+  }
+  P.do_lj = (flags & PSIM_SR_LJ) && lj_cut > 0.0f && lj_present;
+  P.do_rep = (flags & PSIM_SR_REPULSION) && rep_cut > 0.0f && rep_present;  // forces.rs:252-255
   P.do_stack = (flags & PSIM_SR_STACK_PRESSURE) && ctx->cfg.stack_pressure_enabled && ctx->cfg.stack_pressure > 0.0f;
   if (!P.do_lj && !P.do_rep && !P.do_stack) return PSIM_OK;
   if ((P.do_lj || P.do_rep) && !ctx->grid_valid)
     return fail(ctx, PSIM_E_STATE, "psim_short_range: no cell grid (call psim_cell_build after the last psim_build)");
   P.g = ctx->grid;
-  if (!ctx->grid_valid) P.g.hw = 0.f;
+  if (!ctx->grid_valid) P.g.hw = 0.f, P.g.gx = P.g.gy = 1;
   P.max_lj_cutoff = lj_cut;
+  P.max_rep_cutoff = P.do_rep ? rep_cut : 0.0f;
   P.max_lj_force = (float)ctx->cfg.collision_passes * ctx->cfg.lj_force_max;
   P.stack_pressure = ctx->cfg.stack_pressure;
   P.stack_decay = ctx->cfg.stack_pressure_decay;
+  if (!ctx->grid_valid && P.do_stack) P.g.hw = ctx->grid.hw;
   const float reach = fmaxf(P.do_lj ? lj_cut : 0.0f, P.do_rep ? rep_cut : 0.0f);
   P.range = (P.do_lj || P.do_rep) ? (int)ceilf(reach / ctx->grid.cell_size) : 0;
   if (P.range < 0) P.range = 0;
   BodyArrays& b = ctx->b[ctx->cur];
+  if ((P.do_lj || P.do_rep) && !ctx->cell_off_valid) {
+    const uint64_t ncells = (uint64_t)ctx->grid.gx * ctx->grid.gy;
+    int32_t rc = ensure_qstage(ctx, ((size_t)scan_num_tiles((uint32_t)ncells) + 2) * sizeof(uint32_t));
+    if (rc) return rc;
+    CK(exclusive_scan(CellCountFn{ctx->cell_start, ctx->cell_end}, (uint32_t)ncells, ctx->cell_off,
+                      static_cast<uint32_t*>(ctx->qstage), ctx->cell_off + ncells, ctx->stream));
+    ctx->launches += 3;
+    ctx->cell_off_valid = true;
+  }
   uint32_t first, count;
   body_range(ctx, first, count);
   if (count == 0) return PSIM_OK;
   short_range_kernel<<<(count + 127) / 128, 128, 0, ctx->stream>>>(
-      b.pqr, b.species, ctx->table_d, first, first + count, ctx->cell_start, ctx->cell_end, ctx->cpos,
-      ctx->body_cell, P, b.accm);
+      b.pqr, b.species, ctx->table_d, first, first + count, ctx->cell_off, ctx->cpos, ctx->body_cell, P, b.accm);
   LAUNCHED(ctx);
   return PSIM_OK;
 }
@@ -742,7 +835,7 @@ void free_all(psim_ctx* c) {
   F(c->t.rec), F(c->t.ndepth);
   F(c->travA), F(c->travB), F(c->trav_rank), F(c->trav_count);
   F(c->perm), F(c->inv);
-  F(c->cell_start), F(c->cell_end), F(c->order), F(c->body_cell), F(c->cpos), F(c->polarB), F(c->polar_cutoff);
+  F(c->cell_start), F(c->cell_end), F(c->order), F(c->body_cell), F(c->cpos), F(c->polarB), F(c->polar_cutoff), F(c->cell_off);
   F(c->table_d), F(c->stage), F(c->qstage), F(c->step_counter);
 }
 
@@ -850,6 +943,12 @@ int32_t psim_destroy(psim_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->ev_ok)
     for (int k = 0; k < 9; ++k) cudaEventDestroy(ctx->ev[k]);
+  if (ctx->copy_in) cudaStreamSynchronize(ctx->copy_in), cudaStreamDestroy(ctx->copy_in);
+  if (ctx->copy_out) cudaStreamSynchronize(ctx->copy_out), cudaStreamDestroy(ctx->copy_out);
+  for (cudaEvent_t e : {ctx->ev_start, ctx->ev_q, ctx->ev_vel, ctx->ev_mid, ctx->ev_out})
+    if (e) cudaEventDestroy(e);
+  if (ctx->hstage) cudaFree(ctx->hstage);
+  if (ctx->host_map) cudaFree(ctx->host_map);
   free_all(ctx);
   delete ctx;
   return PSIM_OK;
@@ -1000,6 +1099,12 @@ int32_t psim_upload_bodies(psim_ctx* ctx, uint64_t n, const float* pos_xy, const
   r.radius = static_cast<const float*>(up(radius, o_r, 4 * n));
   r.charge = static_cast<const float*>(up(charge, o_q, 4 * n));
   r.species = static_cast<const uint8_t*>(up(species, o_s, n));
+  ctx->species_present = 0;
+  if (species) {
+    for (uint64_t i = 0; i < n; ++i) ctx->species_present |= 1u << (species[i] < kMaxSpecies ? species[i] : 0);
+  } else {
+    ctx->species_present = 1u;
+  }
   CK(cudaGetLastError());
   if (!r.pos) return fail(ctx, PSIM_E_CUDA, "psim_upload_bodies: host to device copy failed");
   pack_bodies_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(r, (uint32_t)n, ctx->b[ctx->cur]);
@@ -1383,15 +1488,25 @@ int32_t psim_iterate(psim_ctx* ctx, float dt, float damping_base, float hw, floa
   return PSIM_OK;
 }
 
-int32_t psim_step(psim_ctx* ctx, const psim_step_params* p) {
-  if (!ctx || !p) return PSIM_E_ARG;
+static int32_t step_async(psim_ctx* ctx, const psim_step_params* p) {
   int32_t rc;
   auto mark = [&](int k) {
     if (ctx->ev_ok) cudaEventRecord(ctx->ev[k], ctx->stream);
   };
+  // psim_step_host: results leave on the copy stream as soon as the main stream has produced them
+  psim_ctx::HostedStep& H = ctx->hosted;
+  const uint64_t n = ctx->n;
+  auto results_from_here = [&]() {
+    cudaEventRecord(ctx->ev_mid, ctx->stream);
+    cudaStreamWaitEvent(ctx->copy_out, ctx->ev_mid, 0);
+  };
   mark(0);
   if ((rc = psim_reset_acc(ctx))) return rc;
   if ((rc = build_async(ctx, PSIM_BUILD_CONTAINING, 0.f, 0.f))) return rc;
+  if (H.active && H.out_orig) {
+    results_from_here();
+    cudaMemcpyAsync(H.out_orig, ctx->b[ctx->cur].orig, 4 * n, cudaMemcpyDeviceToHost, ctx->copy_out);
+  }
   mark(1);
   if (p->do_short_range) {
     // The reference sizes its grid for the polar pass too (3 x the LJ cutoff, forces.rs:17-22).  The
@@ -1404,11 +1519,32 @@ int32_t psim_step(psim_ctx* ctx, const psim_step_params* p) {
   }
   mark(2);
   if ((rc = field_async(ctx, p->k_e, p->bg_x, p->bg_y, 1))) return rc;
+  if (H.active && H.out_ef) {
+    results_from_here();
+    cudaMemcpyAsync(H.out_ef, ctx->b[ctx->cur].efield, 8 * n, cudaMemcpyDeviceToHost, ctx->copy_out);
+  }
   if (p->do_polar && p->do_short_range && (rc = polar_async(ctx, p->k_e, 1))) return rc;
   mark(3);
   if (p->do_short_range && (rc = short_range_async(ctx, PSIM_SR_LJ | PSIM_SR_REPULSION | PSIM_SR_STACK_PRESSURE))) return rc;
   mark(4);
+  if (H.active && H.late_vel) {  // the velocities have had the whole force phase to arrive
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_vel, 0));
+    hosted_velocities_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, ctx->stream>>>(H.late_vel, ctx->perm, H.map, (uint32_t)n,
+                                                                               ctx->b[ctx->cur].velz);
+    LAUNCHED(ctx);
+    H.late_vel = nullptr;
+  }
   if (p->do_iterate && (rc = iterate_async(ctx, p->dt, p->damping_base, p->hw, p->hh, p->hd, (int)p->enable_out_of_plane))) return rc;
+  if (H.active && (H.out_pos || H.out_vel)) {
+    results_from_here();
+    BodyArrays& b = ctx->b[ctx->cur];
+    hosted_unpack_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, ctx->copy_out>>>(b.pqr, b.velz, (uint32_t)n,
+                                                                             H.out_pos ? H.s_pos : nullptr,
+                                                                             H.out_vel ? H.s_vel : nullptr);
+    LAUNCHED(ctx);
+    if (H.out_pos) cudaMemcpyAsync(H.out_pos, H.s_pos, 8 * n, cudaMemcpyDeviceToHost, ctx->copy_out);
+    if (H.out_vel) cudaMemcpyAsync(H.out_vel, H.s_vel, 8 * n, cudaMemcpyDeviceToHost, ctx->copy_out);
+  }
   mark(5);
   if (p->do_electrons) {
     if ((rc = build_async(ctx, PSIM_BUILD_DOMAIN, p->hw, p->hh))) return rc;
@@ -1421,6 +1557,91 @@ int32_t psim_step(psim_ctx* ctx, const psim_step_params* p) {
   ctx->ev_recorded = ctx->ev_ok;
   CK(cudaGetLastError());
   return PSIM_OK;
+}
+
+int32_t psim_step(psim_ctx* ctx, const psim_step_params* p) {
+  if (!ctx || !p) return PSIM_E_ARG;
+  return step_async(ctx, p);
+}
+
+// One hot-path step for a caller whose bodies live in host memory: the state refresh, psim_step and
+// the read-back of the results, pipelined against the device work.
+//   in : positions first, on the main stream (the build needs them at once); charges and velocities
+//        follow on a copy stream and are applied where they are first needed — the charges before the
+//        bodies are gathered into tree order, the velocities before the integrator;
+//   out: every result leaves on a second copy stream as soon as it is final — the original indices
+//        after the first build, the fields after the traversal, positions and velocities after the
+//        integrator — underneath the second build and the electron field sampling.
+// The outputs are therefore in the body order of the step's FIRST build; the electron pass re-sorts the
+// device arrays afterwards, and its permutation is kept (host_map) so that the next call, whose inputs
+// are in the order of these outputs, lands every row on the right body.
+int32_t psim_step_host(psim_ctx* ctx, const psim_step_params* p, uint64_t n, const float* pos_xy,
+                       const float* vel_xy, const float* charge, float* out_pos_xy, float* out_vel_xy,
+                       float* out_e_field_xy, uint32_t* out_orig_index) {
+  if (!ctx || !p) return PSIM_E_ARG;
+  if (n != ctx->n || (n && !pos_xy)) return fail(ctx, PSIM_E_ARG, "psim_step_host: size mismatch");
+  if (ctx->tgt_set || ctx->etgt_set) return fail(ctx, PSIM_E_STATE, "psim_step_host: not available on a sharded context");
+  if (n == 0) return step_async(ctx, p);
+  if (!ctx->copy_in) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    bool ok = cudaStreamCreateWithPriority(&ctx->copy_in, cudaStreamNonBlocking, hi) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&ctx->copy_out, cudaStreamNonBlocking, hi) == cudaSuccess;
+    for (cudaEvent_t* e : {&ctx->ev_start, &ctx->ev_q, &ctx->ev_vel, &ctx->ev_mid, &ctx->ev_out})
+      ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->host_map, (size_t)ctx->cap_bodies * sizeof(uint32_t)) == cudaSuccess;
+    if (!ok) return fail(ctx, PSIM_E_CUDA, "psim_step_host: copy streams", cudaGetLastError());
+  }
+  const size_t o_pos = 0, o_vel = align256(8 * n), o_q = o_vel + align256(8 * n), o_opos = o_q + align256(4 * n),
+               o_ovel = o_opos + align256(8 * n), total = o_ovel + align256(8 * n);
+  if (total > ctx->hstage_bytes) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->hstage) cudaFree(ctx->hstage);
+    ctx->hstage = nullptr, ctx->hstage_bytes = 0;
+    cudaError_t e = cudaMalloc(&ctx->hstage, total);
+    if (e != cudaSuccess) return fail(ctx, PSIM_E_OOM, "psim_step_host: staging", e);
+    ctx->hstage_bytes = total;
+  }
+  char* sb = static_cast<char*>(ctx->hstage);
+  cudaStream_t st = ctx->stream;
+  psim_ctx::HostedStep& H = ctx->hosted;
+  H = psim_ctx::HostedStep();
+  H.map = ctx->host_map_valid ? ctx->host_map : nullptr;
+  H.s_pos = reinterpret_cast<float2*>(sb + o_opos), H.s_vel = reinterpret_cast<float2*>(sb + o_ovel);
+  H.out_pos = out_pos_xy, H.out_vel = out_vel_xy, H.out_ef = out_e_field_xy, H.out_orig = out_orig_index;
+  // the late inputs queue up behind the positions so that they do not share the link with them
+  CK(cudaMemcpyAsync(sb + o_pos, pos_xy, 8 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(ctx->ev_start, st));
+  CK(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_start, 0));
+  hosted_positions_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(reinterpret_cast<const float2*>(sb + o_pos), H.map,
+                                                                     (uint32_t)n, ctx->b[ctx->cur].pqr);
+  LAUNCHED(ctx);
+  ctx->tree_valid = ctx->grid_valid = false;
+  if (charge) {
+    CK(cudaMemcpyAsync(sb + o_q, charge, 4 * n, cudaMemcpyHostToDevice, ctx->copy_in));
+    CK(cudaEventRecord(ctx->ev_q, ctx->copy_in));
+    H.late_q = reinterpret_cast<const float*>(sb + o_q);
+  }
+  if (vel_xy) {  // queued by the first build, see build_async
+    H.vel_src = vel_xy;
+    H.late_vel = reinterpret_cast<const float2*>(sb + o_vel);
+  }
+  H.active = true;
+  int32_t rc = step_async(ctx, p);
+  H.active = false;
+  if (rc) {
+    cudaStreamSynchronize(ctx->copy_in), cudaStreamSynchronize(ctx->copy_out), cudaStreamSynchronize(st);
+    return rc;
+  }
+  if (p->do_electrons) {  // the device rows moved once more: remember where the caller's rows went
+    CK(cudaMemcpyAsync(ctx->host_map, ctx->perm, 4 * n, cudaMemcpyDeviceToDevice, st));
+    ctx->host_map_valid = true;
+  }
+  CK(cudaEventRecord(ctx->ev_out, ctx->copy_out));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventSynchronize(ctx->ev_out));
+  return check_build(ctx);
 }
 
 int32_t psim_set_target_range(psim_ctx* ctx, uint64_t first, uint64_t count) {

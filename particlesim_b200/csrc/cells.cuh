@@ -81,6 +81,7 @@ struct ShortRangeParams {
   float max_lj_force;    // COLLISION_PASSES as f32 * LJ_FORCE_MAX (forces.rs:221)
   float stack_pressure, stack_decay;
   int range;             // cells to scan on each side: ceil(max cutoff / cell_size)
+  float max_rep_cutoff;  // species.rs:447-479 (0 when the repulsion pass is off)
 };
 
 // Vec2::normalized() of ultraviolet 0.9.2: multiply by 1/mag
@@ -142,73 +143,155 @@ __device__ __forceinline__ void rep_pair(const SpeciesRow& sa, const SpeciesRow&
   }
 }
 
-// Gather form of the reference's serial pair loops: each body sums the terms of every pair it is
-// in.  One CTA handles a run of consecutive bodies (Morton order => a compact patch); partner data
-// is read from `cpos`, the cell-ordered copy of {x, y, species, index}, so each neighbouring cell is
-// one contiguous run of 16-byte records that the patch's threads share through L1.
+// per-cell body counts, summed into the monotone offsets array `cell_off` (ncells + 1 entries) that
+// makes every row segment of the grid one contiguous run of the cell-ordered records
+struct CellCountFn {
+  const uint32_t* cell_start;
+  const uint32_t* cell_end;
+  __device__ __forceinline__ uint32_t operator()(uint32_t c) const { return cell_end[c] - cell_start[c]; }
+};
+
+// Gather form of the reference's serial pair loops (forces.rs:182-289): each body sums the terms of
+// every pair it is in, in the reference's neighbour order (rows dy, cells dx, index order inside a cell).
+//
+// Shared-memory tile staging: a CTA owns 128 consecutive bodies, a compact patch in Morton order.  It
+// takes the bounding box of their cells, grows it by the interaction range, and stages every record of
+// that box of cells — {x, y, species, index}, one contiguous global run per grid row — plus the box's
+// cell offsets into shared memory; the pair loops then read neighbours from shared memory only, one
+// contiguous run per row.  A patch whose box is larger than the tile limits (a strip of far-apart
+// bodies, e.g. at a curve discontinuity) falls back to reading the same runs from global memory.
+constexpr int kTileMaxW = 32, kTileMaxH = 32, kTileCap = 768;
+
 __global__ void __launch_bounds__(128)
     short_range_kernel(const float4* __restrict__ pqr, const uint8_t* __restrict__ species,
                        const SpeciesRow* __restrict__ table_g, uint32_t first, uint32_t n,
-                       const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end,
-                       const float4* __restrict__ cpos, const uint32_t* __restrict__ body_cell,
-                       ShortRangeParams P, float4* __restrict__ acc_mass) {
+                       const uint32_t* __restrict__ cell_off, const float4* __restrict__ cpos,
+                       const uint32_t* __restrict__ body_cell, ShortRangeParams P,
+                       float4* __restrict__ acc_mass) {
   __shared__ SpeciesRow table[kMaxSpecies];
+  __shared__ float4 s_rec[kTileCap];
+  __shared__ uint16_t s_off[(kTileMaxW + 1) * kTileMaxH];  // offsets into s_rec (kTileCap < 65536)
+  __shared__ uint32_t s_rowsrc[kTileMaxH], s_rowbase[kTileMaxH + 1];
+  __shared__ int s_box[4];  // min x, max x, min y, max y of the cells of the bodies that have pair work
+  __shared__ int s_fits;
   for (int k = threadIdx.x; k < kMaxSpecies * (int)(sizeof(SpeciesRow) / 4); k += blockDim.x)
     reinterpret_cast<uint32_t*>(table)[k] = reinterpret_cast<const uint32_t*>(table_g)[k];
-  const uint32_t block_first = first + blockIdx.x * blockDim.x;  // bodies [first, n) of this rank
-  const uint32_t i = block_first + threadIdx.x;
+  if (threadIdx.x == 0) s_box[0] = 0x7fffffff, s_box[1] = -1, s_box[2] = 0x7fffffff, s_box[3] = -1, s_fits = 0;
+  const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n;
   float4 me = make_float4(0, 0, 0, 0);
-  uint8_t my_sp = 0;
-  if (i < n) {
+  uint32_t my_sp = 0;
+  if (live) {
     me = pqr[i];
     my_sp = species[i] < kMaxSpecies ? species[i] : 0;
   }
   __syncthreads();
-  if (i >= n) return;
   const SpeciesRow si = table[my_sp];
-  float4 am = acc_mass[i];
-  const bool lj_i = P.do_lj && si.lj_enabled;
-  const bool rep_i = P.do_rep;
-  if (lj_i || rep_i) {
+  const bool lj_i = live && P.do_lj && si.lj_enabled;
+  const bool rep_i = live && P.do_rep && si.repulsion_enabled;
+  const bool need = lj_i || rep_i;
+  int cx = 0, cy = 0;
+  if (need) {
     const uint32_t c = body_cell[i];
-    const int cx = (int)(c % P.g.gx), cy = (int)(c / P.g.gx);
-    const float lj_cut_sq = __fmul_rn(P.max_lj_cutoff, P.max_lj_cutoff);
-    float ljx = 0.0f, ljy = 0.0f, rpx = 0.0f, rpy = 0.0f;
-    for (int dy = -P.range; dy <= P.range; ++dy) {
-      const int y = cy + dy;
-      if (y < 0 || y >= (int)P.g.gy) continue;
-      for (int dx = -P.range; dx <= P.range; ++dx) {
-        const int x = cx + dx;
-        if (x < 0 || x >= (int)P.g.gx) continue;
-        const uint32_t cc = (uint32_t)x + (uint32_t)y * P.g.gx;
-        const uint32_t e = cell_end[cc];
-        for (uint32_t k = cell_start[cc]; k < e; ++k) {
-          const float4 cj = __ldg(&cpos[k]);
-          const uint32_t j = __float_as_uint(cj.w);
-          if (j == i) continue;
-          const float jx = cj.x, jy = cj.y;
-          uint32_t jsp = __float_as_uint(cj.z);
-          if (jsp >= kMaxSpecies) jsp = 0;
-          const SpeciesRow& sj = table[jsp];
-          const bool me_is_a = i < j;
-          const float ax = me_is_a ? me.x : jx, ay = me_is_a ? me.y : jy;
-          const float bx = me_is_a ? jx : me.x, by = me_is_a ? jy : me.y;
-          const SpeciesRow& sa = me_is_a ? si : sj;
-          const SpeciesRow& sb = me_is_a ? sj : si;
-          if (lj_i && sj.lj_enabled) {
-            const float rx = __fsub_rn(bx, ax), ry = __fsub_rn(by, ay);
-            if (__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)) < lj_cut_sq)
-              lj_pair(sa, sb, ax, ay, bx, by, me_is_a, am.w, P.max_lj_force, ljx, ljy);
-          }
-          if (rep_i && sa.repulsion_enabled && sb.repulsion_enabled)
-            rep_pair(sa, sb, ax, ay, bx, by, me_is_a, am.w, rpx, rpy);
-        }
-      }
-    }
-    // the reference finishes the LJ pass before the repulsion pass (simulation.rs:1008-1009)
-    am.x = __fadd_rn(__fadd_rn(am.x, ljx), rpx);
-    am.y = __fadd_rn(__fadd_rn(am.y, ljy), rpy);
+    cx = (int)(c % P.g.gx), cy = (int)(c / P.g.gx);
+    atomicMin(&s_box[0], cx), atomicMax(&s_box[1], cx), atomicMin(&s_box[2], cy), atomicMax(&s_box[3], cy);
   }
+  const int any_need = __syncthreads_or(need ? 1 : 0);
+  float4 am = make_float4(0, 0, 0, 0);
+  if (live) am = acc_mass[i];
+  if (any_need) {
+    const int R = P.range;
+    const int x0 = max(s_box[0] - R, 0), x1 = min(s_box[1] + R, (int)P.g.gx - 1);
+    const int y0 = max(s_box[2] - R, 0), y1 = min(s_box[3] + R, (int)P.g.gy - 1);
+    const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
+    const bool box_ok = bw <= kTileMaxW && bh <= kTileMaxH;
+    if (box_ok) {
+      for (int r = threadIdx.x; r < bh; r += blockDim.x)
+        s_rowsrc[r] = cell_off[(uint32_t)x0 + (uint32_t)(y0 + r) * P.g.gx];
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int r = 0; r < bh; ++r) {
+          s_rowbase[r] = run;
+          run += cell_off[(uint32_t)x1 + (uint32_t)(y0 + r) * P.g.gx + 1] - s_rowsrc[r];
+        }
+        s_rowbase[bh] = run;
+        s_fits = run <= (uint32_t)kTileCap;
+      }
+      __syncthreads();
+    }
+    const bool staged = box_ok && s_fits;
+    if (staged) {
+      // the box's cell offsets (re-based to the staged records) and the records themselves
+      for (int idx = threadIdx.x; idx < (bw + 1) * bh; idx += blockDim.x) {
+        const int r = idx / (bw + 1), xx = idx - r * (bw + 1);
+        s_off[idx] = (uint16_t)(cell_off[(uint32_t)(x0 + xx) + (uint32_t)(y0 + r) * P.g.gx] - s_rowsrc[r] + s_rowbase[r]);
+      }
+      for (int r = 0; r < bh; ++r) {
+        const uint32_t len = s_rowbase[r + 1] - s_rowbase[r], src = s_rowsrc[r], dst = s_rowbase[r];
+        for (uint32_t t = threadIdx.x; t < len; t += blockDim.x) s_rec[dst + t] = cpos[src + t];
+      }
+      __syncthreads();
+    }
+    if (need) {
+      const float lj_cut_sq = __fmul_rn(P.max_lj_cutoff, P.max_lj_cutoff);
+      float ljx = 0.0f, ljy = 0.0f, rpx = 0.0f, rpy = 0.0f;
+      const int xa = max(cx - R, 0), xb = min(cx + R, (int)P.g.gx - 1);
+      const int yb = min(cy + R, (int)P.g.gy - 1);
+      // no pair term exists at or beyond this squared distance (LJ: forces.rs:203; repulsion: the
+      // neighbour query of the lower-index body, forces.rs:262)
+      const float reach_sq = fmaxf(P.do_lj ? lj_cut_sq : 0.0f, __fmul_rn(P.max_rep_cutoff, P.max_rep_cutoff));
+      int y = max(cy - R, 0) - 1;
+      uint32_t k = 0, ke = 0;
+      for (;;) {
+        // cheap scan, lanes diverge here: advance to this body's next candidate inside the reach ...
+        float4 cj;
+        bool found = false;
+        for (;;) {
+          if (k >= ke) {
+            if (++y > yb) break;
+            if (staged) {
+              const int r = y - y0;
+              k = s_off[r * (bw + 1) + (xa - x0)], ke = s_off[r * (bw + 1) + (xb - x0) + 1];
+            } else {
+              k = cell_off[(uint32_t)xa + (uint32_t)y * P.g.gx], ke = cell_off[(uint32_t)xb + (uint32_t)y * P.g.gx + 1];
+            }
+            continue;
+          }
+          cj = staged ? s_rec[k] : __ldg(&cpos[k]);
+          ++k;
+          if (__float_as_uint(cj.w) == i) continue;
+          const float ddx = __fsub_rn(cj.x, me.x), ddy = __fsub_rn(cj.y, me.y);
+          if (__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)) < reach_sq) {
+            found = true;
+            break;
+          }
+        }
+        if (!found) break;
+        // ... and the warp reconverges for the pair arithmetic, same neighbour order per body
+        const uint32_t j = __float_as_uint(cj.w);
+        const float jx = cj.x, jy = cj.y;
+        uint32_t jsp = __float_as_uint(cj.z);
+        if (jsp >= kMaxSpecies) jsp = 0;
+        const SpeciesRow& sj = table[jsp];
+        const bool me_is_a = i < j;
+        const float ax = me_is_a ? me.x : jx, ay = me_is_a ? me.y : jy;
+        const float bx = me_is_a ? jx : me.x, by = me_is_a ? jy : me.y;
+        const SpeciesRow& sa = me_is_a ? si : sj;
+        const SpeciesRow& sb = me_is_a ? sj : si;
+        if (lj_i && sj.lj_enabled) {
+          const float rx = __fsub_rn(bx, ax), ry = __fsub_rn(by, ay);
+          if (__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)) < lj_cut_sq)
+            lj_pair(sa, sb, ax, ay, bx, by, me_is_a, am.w, P.max_lj_force, ljx, ljy);
+        }
+        if (rep_i && sj.repulsion_enabled) rep_pair(sa, sb, ax, ay, bx, by, me_is_a, am.w, rpx, rpy);
+      }
+      // the reference finishes the LJ pass before the repulsion pass (simulation.rs:1008-1009)
+      am.x = __fadd_rn(__fadd_rn(am.x, ljx), rpx);
+      am.y = __fadd_rn(__fadd_rn(am.y, ljy), rpy);
+    }
+  }
+  if (!live) return;
   if (P.do_stack) {  // forces.rs:294-321
     const float x_min = -P.g.hw, x_max = P.g.hw;
     const float dist_left = __fsub_rn(me.x, x_min);
@@ -222,7 +305,7 @@ __global__ void __launch_bounds__(128)
       am.x = __fsub_rn(am.x, __fdiv_rn(force, am.w));
     }
   }
-  acc_mass[i] = am;
+  if (need || P.do_stack) acc_mass[i] = am;
 }
 
 // ------------------------------------------------------------------------------------------------

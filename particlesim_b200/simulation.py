@@ -342,6 +342,29 @@ class Simulation:
         p = params or self.step_params()
         self._call("psim_step", C.byref(p))
 
+    def step_host(self, pos, vel=None, charge=None, params=None, out=None):
+        """psim_step_host: state refresh from host arrays + the hot path + read-back, pipelined.
+        Arrays are float32 numpy arrays in the order of the previous step_host outputs (first call: the
+        device's body order); `out` may hold preallocated (ideally page-locked) 'pos', 'vel', 'e_field',
+        'orig' arrays.  Returns the dict of outputs, rows in the order of the step's first build."""
+        p = params or self.step_params()
+        n = len(self.bodies)
+
+        def ptr(a, dt, shape):
+            if a is None:
+                return None
+            assert a.dtype == dt and a.flags["C_CONTIGUOUS"] and a.shape == shape, "step_host: bad array"
+            return a.ctypes.data_as(C.c_void_p)
+
+        if out is None:
+            out = dict(pos=np.empty((n, 2), np.float32), vel=np.empty((n, 2), np.float32),
+                       e_field=np.empty((n, 2), np.float32), orig=np.empty(n, np.uint32))
+        self._call("psim_step_host", C.byref(p), n, ptr(pos, np.float32, (n, 2)), ptr(vel, np.float32, (n, 2)),
+                   ptr(charge, np.float32, (n,)), ptr(out.get("pos"), np.float32, (n, 2)),
+                   ptr(out.get("vel"), np.float32, (n, 2)), ptr(out.get("e_field"), np.float32, (n, 2)),
+                   ptr(out.get("orig"), np.uint32, (n,)))
+        return out
+
 
 class forces:
     """src/simulation/forces.rs — free functions taking the simulation, like the reference."""

@@ -117,6 +117,9 @@ extern "C" {
     pub fn psim_apply_polar_forces(ctx: *mut psim_ctx, k_e: f32, dipole_model: i32) -> i32;
     pub fn psim_iterate(ctx: *mut psim_ctx, dt: f32, damping_base: f32, hw: f32, hh: f32, hd: f32, enable_out_of_plane: i32) -> i32;
     pub fn psim_step(ctx: *mut psim_ctx, p: *const psim_step_params) -> i32;
+    pub fn psim_step_host(ctx: *mut psim_ctx, p: *const psim_step_params, n: u64, pos_xy: *const f32,
+                          vel_xy: *const f32, charge: *const f32, out_pos_xy: *mut f32, out_vel_xy: *mut f32,
+                          out_e_field_xy: *mut f32, out_orig_index: *mut u32) -> i32;
     pub fn psim_sync(ctx: *mut psim_ctx) -> i32;
 }
 

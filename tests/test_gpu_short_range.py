@@ -268,3 +268,55 @@ def test_fused_step_with_polar_forces(cuda_device):
     assert rel_l2(sim.bodies.vel, ob["vel"]) <= TOL
     assert rel_l2(sim.bodies.pos, ob["pos"]) <= 1e-6
     sim.close()
+
+
+@pytest.mark.parametrize("do_electrons", [True, False])
+def test_hosted_step_equals_update_step_download(cuda_device, do_electrons):
+    """psim_step_host (pipelined copies) == psim_update_state + psim_step + psim_download_bodies, bit for
+    bit per body, over consecutive steps fed with their own outputs.  The hosted step returns rows in the
+    order of the step's first build, the sequence in the order the step leaves on the device: compare by
+    original index."""
+    bodies = electrolyte(60_000)
+    n = len(bodies["pos"])
+    a, b = make_sim(bodies), make_sim(bodies)
+    rng = np.random.default_rng(5)
+    # per-body state, by original index
+    pos0 = bodies["pos"].copy()
+    vel0 = rng.normal(0, 0.02, (n, 2)).astype(np.float32)
+    q0 = bodies["charge"].copy()
+    a_rows = np.arange(n)  # original index of each row, as each side's host sees it
+    b_rows = np.arange(n)
+    for step in range(4):
+        # sequence on context a (rows in a's device order)
+        pa, va, qa = (np.ascontiguousarray(v[a_rows]) for v in (pos0, vel0, q0))  # keep the arrays alive
+        a._call("psim_update_state", n, pa.ctypes.data, va.ctypes.data, qa.ctypes.data)
+        a.step_device(a.step_params(do_electrons=do_electrons))
+        o_pos, o_vel, o_e = (np.zeros((n, 2), np.float32) for _ in range(3))
+        o_orig = np.zeros(n, np.uint32)
+        a._call("psim_download_bodies", o_pos.ctypes.data, None, o_vel.ctypes.data, *([None] * 7), o_e.ctypes.data,
+                o_orig.ctypes.data)
+        # hosted step on context b (rows in the order of b's previous outputs)
+        out = b.step_host(np.ascontiguousarray(pos0[b_rows]), np.ascontiguousarray(vel0[b_rows]),
+                          np.ascontiguousarray(q0[b_rows]), params=b.step_params(do_electrons=do_electrons))
+        assert sorted(out["orig"].tolist()) == list(range(n))
+        ia, ib = np.argsort(o_orig), np.argsort(out["orig"])
+        assert np.array_equal(out["pos"][ib], o_pos[ia])
+        assert np.array_equal(out["vel"][ib], o_vel[ia])
+        assert np.array_equal(out["e_field"][ib], o_e[ia])
+        if not do_electrons:
+            assert np.array_equal(out["orig"], o_orig)  # no second sort: the same row order
+        # the host changes the state between steps (collisions / foils would): by original index
+        pos0[o_orig] = o_pos
+        vel0[o_orig] = o_vel * np.float32(0.5)
+        flip = rng.integers(0, n, 50)
+        q0[flip] = -q0[flip]
+        a_rows, b_rows = o_orig.astype(np.int64), out["orig"].astype(np.int64)
+    if do_electrons:
+        # both contexts end in the same device order with the same electrons
+        for sim in (a, b):
+            sim.download_electrons()
+        assert np.array_equal(a.bodies.erel, b.bodies.erel) and np.array_equal(a.bodies.evel, b.bodies.evel)
+        d_orig = np.zeros(n, np.uint32)
+        b._call("psim_download_bodies", *([None] * 11), d_orig.ctypes.data)
+        assert np.array_equal(d_orig, o_orig)
+    a.close(), b.close()

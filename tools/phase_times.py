@@ -19,6 +19,7 @@ ap.add_argument("--gen", default="electrolyte")
 ap.add_argument("--theta", type=float, default=1.0)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--fast", type=int, default=0)
+ap.add_argument("--cells", default="11.88", help="comma-separated cell sizes to time the short-range pass on")
 args = ap.parse_args()
 
 gen = dict(electrolyte=electrolyte, uniform=uniform_pm1, clustered=clustered)[args.gen]
@@ -51,12 +52,13 @@ C = sim._call
 timed("build(CONTAINING)", lambda: C("psim_build", 0, 0.0, 0.0))
 print(sim.stats())
 timed("build(DOMAIN)", lambda: C("psim_build", 1, hw, hh))
-timed("cell_build 11.88", lambda: C("psim_cell_build", hw, hh, 11.88))
+for cs in [float(v) for v in args.cells.split(",")]:
+    timed(f"cell_build {cs}", lambda: C("psim_cell_build", hw, hh, cs))
+    timed(f"short_range(LJ) @ {cs}", lambda: C("psim_short_range", 7))
 C("psim_reset_counters")
 tf = timed("field+attract", lambda: C("psim_field", float(KE), 0.0, 0.0, 1, None, None))
 st = sim.stats()
 print("warp steps per group:", st["traversal_warp_steps"] / args.reps / ((args.n + 31) // 32))
-timed("short_range(LJ)", lambda: C("psim_short_range", 7))
 if len(b.ebody):
     timed("update_electrons", lambda: C("psim_update_electrons", 0.0, 0.0, 5.0, float(KE)))
 p = sim.step_params()
