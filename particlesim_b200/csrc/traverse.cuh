@@ -40,6 +40,19 @@ struct Arith {
   static __device__ __forceinline__ float sqrt(float a) { return PARITY ? __fsqrt_rn(a) : __fsqrt_rn(a); }
 };
 
+// MUFU approximations without the denormal pre-scaling of rsqrtf() / __fdividef() (inputs here are
+// squared distances and softened cubes of them, never denormal unless exactly zero)
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 struct TraverseCounters {
   unsigned long long steps;  // warp steps (nodes visited by a warp)
 };
@@ -253,8 +266,11 @@ struct WarpShared {
   uint32_t st_node[kStackCap], st_mask[kStackCap];
   // the round's nodes that some target may accept, staged for broadcast reads
   float4 l_node[32];  // {centre.x, centre.y, charge, size}
-  uint2 l_mc[32];     // {mask of targets that reach the node, 1 if every target accepts}
-  uint32_t l_acc[32]; // result: mask of targets that accepted
+  uint32_t l_mask[32]; // mask of targets that reach the node
+  uint32_t l_acc[32];  // result: mask of targets that accepted
+  // the round's charged nodes that every target reaching them accepts: no test, no result
+  float4 s_node[32];
+  uint32_t s_mask[32];
 };
 
 template <bool PARITY>
@@ -336,51 +352,76 @@ __device__ __forceinline__ float2 bh_group_walk(const float4* __restrict__ nodeA
         else if (dmax2 < lr * lr * 0.99998f) cls = 2;
       }
     }
-    // every node that some target may accept is staged in shared memory; then each lane applies the
-    // reference's opening test with its own position and radius (quadtree.rs:361-371) to every staged
-    // node (broadcast reads) and, if it accepts, adds the monopole (:372-375)
-    uint32_t acc_mask = (has && cls == 1 && na.z == 0.0f) ? mask : 0u;  // charge 0: adds exactly +-0
-    const bool in_list = has && cls != 2 && !(cls == 1 && na.z == 0.0f);
+    // Nodes that every reaching target accepts (and that carry charge) go to the "sure" list: monopole
+    // only.  Undecided nodes go to the second list: each lane applies the reference's opening test
+    // with its own position and radius (quadtree.rs:361-371) to every staged node (broadcast reads)
+    // and, if it accepts, adds the monopole (:372-375); the ballot is the node's accept mask.
+    uint32_t acc_mask = (has && cls == 1) ? mask : 0u;
+    const bool in_sure = has && cls == 1 && na.z != 0.0f;  // charge 0 adds exactly +-0
+    const bool in_list = has && cls == 0;
+    const uint32_t sm = __ballot_sync(FULL, in_sure);
     const uint32_t lm = __ballot_sync(FULL, in_list);
-    const int cnt = __popc(lm);
+    const int scnt = __popc(sm), cnt = __popc(lm);
     const int my_slot = __popc(lm & lt);
+    if (in_sure) {
+      const int sl = __popc(sm & lt);
+      ws.s_node[sl] = na;
+      ws.s_mask[sl] = mask;
+    }
     if (in_list) {
       ws.l_node[my_slot] = na;
-      ws.l_mc[my_slot] = make_uint2(mask, cls == 1 ? 1u : 0u);
+      ws.l_mask[my_slot] = mask;
     }
     __syncwarp();
+    auto monopole = [&](const float4& nd, float dx, float dy, float d_sq, float dist, bool have_dist) {
+      if (PARITY) {
+        if (!have_dist) dist = __fsqrt_rn(d_sq);
+        const float r_eff = fmaxf(dist, __fadd_rn(radius, __fmul_rn(nd.w, 0.5f)));
+        const float denom = __fmul_rn(__fadd_rn(__fmul_rn(r_eff, r_eff), P.e_sq), r_eff);
+        const float sc = __fdiv_rn(__fmul_rn(kq, nd.z), denom);
+        ax = __fadd_rn(ax, __fmul_rn(dx, sc));
+        ay = __fadd_rn(ay, __fmul_rn(dy, sc));
+      } else {
+        // fast arithmetic on the same interaction set: rsqrt / rcp approximations (2 ulp each), FMA
+        const float r_eff = fmaxf(d_sq * rsqrt_ftz(d_sq), fmaf(nd.w, 0.5f, radius));  // fmaxf drops the NaN of d_sq = 0
+        const float denom = fmaf(r_eff, r_eff, P.e_sq) * r_eff;
+        const float sc = (kq * nd.z) * rcp_ftz(denom);
+        ax = fmaf(dx, sc, ax);
+        ay = fmaf(dy, sc, ay);
+      }
+    };
+    for (int it = 0; it < scnt; ++it) {
+      const float4 nd = ws.s_node[it];
+      const uint32_t m = ws.s_mask[it];
+      if ((m >> lane) & 1u) {
+        const float dx = A::sub(px, nd.x), dy = A::sub(py, nd.y);
+        const float d_sq = A::add(A::mul(dx, dx), A::mul(dy, dy));
+        monopole(nd, dx, dy, d_sq, 0.0f, false);
+      }
+    }
     for (int it = 0; it < cnt; ++it) {
       const float4 nd = ws.l_node[it];
-      const uint2 mc = ws.l_mc[it];
-      const float dx = A::sub(px, nd.x), dy = A::sub(py, nd.y);
-      const float d_sq = A::add(A::mul(dx, dx), A::mul(dy, dy));
-      bool acc = ((mc.x >> lane) & 1u) != 0;
+      const uint32_t m = ws.l_mask[it];
+      // the distance feeds the opening decision: reference arithmetic in every mode
+      const float dx = __fsub_rn(px, nd.x), dy = __fsub_rn(py, nd.y);
+      const float d_sq = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+      const bool reach = ((m >> lane) & 1u) != 0;
+      // conservative pre-test with this target's own radius; only the band in between takes the
+      // reference's test, which alone decides a borderline case
+      const float lim = fmaf(nd.w, P.inv_theta, my_lim_r);
+      const float lim2 = lim * lim;
+      bool acc = reach && d_sq > lim2 * 1.00002f;
       float dist = 0.0f;
       bool have_dist = false;
-      if (mc.y == 0u && acc) {
-        const float lim = nd.w * P.inv_theta + my_lim_r;
-        const float lim2 = lim * lim;
-        if (d_sq > lim2 * 1.00002f) {
-          acc = true;
-        } else if (d_sq < lim2 * 0.99998f) {
-          acc = false;
-        } else {
-          dist = A::sqrt(d_sq);
-          have_dist = true;
-          const float dist_adj = fmaxf(A::sub(dist, radius), 0.0f);
-          acc = A::mul(nd.w, nd.w) < A::mul(A::mul(dist_adj, dist_adj), P.t_sq);
-        }
+      if (reach && !acc && !(d_sq < lim2 * 0.99998f)) {
+        dist = __fsqrt_rn(d_sq);
+        have_dist = true;
+        const float dist_adj = fmaxf(__fsub_rn(dist, radius), 0.0f);
+        acc = __fmul_rn(nd.w, nd.w) < __fmul_rn(__fmul_rn(dist_adj, dist_adj), P.t_sq);
       }
       const uint32_t am = __ballot_sync(FULL, acc);
       if (lane == 0) ws.l_acc[it] = am;
-      if (acc && nd.z != 0.0f) {
-        if (!have_dist) dist = A::sqrt(d_sq);
-        const float r_eff = fmaxf(dist, A::add(radius, A::mul(nd.w, 0.5f)));
-        const float denom = A::mul(A::add(A::mul(r_eff, r_eff), P.e_sq), r_eff);
-        const float sc = A::div(A::mul(kq, nd.z), denom);
-        ax = A::add(ax, A::mul(dx, sc));
-        ay = A::add(ay, A::mul(dy, sc));
-      }
+      if (acc && nd.z != 0.0f) monopole(nd, dx, dy, d_sq, dist, have_dist);
     }
     __syncwarp();
     if (in_list) acc_mask = ws.l_acc[my_slot];
