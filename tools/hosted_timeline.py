@@ -18,12 +18,14 @@ from particlesim_b200 import Bodies, Simulation  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=16_000_000)
 ap.add_argument("--reps", type=int, default=4)
+ap.add_argument("--flush", type=int, default=0, help="MB of host scratch written before each call (evicts the CPU caches)")
+ap.add_argument("--fast", type=int, default=0)
 args = ap.parse_args()
 n = args.n
 bd = electrolyte(n)
 b = Bodies(bd["pos"], vel=bd.get("vel"), mass=bd["mass"], radius=bd["radius"], charge=bd["charge"],
            species=bd["species"], ebody=bd.get("ebody"), erel=bd.get("erel"))
-sim = Simulation(b, bd["hw"], bd["hh"], theta=1.0, stream=torch.cuda.current_stream().cuda_stream)
+sim = Simulation(b, bd["hw"], bd["hh"], theta=1.0, parity_mode=0 if args.fast else 1, stream=torch.cuda.current_stream().cuda_stream)
 sim.config.coulomb_constant = float(KE)
 params = sim.step_params()
 pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -31,11 +33,14 @@ h_pos, h_vel, h_q = pin(bd["pos"]), pin(np.zeros((n, 2), np.float32)), pin(bd["c
 o_pos, o_vel, o_ef = (torch.empty(n, 2).pin_memory() for _ in range(3))
 o_orig = torch.empty(n, dtype=torch.int32).pin_memory()
 charge0 = torch.from_numpy(bd["charge"])
+scratch = torch.empty(max(1, args.flush) * (1 << 18), dtype=torch.float32)
 
 
 def run(name, vel=True, q=True, outs=(1, 1, 1, 1)):
     ts, ph = [], None
     for k in range(args.reps + 1):
+        if args.flush:
+            scratch.add_(1.0)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         sim._call("psim_step_host", C.byref(params), n, h_pos.data_ptr(), h_vel.data_ptr() if vel else None,
