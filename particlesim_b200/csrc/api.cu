@@ -24,7 +24,7 @@ static_assert(sizeof(psim_node) == sizeof(PsimNodeOut) && sizeof(psim_node) == 6
 
 namespace {
 
-constexpr int kTreePasses = 8;  // 64-bit keys, 8-bit digits
+constexpr int kTreePasses = 4;  // radix passes over the upper key word (sort.cuh, two-tier key sort)
 
 struct BodyArrays {
   float4* pqr;      // {x, y, charge, radius}
@@ -60,8 +60,10 @@ struct psim_ctx {
   float2* efld = nullptr;
 
   // sort
-  uint64_t* keys[2] = {nullptr, nullptr};
+  uint64_t* keys[2] = {nullptr, nullptr};  // [0] keys in body order (scratch after the sort), [1] sorted
+  uint32_t* khi[2] = {nullptr, nullptr};   // upper key words, ping-pong buffers of the radix passes
   uint32_t* idx[2] = {nullptr, nullptr};
+  uint32_t* long_runs = nullptr;           // [0] count, [1..] heads of long equal-upper-word runs
   uint32_t* ckeys[2] = {nullptr, nullptr};
   uint32_t* cidx[2] = {nullptr, nullptr};
   SortScratch sc = {};
@@ -500,12 +502,21 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
   }
   root_quad_kernel<<<1, 32, 0, st>>>(ctx->bounds_partial, nb, mode, hw, hh, n, ctx->meta);
   LAUNCHED(ctx);
-  keygen_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(in.pqr, n, ctx->meta, ctx->keys[0], ctx->idx[0]);
+  keygen_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(in.pqr, n, ctx->meta, ctx->keys[0], ctx->khi[0],
+                                                           ctx->idx[0]);
   LAUNCHED(ctx);
   ctx->sc.plan = ctx->tree_plan;
-  CK(onesweep_sort<uint64_t>(ctx->keys[0], ctx->keys[1], ctx->idx[0], ctx->idx[1], n, 0, kTreePasses,
+  CK(onesweep_sort<uint32_t>(ctx->khi[0], ctx->khi[1], ctx->idx[0], ctx->idx[1], n, 0, kTreePasses,
                              ctx->sc, ctx->sm_count, st));
   ctx->launches += 2 + kTreePasses;
+  gather_keys_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(ctx->keys[0], ctx->idx[0], ctx->idx[1], ctx->tree_plan,
+                                                                kTreePasses, n, ctx->keys[1], ctx->long_runs);
+  fix_runs_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(ctx->keys[1], ctx->idx[0], ctx->idx[1], ctx->tree_plan,
+                                                             kTreePasses, n, ctx->long_runs, ctx->long_runs + 1);
+  sort_long_runs_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->keys[1], ctx->idx[0], ctx->idx[1], ctx->tree_plan,
+                                                       kTreePasses, n, ctx->long_runs, ctx->long_runs + 1,
+                                                       ctx->keys[0]);
+  ctx->launches += 3;
   if (ctx->hosted.active && ctx->hosted.late_q) {  // psim_step_host: the charges arrived during the sort
     CK(cudaStreamWaitEvent(st, ctx->ev_q, 0));
     hosted_charges_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(ctx->hosted.late_q, ctx->hosted.map, n, in.pqr);
@@ -540,14 +551,14 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
   }
   const uint32_t c_eff = effective_capacity(ctx->cfg.leaf_capacity, ctx->cfg.thread_capacity);
   tree_count_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, st>>>(
-      ctx->keys[0], ctx->keys[1], ctx->tree_plan, kTreePasses, b.pqr, n, c_eff, ctx->meta, ctx->le);
+      ctx->keys[1], ctx->keys[1], ctx->tree_plan, kTreePasses, b.pqr, n, c_eff, ctx->meta, ctx->le);
   LAUNCHED(ctx);
   CK(exclusive_scan(LeCountFn{ctx->le}, n, ctx->nodebase, ctx->scan_partials, &ctx->meta->num_nodes, st));
   ctx->launches += 3;
   level_scan_kernel<<<1, 32, 0, st>>>(ctx->meta, ctx->node_cap);
   LAUNCHED(ctx);
   tree_emit_kernel<<<grid_for(ctx, n, 128, 16), 128, 0, st>>>(
-      ctx->keys[0], ctx->keys[1], ctx->tree_plan, kTreePasses, n, ctx->le, ctx->nodebase, b.pqr,
+      ctx->keys[1], ctx->keys[1], ctx->tree_plan, kTreePasses, n, ctx->le, ctx->nodebase, b.pqr,
       b.accm, ctx->cfg.leaf_capacity, ctx->cfg.thread_capacity,
       ctx->meta, ctx->t);
   LAUNCHED(ctx);
@@ -564,7 +575,7 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
     LAUNCHED(ctx);
   }
   // traversal arrays (charged nodes only)
-  CK(exclusive_scan_dyn(ChargedFlagFn{ctx->t.rec}, &ctx->meta->num_nodes, ctx->node_cap, ctx->trav_rank,
+  CK(exclusive_scan_dyn(ChargedFlagFn{ctx->t.ndepth}, &ctx->meta->num_nodes, ctx->node_cap, ctx->trav_rank,
                         ctx->scan_partials, ctx->trav_count, st));
   ctx->launches += 3;
   compact_traversal_kernel<<<grid_for(ctx, (uint64_t)n * 2, 256, 16), 256, 0, st>>>(
@@ -826,10 +837,10 @@ void free_all(psim_ctx* c) {
   for (int k = 0; k < 2; ++k) {
     F(c->b[k].pqr), F(c->b[k].velz), F(c->b[k].accm), F(c->b[k].efield), F(c->b[k].species), F(c->b[k].orig), F(c->b[k].ecount);
     F(c->ebody[k]), F(c->erel[k]), F(c->evel[k]), F(c->eoff[k]);
-    F(c->keys[k]), F(c->idx[k]), F(c->ckeys[k]), F(c->cidx[k]);
+    F(c->keys[k]), F(c->khi[k]), F(c->idx[k]), F(c->ckeys[k]), F(c->cidx[k]);
   }
   F(c->epts), F(c->efld);
-  F(c->sc.hist), F(c->sc.status), F(c->sc.ticket), F(c->tree_plan), F(c->cell_plan);
+  F(c->sc.hist), F(c->sc.status), F(c->sc.ticket), F(c->tree_plan), F(c->cell_plan), F(c->long_runs);
   F(c->meta), F(c->le), F(c->nodebase), F(c->scan_partials), F(c->irank), F(c->bounds_partial);
   F(c->t.nodeA), F(c->t.nodeB), F(c->t.node_mass), F(c->t.parent), F(c->t.sums), F(c->t.level_nodes);
   F(c->t.rec), F(c->t.ndepth);
@@ -899,13 +910,13 @@ int32_t psim_create(int32_t device, uint64_t max_bodies, uint64_t max_electrons,
     A(&ctx->b[k].pqr, nb), A(&ctx->b[k].velz, nb), A(&ctx->b[k].accm, nb), A(&ctx->b[k].efield, nb);
     A(&ctx->b[k].species, nb), A(&ctx->b[k].orig, nb), A(&ctx->b[k].ecount, nb);
     A(&ctx->ebody[k], ne), A(&ctx->erel[k], ne), A(&ctx->evel[k], ne), A(&ctx->eoff[k], nb + 1);
-    A(&ctx->keys[k], nb), A(&ctx->idx[k], nb), A(&ctx->ckeys[k], nb), A(&ctx->cidx[k], nb);
+    A(&ctx->keys[k], nb), A(&ctx->khi[k], nb), A(&ctx->idx[k], nb), A(&ctx->ckeys[k], nb), A(&ctx->cidx[k], nb);
   }
   A(&ctx->epts, ne), A(&ctx->efld, ne);
   A(&ctx->sc.hist, 8 * kRadix), A(&ctx->sc.ticket, 8);
   ctx->sc.status_words = sort_status_words((uint32_t)nb, kTreePasses);
   A(&ctx->sc.status, ctx->sc.status_words);
-  A(&ctx->tree_plan, 1), A(&ctx->cell_plan, 1);
+  A(&ctx->tree_plan, 1), A(&ctx->cell_plan, 1), A(&ctx->long_runs, nb / kFixInsertion + 2);
   A(&ctx->meta, 1), A(&ctx->le, nb), A(&ctx->nodebase, nb + 1);
   A(&ctx->scan_partials, (size_t)scan_num_tiles(ctx->node_cap > nb ? ctx->node_cap : (uint32_t)nb) + 1);
   A(&ctx->irank, ctx->node_cap), A(&ctx->bounds_partial, (size_t)ctx->sm_count * 4 + 1);
@@ -1263,10 +1274,8 @@ int32_t psim_get_keys(psim_ctx* ctx, uint64_t* out) {
   if (!ctx || !out) return PSIM_E_ARG;
   if (!ctx->perm_valid && ctx->n) return fail(ctx, PSIM_E_STATE, "psim_get_keys: no build since the last upload");
   if (!ctx->n) return PSIM_OK;
-  SortPlan plan;
   CK(cudaStreamSynchronize(ctx->stream));
-  CK(cudaMemcpy(&plan, ctx->tree_plan, sizeof plan, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(out, ctx->keys[plan.src[kTreePasses] ? 1 : 0], (size_t)ctx->n * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out, ctx->keys[1], (size_t)ctx->n * 8, cudaMemcpyDeviceToHost));
   return PSIM_OK;
 }
 
@@ -1300,7 +1309,7 @@ int32_t psim_download_nodes(psim_ctx* ctx, psim_node* out, uint64_t cap, uint64_
   if (rc) return rc;
   CK(cudaMemsetAsync(ctx->qstage, 0, ncopy * sizeof(PsimNodeOut), st));
   export_nodes_kernel<<<grid_for(ctx, M, 128, 16), 128, 0, st>>>(
-      ctx->keys[0], ctx->keys[1], ctx->tree_plan, kTreePasses, ctx->meta, ctx->t, ctx->irank,
+      ctx->keys[1], ctx->keys[1], ctx->tree_plan, kTreePasses, ctx->meta, ctx->t, ctx->irank,
       static_cast<PsimNodeOut*>(ctx->qstage), ncopy);
   LAUNCHED(ctx);
   CK(cudaMemcpyAsync(out, ctx->qstage, ncopy * sizeof(PsimNodeOut), cudaMemcpyDeviceToHost, st));

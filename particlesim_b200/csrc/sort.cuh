@@ -291,6 +291,155 @@ cudaError_t onesweep_sort(K* keys0, K* keys1, uint32_t* vals0, uint32_t* vals1, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Two-tier key sort.  The quadrant keys are 64 bits (32 levels), but bodies are almost always told
+// apart by the upper 32 (16 levels: cells of root / 65536), so the radix passes run on the upper word
+// only (4 passes over 8-byte pairs instead of 8 over 12-byte pairs) and the few runs of bodies that
+// share it are put in order of the full key afterwards:
+//   gather_keys_kernel   sorted 64-bit keys through the sorted payload
+//   fix_runs_kernel      one thread per run head; runs of <= kFixInsertion keys by insertion sort,
+//                        longer ones are queued
+//   sort_long_runs_kernel  one CTA per queued run: nothing to do if it is already in order (identical
+//                        bodies), else a stable CTA-wide LSD radix sort of the lower word
+// Both steps are stable, so the result equals a stable sort by the full key.
+constexpr int kFixInsertion = 64;
+
+__global__ void __launch_bounds__(256)
+    gather_keys_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ idx0,
+                       const uint32_t* __restrict__ idx1, const SortPlan* __restrict__ plan, int npass,
+                       uint32_t n, uint64_t* __restrict__ out, uint32_t* __restrict__ long_count) {
+  const uint32_t* __restrict__ idx = plan->src[npass] ? idx1 : idx0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *long_count = 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = keys_in[idx[i]];
+}
+
+__global__ void __launch_bounds__(256)
+    fix_runs_kernel(uint64_t* __restrict__ skeys, uint32_t* __restrict__ idx0, uint32_t* __restrict__ idx1,
+                    const SortPlan* __restrict__ plan, int npass, uint32_t n,
+                    uint32_t* __restrict__ long_count, uint32_t* __restrict__ long_start) {
+  uint32_t* __restrict__ idx = plan->src[npass] ? idx1 : idx0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    // a run's upper words never change while it is being reordered, so neighbours can be read freely
+    const uint32_t hi = (uint32_t)(skeys[i] >> 32);
+    if (i + 1 >= n || (uint32_t)(skeys[i + 1] >> 32) != hi) continue;
+    if (i > 0 && (uint32_t)(skeys[i - 1] >> 32) == hi) continue;  // not the head of its run
+    uint32_t e = i + 2;
+    while (e < n && e - i <= (uint32_t)kFixInsertion && (uint32_t)(skeys[e] >> 32) == hi) ++e;
+    if (e - i > (uint32_t)kFixInsertion) {
+      long_start[atomicAdd(long_count, 1u)] = i;  // at most n / kFixInsertion runs exist
+      continue;
+    }
+    for (uint32_t a = i + 1; a < e; ++a) {
+      const uint64_t k = skeys[a];
+      const uint32_t v = idx[a];
+      uint32_t b = a;
+      while (b > i && skeys[b - 1] > k) {
+        skeys[b] = skeys[b - 1];
+        idx[b] = idx[b - 1];
+        --b;
+      }
+      skeys[b] = k;
+      idx[b] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    sort_long_runs_kernel(uint64_t* __restrict__ skeys, uint32_t* __restrict__ idx0, uint32_t* __restrict__ idx1,
+                          const SortPlan* __restrict__ plan, int npass, uint32_t n,
+                          const uint32_t* __restrict__ long_count, const uint32_t* __restrict__ long_start,
+                          uint64_t* __restrict__ kscratch) {
+  uint32_t* __restrict__ idx = plan->src[npass] ? idx1 : idx0;
+  uint32_t* __restrict__ vscratch = plan->src[npass] ? idx0 : idx1;
+  __shared__ uint32_t s_hist[kRadix], s_base[kRadix], s_wcnt[8][kRadix];
+  __shared__ uint32_t s_len, s_flag;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint32_t runs = *long_count;
+  for (uint32_t r = blockIdx.x; r < runs; r += gridDim.x) {
+    const uint32_t start = long_start[r];
+    __syncthreads();
+    if (t == 0) {
+      // end of the run of equal upper words: galloping + binary search on the sorted upper words
+      const uint32_t hi = (uint32_t)(skeys[start] >> 32);
+      uint64_t in = start, step = 1;
+      while (in + step < n && (uint32_t)(skeys[in + step] >> 32) == hi) in += step, step <<= 1;
+      uint64_t a = in, b = in + step < n ? in + step : n;
+      while (b - a > 1) {
+        const uint64_t mid = a + ((b - a) >> 1);
+        if ((uint32_t)(skeys[mid] >> 32) == hi) a = mid; else b = mid;
+      }
+      s_len = (uint32_t)(b - start);
+      s_flag = 0;
+    }
+    __syncthreads();
+    const uint32_t len = s_len;
+    for (uint32_t j = t; j + 1 < len; j += 256)
+      if (skeys[start + j] > skeys[start + j + 1]) s_flag = 1;
+    __syncthreads();
+    if (!s_flag) continue;  // already in order (the common case: identical bodies)
+    uint64_t* ksrc = skeys + start;
+    uint64_t* kdst = kscratch + start;
+    uint32_t* vsrc = idx + start;
+    uint32_t* vdst = vscratch + start;
+    bool swapped = false;
+    for (int shift = 0; shift < 32; shift += 8) {
+      s_hist[t] = 0;
+      __syncthreads();
+      for (uint32_t j = t; j < len; j += 256) atomicAdd(&s_hist[(uint32_t)(ksrc[j] >> shift) & 0xffu], 1u);
+      __syncthreads();
+      if (t == 0) {
+        uint32_t run = 0, uniform = 0;
+        for (int d = 0; d < kRadix; ++d) {
+          if (s_hist[d] == len) uniform = 1;
+          s_base[d] = run;
+          run += s_hist[d];
+        }
+        s_flag = uniform;
+      }
+      __syncthreads();
+      if (s_flag) continue;  // every key has the same digit: nothing moves
+      for (uint32_t c = 0; c < len; c += 256) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s_wcnt[w][t] = 0;
+        __syncthreads();
+        const uint32_t j = c + t;
+        const bool valid = j < len;
+        const uint64_t k = valid ? ksrc[j] : 0ull;
+        const uint32_t v = valid ? vsrc[j] : 0u;
+        const uint32_t d = (uint32_t)(k >> shift) & 0xffu;
+        const uint32_t m = __match_any_sync(0xffffffffu, valid ? d : 0x100u);
+        if (valid && lane == __ffs(m) - 1) s_wcnt[warp][d] = __popc(m);
+        __syncthreads();
+        if (valid) {
+          uint32_t off = 0;
+          for (int w = 0; w < warp; ++w) off += s_wcnt[w][d];
+          const uint32_t pos = s_base[d] + off + __popc(m & lt);
+          kdst[pos] = k;
+          vdst[pos] = v;
+        }
+        __syncthreads();
+        uint32_t tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += s_wcnt[w][t];
+        s_base[t] += tot;
+        __syncthreads();
+      }
+      __threadfence_block();
+      uint64_t* kt = ksrc; ksrc = kdst; kdst = kt;
+      uint32_t* vt = vsrc; vsrc = vdst; vdst = vt;
+      swapped = !swapped;
+    }
+    __syncthreads();
+    if (swapped) {
+      for (uint32_t j = t; j < len; j += 256) kdst[j] = ksrc[j], vdst[j] = vsrc[j];
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Exclusive scan of u32 values produced by a functor f(i), i in [0, n): reduce / scan-partials /
 // downsweep.  total (if not null) receives the grand sum on the device.
 constexpr int kScanThreads = 256;

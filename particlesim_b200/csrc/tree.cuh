@@ -87,12 +87,14 @@ __global__ void root_quad_kernel(const float4* __restrict__ partial, int nblocks
 
 __global__ void __launch_bounds__(256)
     keygen_kernel(const float4* __restrict__ pqr, uint32_t n, const TreeMeta* __restrict__ meta,
-                  uint64_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+                  uint64_t* __restrict__ keys, uint32_t* __restrict__ khi, uint32_t* __restrict__ idx) {
   const RootQuad r = meta->root;
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float4 p = pqr[i];
-    keys[i] = morton_key(p.x, p.y, r);
+    const uint64_t k = morton_key(p.x, p.y, r);
+    keys[i] = k;
+    khi[i] = (uint32_t)(k >> 32);  // what the radix passes sort (sort.cuh, two-tier key sort)
     idx[i] = i;
   }
 }
@@ -279,8 +281,8 @@ __global__ void __launch_bounds__(128)
 // below them, compacted in pre-order (skip pointers remapped).  A node without charge adds exactly
 // +-0 to every acc_pos sum whatever the opening test says, so the reference's result is unchanged.
 struct ChargedFlagFn {
-  const NodeRec* rec;
-  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return rec[i].aq > 0.0 ? 1u : 0u; }
+  const uint8_t* ndepth;
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return ndepth[i] >> 7; }
 };
 
 __global__ void __launch_bounds__(256)

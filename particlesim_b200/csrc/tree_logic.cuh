@@ -42,6 +42,10 @@ struct NodeRec {
   uint32_t next;        // skip pointer | kLastSibling if the node is its parent's last non-empty child
 };
 constexpr uint32_t kLastSibling = 1u << 31;
+// ndepth[node] = depth | kDepthCharged if some body below the node carries charge (one byte per node:
+// the traversal compaction scans these instead of the 32-byte records)
+constexpr uint32_t kDepthCharged = 0x80u;
+constexpr uint32_t kDepthMask8 = 0x7fu;
 constexpr uint32_t kNextMask = ~kLastSibling;
 
 struct TreeArrays {
@@ -190,7 +194,7 @@ PSIM_HD void emit_nodes_for_body(const uint64_t* keys, uint32_t n, uint32_t i, u
     NodeRec r;
     r.aq = aq, r.aqx = aqx, r.aqy = aqy, r.charge = tq, r.next = next | (last ? kLastSibling : 0u);
     t.rec[node] = r;
-    t.ndepth[node] = (uint8_t)d;
+    t.ndepth[node] = (uint8_t)((uint32_t)d | (aq > 0.0 ? kDepthCharged : 0u));
   }
   for (int d = ell - 1; d > lam; --d) {
     const uint32_t node = base + (uint32_t)(d - lam - 1);
@@ -217,10 +221,11 @@ PSIM_HD void aggregate_node_lean(uint32_t node, int depth, uint32_t M, const Tre
     if (r.next & kLastSibling) break;
   }
   // the node that follows my subtree is my sibling iff it sits at my depth
-  const bool last = (c >= M) || ((int)t.ndepth[c] != depth);
+  const bool last = (c >= M) || ((int)(t.ndepth[c] & kDepthMask8) != depth);
   NodeRec out;
   out.aq = aq, out.aqx = aqx, out.aqy = aqy, out.charge = charge, out.next = c | (last ? kLastSibling : 0u);
   t.rec[node] = out;
+  if (aq > 0.0) t.ndepth[node] = (uint8_t)((uint32_t)depth | kDepthCharged);
 }
 
 // Streaming pass over all nodes in pre-order after the sweep: topology record and centre of every

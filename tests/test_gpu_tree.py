@@ -182,3 +182,29 @@ def test_fused_step_survives_arena_overflow(cuda_device):
             sim._call("psim_build_status")
         assert e.value.code == -4
         sim.close()
+
+
+@pytest.mark.parametrize("clump", [40, 3000])
+def test_dense_subcell_clumps_sort_by_the_full_key(cuda_device, clump):
+    """bodies closer than root / 65536 share the upper key word: the radix passes leave them in input order
+    and the run fix-up (insertion sort for short runs, CTA radix sort for long ones) must finish the job"""
+    rng = np.random.default_rng(5)
+    b = uniform_pm1(6000 + clump)
+    n = len(b["pos"])
+    # a clump of distinct positions inside one 0.1 A cell of a 16 000 A domain (cell of the upper word: 0.24 A)
+    base = np.array([1000.3, -2000.7], np.float32)
+    grid = np.stack(np.meshgrid(np.arange(64), np.arange(64)), -1).reshape(-1, 2)[:clump]
+    b["pos"][:clump] = base + (grid * np.float32(0.1 / 64)).astype(np.float32)
+    sel = rng.permutation(n)
+    for k in ("pos", "charge", "radius", "mass", "species"):
+        if k in b and b[k] is not None:
+            b[k] = np.ascontiguousarray(b[k][sel])
+    b["hw"] = b["hh"] = 8000.0
+    assert len(np.unique(b["pos"], axis=0)) == n
+    for mode in (0, 1):
+        sim, o = build_both(b, mode)
+        keys = sim.quadtree.keys()
+        assert np.all(keys[:-1] <= keys[1:])
+        assert np.array_equal(sim.bodies.id.astype(np.int64), o.permutation())
+        assert_same_topology(canonical_from_nodes(sim.quadtree.nodes), o.canonical())
+        sim.close()
