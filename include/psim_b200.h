@@ -262,6 +262,22 @@ int32_t psim_set_electron_range(psim_ctx *ctx, uint64_t first, uint64_t count);
  * e_field (float2), electron rel_pos (float2), electron vel (float2); out[6] = body capacity,
  * out[7] = electron capacity */
 int32_t psim_device_ptrs(psim_ctx *ctx, uint64_t *out8);
+/* Sharded build (replaces the single work queue of Quadtree::build_internal,
+ * src/quadtree/quadtree.rs:197-345, across ranks).  Every rank holds all bodies; rank r sorts the keys of
+ * a contiguous range of 65 536 top-level cells and emits the tree nodes that start in it.  The pieces
+ * concatenate into exactly the single-GPU tree.  psim_shard_phase runs phase 0..5 in order; between
+ * phases the caller performs the exchange on the device buffers psim_shard_ptrs names:
+ *   after 0: nothing (out = first sorted body of each rank, world + 1 entries; synchronises)
+ *   after 1: all-gather of the sorted-order segments  [out[r], out[r+1]) of ptrs[0] (uint32 per body)
+ *   after 2, after 4: all-reduce (sum) of ptrs[1], ptrs[5] uint64 words
+ *   after 3: all-reduce (sum) of ptrs[2], ptrs[6] uint64 words
+ *   after 5: all-gather of the traversal segments [out[r], out[r+1]) of ptrs[3] and ptrs[4] (16 bytes
+ *            per node each; out = first traversal node of each rank; synchronises)
+ * ptrs[7] = node capacity.  The tree export (psim_download_nodes) and parity_mode 2 need the whole node
+ * array and are single-GPU only. */
+int32_t psim_shard_init(psim_ctx *ctx, uint32_t rank, uint32_t world);
+int32_t psim_shard_phase(psim_ctx *ctx, int32_t phase, int32_t mode, float hw, float hh, uint32_t *out);
+int32_t psim_shard_ptrs(psim_ctx *ctx, uint64_t *out8);
 /* the caller wrote positions into the device arrays (e.g. an all-gather): tree and grid are stale */
 int32_t psim_mark_positions_changed(psim_ctx *ctx);
 

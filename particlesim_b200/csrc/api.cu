@@ -15,6 +15,7 @@
 #include "polar.cuh"
 #include "sort.cuh"
 #include "traverse.cuh"
+#include "shard.cuh"
 #include "tree.cuh"
 
 using namespace psim;
@@ -64,6 +65,7 @@ struct psim_ctx {
   uint32_t* khi[2] = {nullptr, nullptr};   // upper key words, ping-pong buffers of the radix passes
   uint32_t* idx[2] = {nullptr, nullptr};
   uint32_t* long_runs = nullptr;           // [0] count, [1..] heads of long equal-upper-word runs
+  uint32_t* keys_idx_all = nullptr;        // sharded build: the all-gathered sorted order
   uint32_t* ckeys[2] = {nullptr, nullptr};
   uint32_t* cidx[2] = {nullptr, nullptr};
   SortScratch sc = {};
@@ -87,6 +89,25 @@ struct psim_ctx {
   uint32_t* inv = nullptr;
   bool tree_valid = false;
   bool perm_valid = false;
+
+  // sharded build (shard.cuh): allocated by psim_shard_init
+  struct Shard {
+    bool on = false;
+    uint32_t rank = 0, world = 1;
+    int phase = 0, mode = 0;
+    uint32_t halo = 0, n_local = 0, hl = 0, L = 0, s_lo = 0;
+    uint32_t* binhist = nullptr;
+    uint32_t* binprefix = nullptr;
+    uint32_t* nb_bin = nullptr;
+    uint32_t* trav_bin = nullptr;
+    uint64_t* lkeys = nullptr;
+    unsigned long long* xbuf = nullptr;  // kBins + kMaxRanks words (tables, all-reduced)
+    TopRec* heap = nullptr;              // kTopSlots records (all-reduced)
+    ShardPlan* plan = nullptr;
+    ShardMeta* meta = nullptr;
+    ShardPlan plan_h = {};
+    ShardMeta meta_h = {};
+  } sh;
 
   // cells
   uint32_t *cell_start = nullptr, *cell_end = nullptr, *order = nullptr, *body_cell = nullptr;
@@ -479,6 +500,47 @@ int32_t fetch_meta(psim_ctx* ctx) {
 }
 
 // ---- launch sequences (no host synchronisation inside) ------------------------------------------
+// bodies (and their electrons) into the order given by the sorted payload; swaps the body buffers
+int32_t gather_stage(psim_ctx* ctx, const uint32_t* idx0, const uint32_t* idx1, const SortPlan* plan, int npass) {
+  const uint32_t n = ctx->n;
+  cudaStream_t st = ctx->stream;
+  BodyArrays& in = ctx->b[ctx->cur];
+  BodyArrays& out = ctx->b[ctx->cur ^ 1];
+  if (ctx->hosted.active && ctx->hosted.late_q) {  // psim_step_host: the charges arrived during the sort
+    CK(cudaStreamWaitEvent(st, ctx->ev_q, 0));
+    hosted_charges_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(ctx->hosted.late_q, ctx->hosted.map, n, in.pqr);
+    LAUNCHED(ctx);
+    ctx->hosted.late_q = nullptr;
+  }
+  if (ctx->hosted.active && ctx->hosted.vel_src) {
+    // the velocities are not needed before the integrator: their copy starts here, so that it neither
+    // shares the link with the positions and charges nor delays their completion event
+    CK(cudaEventRecord(ctx->ev_start, st));
+    CK(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_start, 0));
+    CK(cudaMemcpyAsync(const_cast<float2*>(ctx->hosted.late_vel), ctx->hosted.vel_src, 8 * (size_t)n,
+                       cudaMemcpyHostToDevice, ctx->copy_in));
+    CK(cudaEventRecord(ctx->ev_vel, ctx->copy_in));
+    ctx->hosted.vel_src = nullptr;
+  }
+  gather_bodies_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(
+      idx0, idx1, plan, npass, n, in, out, ctx->perm, ctx->inv);
+  LAUNCHED(ctx);
+  ctx->cur ^= 1;
+  BodyArrays& b = ctx->b[ctx->cur];
+  if (ctx->m > 0) {
+    // electrons follow their bodies: new offsets from the permuted counts, then a grouped copy
+    const int eo = ctx->ecur, en = ctx->ecur ^ 1;
+    CK(exclusive_scan(EcountFn{b.ecount}, n, ctx->eoff[en], ctx->scan_partials, nullptr, st));
+    ctx->launches += 3;
+    regroup_electrons_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(
+        ctx->perm, b.ecount, ctx->eoff[eo], ctx->eoff[en], n, ctx->erel[eo], ctx->evel[eo],
+        ctx->ebody[en], ctx->erel[en], ctx->evel[en]);
+    LAUNCHED(ctx);
+    ctx->ecur = en;
+  }
+  return PSIM_OK;
+}
+
 int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
   const uint32_t n = ctx->n;
   cudaStream_t st = ctx->stream;
@@ -517,38 +579,11 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
                                                        kTreePasses, n, ctx->long_runs, ctx->long_runs + 1,
                                                        ctx->keys[0]);
   ctx->launches += 3;
-  if (ctx->hosted.active && ctx->hosted.late_q) {  // psim_step_host: the charges arrived during the sort
-    CK(cudaStreamWaitEvent(st, ctx->ev_q, 0));
-    hosted_charges_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(ctx->hosted.late_q, ctx->hosted.map, n, in.pqr);
-    LAUNCHED(ctx);
-    ctx->hosted.late_q = nullptr;
+  {
+    const int32_t rc = gather_stage(ctx, ctx->idx[0], ctx->idx[1], ctx->tree_plan, kTreePasses);
+    if (rc) return rc;
   }
-  if (ctx->hosted.active && ctx->hosted.vel_src) {
-    // the velocities are not needed before the integrator: their copy starts here, so that it neither
-    // shares the link with the positions and charges nor delays their completion event
-    CK(cudaEventRecord(ctx->ev_start, st));
-    CK(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_start, 0));
-    CK(cudaMemcpyAsync(const_cast<float2*>(ctx->hosted.late_vel), ctx->hosted.vel_src, 8 * (size_t)n,
-                       cudaMemcpyHostToDevice, ctx->copy_in));
-    CK(cudaEventRecord(ctx->ev_vel, ctx->copy_in));
-    ctx->hosted.vel_src = nullptr;
-  }
-  gather_bodies_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(
-      ctx->idx[0], ctx->idx[1], ctx->tree_plan, kTreePasses, n, in, out, ctx->perm, ctx->inv);
-  LAUNCHED(ctx);
-  ctx->cur ^= 1;
   BodyArrays& b = ctx->b[ctx->cur];
-  if (ctx->m > 0) {
-    // electrons follow their bodies: new offsets from the permuted counts, then a grouped copy
-    const int eo = ctx->ecur, en = ctx->ecur ^ 1;
-    CK(exclusive_scan(EcountFn{b.ecount}, n, ctx->eoff[en], ctx->scan_partials, nullptr, st));
-    ctx->launches += 3;
-    regroup_electrons_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(
-        ctx->perm, b.ecount, ctx->eoff[eo], ctx->eoff[en], n, ctx->erel[eo], ctx->evel[eo],
-        ctx->ebody[en], ctx->erel[en], ctx->evel[en]);
-    LAUNCHED(ctx);
-    ctx->ecur = en;
-  }
   const uint32_t c_eff = effective_capacity(ctx->cfg.leaf_capacity, ctx->cfg.thread_capacity);
   tree_count_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, st>>>(
       ctx->keys[1], ctx->keys[1], ctx->tree_plan, kTreePasses, b.pqr, n, c_eff, ctx->meta, ctx->le);
@@ -584,6 +619,151 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
   LAUNCHED(ctx);
   ctx->tree_valid = true;
   ctx->perm_valid = true;
+  return PSIM_OK;
+}
+
+// ---- sharded build (shard.cuh).  The phases alternate with the exchanges the host performs on the
+// buffers psim_shard_ptrs names (particlesim_b200/parallel.py):
+//   0  root, keys + bin histogram of all bodies, splitters        -> sync, out = body_lo[world + 1]
+//   1  owned keys: select, radix passes, run fix-up, index segment -> all-gather perm (uneven segments)
+//   2  gather bodies, halo keys, levels, node scan, table 1        -> all-reduce xbuf
+//   3  node offsets, emit, local sweeps, top heap                  -> all-reduce heap
+//   4  top sweep, centres, charged scan, table 2                   -> all-reduce xbuf
+//   5  traversal offsets, compaction into the rank's segment       -> sync, out = trav_lo[world + 1];
+//                                                                    all-gather travA / travB segments
+int32_t shard_phase(psim_ctx* ctx, int phase, int mode, float hw, float hh, uint32_t* out) {
+  auto& S = ctx->sh;
+  if (!S.on) return fail(ctx, PSIM_E_STATE, "psim_shard_phase: call psim_shard_init first");
+  if (ctx->cfg.strict_centres) return fail(ctx, PSIM_E_ARG, "sharded build: strict_centres is a single-GPU parity switch");
+  if (phase != 0 && phase != S.phase) return fail(ctx, PSIM_E_STATE, "psim_shard_phase: phases must run in order");
+  const uint32_t n = ctx->n;
+  cudaStream_t st = ctx->stream;
+  const uint32_t c_eff = effective_capacity(ctx->cfg.leaf_capacity, ctx->cfg.thread_capacity);
+  if (c_eff + 1 > kHaloMax) return fail(ctx, PSIM_E_ARG, "sharded build: leaf capacity above 2048");
+  if (n == 0) return fail(ctx, PSIM_E_ARG, "sharded build: no bodies");
+  const uint32_t nl = S.n_local;
+  switch (phase) {
+    case 0: {
+      ctx->tree_valid = ctx->perm_valid = ctx->host_map_valid = ctx->grid_valid = false;
+      S.mode = mode;
+      BodyArrays& in = ctx->b[ctx->cur];
+      int nb = 1;
+      if (mode == PSIM_BUILD_CONTAINING) {
+        nb = grid_for(ctx, n, 256, 4);
+        bounds_partial_kernel<<<nb, 256, 0, st>>>(in.pqr, n, ctx->bounds_partial);
+        LAUNCHED(ctx);
+      }
+      root_quad_kernel<<<1, 32, 0, st>>>(ctx->bounds_partial, nb, mode, hw, hh, n, ctx->meta);
+      CK(cudaMemsetAsync(S.binhist, 0, kBins * sizeof(uint32_t), st));
+      keygen_bins_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(in.pqr, n, ctx->meta, ctx->keys[0], S.binhist);
+      bin_split_kernel<<<1, 1024, 0, st>>>(S.binhist, n, S.world, S.binprefix, S.plan);
+      ctx->launches += 3;
+      CK(cudaMemcpyAsync(&S.plan_h, S.plan, sizeof(ShardPlan), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      S.s_lo = S.plan_h.body_lo[S.rank];
+      S.n_local = S.plan_h.body_lo[S.rank + 1] - S.s_lo;
+      S.halo = c_eff + 1;
+      S.hl = S.s_lo < S.halo ? S.s_lo : S.halo;
+      const uint32_t after = n - S.plan_h.body_lo[S.rank + 1];
+      S.L = S.hl + S.n_local + (after < S.halo ? after : S.halo);
+      ShardMeta& m = S.meta_h;
+      memset(&m, 0, sizeof m);
+      m.rank = S.rank, m.world = S.world, m.n_local = S.n_local, m.hl = S.hl, m.L = S.L;
+      m.body_base = S.s_lo - S.hl;
+      CK(cudaMemcpyAsync(S.meta, &m, sizeof m, cudaMemcpyHostToDevice, st));
+      if (out) memcpy(out, S.plan_h.body_lo, (S.world + 1) * sizeof(uint32_t));
+      break;
+    }
+    case 1: {
+      const uint32_t b0 = S.plan_h.bin_lo[S.rank], b1 = S.plan_h.bin_lo[S.rank + 1];
+      CK(exclusive_scan(InRangeFn{ctx->keys[0], b0, b1}, n, ctx->trav_rank, ctx->scan_partials, nullptr, st));
+      select_owned_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(ctx->keys[0], ctx->trav_rank, n, b0, b1,
+                                                                     ctx->khi[0], ctx->idx[0]);
+      ctx->launches += 4;
+      ctx->sc.plan = ctx->tree_plan;
+      CK(onesweep_sort<uint32_t>(ctx->khi[0], ctx->khi[1], ctx->idx[0], ctx->idx[1], nl, 0, kTreePasses, ctx->sc,
+                                 ctx->sm_count, st));
+      ctx->launches += 2 + kTreePasses;
+      uint64_t* lk = S.lkeys + S.hl;
+      gather_keys_kernel<<<grid_for(ctx, nl, 256, 16), 256, 0, st>>>(ctx->keys[0], ctx->idx[0], ctx->idx[1],
+                                                                    ctx->tree_plan, kTreePasses, nl, lk, ctx->long_runs);
+      fix_runs_kernel<<<grid_for(ctx, nl, 256, 16), 256, 0, st>>>(lk, ctx->idx[0], ctx->idx[1], ctx->tree_plan,
+                                                                 kTreePasses, nl, ctx->long_runs, ctx->long_runs + 1);
+      sort_long_runs_kernel<<<ctx->sm_count, 256, 0, st>>>(lk, ctx->idx[0], ctx->idx[1], ctx->tree_plan, kTreePasses,
+                                                           nl, ctx->long_runs, ctx->long_runs + 1, ctx->keys[0]);
+      copy_sorted_idx_kernel<<<grid_for(ctx, nl, 256, 16), 256, 0, st>>>(ctx->idx[0], ctx->idx[1], ctx->tree_plan,
+                                                                        kTreePasses, nl, ctx->keys_idx_all + S.s_lo);
+      ctx->launches += 4;
+      break;
+    }
+    case 2: {
+      // keys_idx_all now holds the global sorted order (all-gathered)
+      const int32_t rc = gather_stage(ctx, ctx->keys_idx_all, ctx->keys_idx_all, ctx->tree_plan, kTreePasses);
+      if (rc) return rc;
+      BodyArrays& b = ctx->b[ctx->cur];
+      halo_kernel<<<grid_for(ctx, 2 * S.halo, 256, 1), 256, 0, st>>>(S.binprefix, S.meta, S.lkeys, ctx->le);
+      tree_count_range_kernel<<<grid_for(ctx, nl, 256, 8), 256, 0, st>>>(
+          S.lkeys, b.pqr + (S.s_lo - S.hl), S.L, S.hl, nl, c_eff, kShardDepth, ctx->meta, ctx->le);
+      CK(exclusive_scan(LeCountFn{ctx->le}, S.L, ctx->nodebase, ctx->scan_partials, &S.meta->M_local, st));
+      CK(cudaMemsetAsync(S.xbuf, 0, (kBins + kMaxRanks) * sizeof(unsigned long long), st));
+      table_nodes_kernel<<<grid_for(ctx, kBins, 256, 2), 256, 0, st>>>(S.binhist, S.binprefix, S.plan, S.meta,
+                                                                      ctx->nodebase, &S.meta->M_local, S.xbuf);
+      ctx->launches += 6;
+      break;
+    }
+    case 3: {
+      BodyArrays& b = ctx->b[ctx->cur];
+      resolve_table_kernel<<<grid_for(ctx, kBins + 1, 256, 2), 256, 0, st>>>(S.binhist, S.binprefix, S.plan, S.meta,
+                                                                            S.xbuf, n, 0, S.nb_bin);
+      globalize_nodebase_kernel<<<grid_for(ctx, S.L, 256, 16), 256, 0, st>>>(S.meta, S.lkeys, S.nb_bin, ctx->nodebase,
+                                                                            ctx->t.ndepth);
+      level_scan_shard_kernel<<<1, 32, 0, st>>>(ctx->meta, S.meta, ctx->node_cap);
+      CK(cudaMemsetAsync(S.heap, 0, kTopSlots * sizeof(TopRec), st));
+      tree_emit_range_kernel<<<grid_for(ctx, nl, 128, 16), 128, 0, st>>>(
+          S.lkeys, S.meta, ctx->le, ctx->nodebase, b.pqr + (S.s_lo - S.hl), ctx->cfg.leaf_capacity,
+          ctx->cfg.thread_capacity, ctx->meta, ctx->t, S.heap);
+      for (int level = kMaxLevels - 1; level >= kShardDepth; --level)
+        aggregate_level_shard_kernel<<<ctx->sm_count * 16, 128, 0, st>>>(level, ctx->meta, S.meta, ctx->t);
+      heap_bins_kernel<<<grid_for(ctx, kBins, 256, 2), 256, 0, st>>>(S.plan, S.meta, ctx->t, S.heap);
+      ctx->launches += 5 + (kMaxLevels - kShardDepth);
+      break;
+    }
+    case 4: {
+      BodyArrays& b = ctx->b[ctx->cur];
+      heap_sweep_kernel<<<1, 1024, 0, st>>>(S.heap);
+      heap_writeback_kernel<<<grid_for(ctx, kTopSlots, 256, 2), 256, 0, st>>>(S.meta, S.heap, ctx->t);
+      finalize_nodes_shard_kernel<<<grid_for(ctx, (uint64_t)nl * 2 + 1, 256, 16), 256, 0, st>>>(
+          ctx->meta, S.meta, b.pqr, b.accm, S.lkeys, S.binprefix, ctx->t);
+      CK(exclusive_scan_dyn(ChargedFlagFn{ctx->t.ndepth}, &S.meta->M_local, ctx->node_cap, ctx->trav_rank,
+                            ctx->scan_partials, &S.meta->T_local, st));
+      CK(cudaMemsetAsync(S.xbuf, 0, (kBins + kMaxRanks) * sizeof(unsigned long long), st));
+      table_trav_kernel<<<grid_for(ctx, kBins, 256, 2), 256, 0, st>>>(S.binhist, S.plan, S.meta, S.nb_bin, ctx->trav_rank,
+                                                                     &S.meta->T_local, S.xbuf);
+      ctx->launches += 7;
+      break;
+    }
+    case 5: {
+      resolve_table_kernel<<<grid_for(ctx, kBins + 1, 256, 2), 256, 0, st>>>(S.binhist, S.binprefix, S.plan, S.meta,
+                                                                            S.xbuf, n, 1, S.trav_bin);
+      compact_traversal_shard_kernel<<<grid_for(ctx, (uint64_t)nl * 2 + 1, 256, 16), 256, 0, st>>>(
+          S.meta, ctx->t.nodeA, ctx->t.nodeB, ctx->trav_rank, S.nb_bin, S.trav_bin, ctx->node_cap, ctx->travA,
+          ctx->travB, ctx->trav_count);
+      ctx->launches += 2;
+      CK(cudaMemcpyAsync(&S.meta_h, S.meta, sizeof(ShardMeta), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (S.meta_h.M_local > ctx->node_cap || S.meta_h.T_total > ctx->node_cap)
+        return fail(ctx, PSIM_E_NODE_OVERFLOW, "sharded build: node arena overflow (raise node_factor)");
+      if (out) memcpy(out, S.meta_h.trav_lo, (S.world + 1) * sizeof(uint32_t));
+      ctx->tree_valid = true;   // once the caller has all-gathered the traversal segments
+      ctx->perm_valid = true;
+      break;
+    }
+    default:
+      return fail(ctx, PSIM_E_ARG, "psim_shard_phase: phase 0..5");
+  }
+  S.phase = phase == 5 ? 0 : phase + 1;
+  const cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) return fail(ctx, PSIM_E_CUDA, "sharded build launch", le);
   return PSIM_OK;
 }
 
@@ -840,7 +1020,9 @@ void free_all(psim_ctx* c) {
     F(c->keys[k]), F(c->khi[k]), F(c->idx[k]), F(c->ckeys[k]), F(c->cidx[k]);
   }
   F(c->epts), F(c->efld);
-  F(c->sc.hist), F(c->sc.status), F(c->sc.ticket), F(c->tree_plan), F(c->cell_plan), F(c->long_runs);
+  F(c->sc.hist), F(c->sc.status), F(c->sc.ticket), F(c->tree_plan), F(c->cell_plan), F(c->long_runs), F(c->keys_idx_all);
+  F(c->sh.binhist), F(c->sh.binprefix), F(c->sh.nb_bin), F(c->sh.trav_bin), F(c->sh.lkeys), F(c->sh.xbuf), F(c->sh.heap);
+  F(c->sh.plan), F(c->sh.meta);
   F(c->meta), F(c->le), F(c->nodebase), F(c->scan_partials), F(c->irank), F(c->bounds_partial);
   F(c->t.nodeA), F(c->t.nodeB), F(c->t.node_mass), F(c->t.parent), F(c->t.sums), F(c->t.level_nodes);
   F(c->t.rec), F(c->t.ndepth);
@@ -917,12 +1099,12 @@ int32_t psim_create(int32_t device, uint64_t max_bodies, uint64_t max_electrons,
   ctx->sc.status_words = sort_status_words((uint32_t)nb, kTreePasses);
   A(&ctx->sc.status, ctx->sc.status_words);
   A(&ctx->tree_plan, 1), A(&ctx->cell_plan, 1), A(&ctx->long_runs, nb / kFixInsertion + 2);
-  A(&ctx->meta, 1), A(&ctx->le, nb), A(&ctx->nodebase, nb + 1);
+  A(&ctx->meta, 1), A(&ctx->le, nb + 2 * kHaloMax + 2), A(&ctx->nodebase, nb + 2 * kHaloMax + 2);
   A(&ctx->scan_partials, (size_t)scan_num_tiles(ctx->node_cap > nb ? ctx->node_cap : (uint32_t)nb) + 1);
   A(&ctx->irank, ctx->node_cap), A(&ctx->bounds_partial, (size_t)ctx->sm_count * 4 + 1);
   A(&ctx->t.nodeA, ctx->node_cap), A(&ctx->t.nodeB, ctx->node_cap), A(&ctx->t.node_mass, ctx->node_cap);
   A(&ctx->t.parent, ctx->node_cap), A(&ctx->t.sums, ctx->node_cap), A(&ctx->t.level_nodes, ctx->node_cap);
-  A(&ctx->t.rec, ctx->node_cap), A(&ctx->t.ndepth, ctx->node_cap);
+  A(&ctx->t.rec, ctx->node_cap), A(&ctx->t.ndepth, (size_t)ctx->node_cap + 1);
   A(&ctx->travA, ctx->node_cap), A(&ctx->travB, ctx->node_cap), A(&ctx->trav_rank, ctx->node_cap), A(&ctx->trav_count, 1);
   ctx->t.node_cap = ctx->node_cap;
   A(&ctx->perm, nb), A(&ctx->inv, nb);
@@ -1670,6 +1852,40 @@ int32_t psim_device_ptrs(psim_ctx* ctx, uint64_t* out8) {
   out8[3] = (uint64_t)(uintptr_t)b.efield;
   out8[4] = (uint64_t)(uintptr_t)ctx->erel[ctx->ecur], out8[5] = (uint64_t)(uintptr_t)ctx->evel[ctx->ecur];
   out8[6] = ctx->cap_bodies, out8[7] = ctx->cap_elec;
+  return PSIM_OK;
+}
+int32_t psim_shard_init(psim_ctx* ctx, uint32_t rank, uint32_t world) {
+  if (!ctx || world < 1 || world > (uint32_t)kMaxRanks || rank >= world)
+    return fail(ctx, PSIM_E_ARG, "psim_shard_init: rank / world (at most 64 ranks)");
+  auto& S = ctx->sh;
+  if (!S.binhist) {
+    bool ok = true;
+    auto A = [&](auto** p, size_t cnt) {
+      if (ok && dalloc(p, cnt) != cudaSuccess) ok = false;
+    };
+    A(&S.binhist, kBins), A(&S.binprefix, kBins + 1), A(&S.nb_bin, kBins + 1), A(&S.trav_bin, kBins + 1);
+    A(&S.lkeys, ctx->cap_bodies + 2 * kHaloMax + 2), A(&S.xbuf, kBins + kMaxRanks), A(&S.heap, kTopSlots);
+    A(&S.plan, 1), A(&S.meta, 1), A(&ctx->keys_idx_all, ctx->cap_bodies);
+    if (!ok) {
+      cudaGetLastError();
+      return fail(ctx, PSIM_E_OOM, "psim_shard_init: device allocation");
+    }
+  }
+  S.on = true, S.rank = rank, S.world = world, S.phase = 0;
+  return PSIM_OK;
+}
+int32_t psim_shard_phase(psim_ctx* ctx, int32_t phase, int32_t mode, float hw, float hh, uint32_t* out) {
+  if (!ctx) return PSIM_E_ARG;
+  if (mode != PSIM_BUILD_CONTAINING && mode != PSIM_BUILD_DOMAIN) return fail(ctx, PSIM_E_ARG, "psim_shard_phase: mode");
+  return shard_phase(ctx, phase, mode, hw, hh, out);
+}
+int32_t psim_shard_ptrs(psim_ctx* ctx, uint64_t* out8) {
+  if (!ctx || !out8) return PSIM_E_ARG;
+  if (!ctx->sh.on) return fail(ctx, PSIM_E_STATE, "psim_shard_ptrs: call psim_shard_init first");
+  out8[0] = (uint64_t)(uintptr_t)ctx->keys_idx_all, out8[1] = (uint64_t)(uintptr_t)ctx->sh.xbuf;
+  out8[2] = (uint64_t)(uintptr_t)ctx->sh.heap, out8[3] = (uint64_t)(uintptr_t)ctx->travA;
+  out8[4] = (uint64_t)(uintptr_t)ctx->travB;
+  out8[5] = kBins + kMaxRanks, out8[6] = (uint64_t)kTopSlots * (sizeof(TopRec) / 8), out8[7] = ctx->node_cap;
   return PSIM_OK;
 }
 int32_t psim_mark_positions_changed(psim_ctx* ctx) {

@@ -142,6 +142,9 @@ __global__ void level_scan_kernel(TreeMeta* __restrict__ meta, uint32_t node_cap
 // of each depth its bodies start, reserves one contiguous range per depth with a single global atomic,
 // and then hands slots out of shared-memory counters while it emits.
 struct DeviceSink {
+  static constexpr bool kTop = false;
+  __device__ __forceinline__ void top_leaf(int, uint64_t, uint32_t, const NodeRec&) {}
+  __device__ __forceinline__ void top_internal(int, uint64_t, uint32_t) {}
   TreeMeta* meta;
   uint32_t* s_cursor;  // [kLevels] next free slot per depth (absolute index into level_nodes)
   __device__ __forceinline__ uint32_t level_slot(int d) { return atomicAdd(&s_cursor[d], 1u); }
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(256)
   const uint32_t n_bodies = meta->n;
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t node = blockIdx.x * blockDim.x + threadIdx.x; node < M; node += stride)
-    finalize_node(node, M, n_bodies, root_size, pqr, accm, t);
+    finalize_node(node, root_size, pqr, accm, t, SubtreeEndLocal{M, n_bodies, t.nodeB});
 }
 
 // one level of the export sweep (psim_download_nodes only)

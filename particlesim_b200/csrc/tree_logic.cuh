@@ -153,7 +153,11 @@ template <class Sink>
 PSIM_HD void emit_nodes_for_body(const uint64_t* keys, uint32_t n, uint32_t i, uint16_t lev,
                                  const uint32_t* nodebase, uint32_t M, const float4* pqr,
                                  const float4* accm, uint32_t leaf_capacity, uint32_t thread_capacity,
-                                 float root_size, int dcap, const TreeArrays& t, Sink& sink) {
+                                 float root_size, int dcap, const TreeArrays& t, Sink& sink,
+                                 uint32_t body_base = 0, int min_bucket_depth = 0) {
+  // body_base / min_bucket_depth / Sink::kTop serve the sharded build (shard.cuh): `keys`, `pqr` and
+  // `nodebase` are then a rank's slice of the sorted order plus a halo, i + body_base is the global body
+  // index, cells above the shard depth are reported to the sink instead of the level buckets
   (void)accm;
   const int lam = le_lambda(lev), ell = le_ell(lev);
   if (!(lam < ell)) return;
@@ -188,19 +192,21 @@ PSIM_HD void emit_nodes_for_body(const uint64_t* keys, uint32_t n, uint32_t i, u
     }
     if (count > 1 && d == dcap) sink.cap_leaf();
     t.nodeA[node] = make_float4(wx, wy, tq, size);
-    t.nodeB[node] = make_uint4(next, i, count, (uint32_t)d | kNodeLeaf | (agg ? 0u : kNodeZeroAgg) |
-                                                   (aq > 0.0 ? kNodeCharged : 0u));
+    t.nodeB[node] = make_uint4(next, i + body_base, count, (uint32_t)d | kNodeLeaf | (agg ? 0u : kNodeZeroAgg) |
+                                                               (aq > 0.0 ? kNodeCharged : 0u));
     const bool last = (j >= n) || lcp_levels(keys[i], keys[j]) < d - 1;
     NodeRec r;
     r.aq = aq, r.aqx = aqx, r.aqy = aqy, r.charge = tq, r.next = next | (last ? kLastSibling : 0u);
     t.rec[node] = r;
     t.ndepth[node] = (uint8_t)((uint32_t)d | (aq > 0.0 ? kDepthCharged : 0u));
+    if (Sink::kTop && d <= min_bucket_depth) sink.top_leaf(d, keys[i], node, r);
   }
   for (int d = ell - 1; d > lam; --d) {
     const uint32_t node = base + (uint32_t)(d - lam - 1);
-    t.nodeB[node] = make_uint4(0u, i, 0u, (uint32_t)d);
+    t.nodeB[node] = make_uint4(0u, i + body_base, 0u, (uint32_t)d);
     t.ndepth[node] = (uint8_t)d;
-    t.level_nodes[sink.level_slot(d)] = node;
+    if (d >= min_bucket_depth) t.level_nodes[sink.level_slot(d)] = node;
+    if (Sink::kTop && d <= min_bucket_depth) sink.top_internal(d, keys[i], node);
   }
 }
 
@@ -232,8 +238,15 @@ PSIM_HD void aggregate_node_lean(uint32_t node, int depth, uint32_t M, const Tre
 // internal node from its sums.  A node whose Σ|q| is <= 1e-6 takes the reference's mass / centroid
 // fall-back by a direct pass over its bodies; for Σ|q| == 0 (no charge below: the node
 // can never contribute to a field sum) that is left to the export sweep.
-PSIM_HD void finalize_node(uint32_t node, uint32_t M, uint32_t n_bodies, float root_size,
-                           const float4* pqr, const float4* accm, const TreeArrays& t) {
+struct SubtreeEndLocal {  // first body after the subtree that ends where node c starts
+  uint32_t M, n_bodies;
+  const uint4* nodeB;
+  PSIM_HD uint32_t operator()(uint32_t c, const uint4&) const { return c < M ? nodeB[c].y : n_bodies; }
+};
+
+template <class SubtreeEnd>
+PSIM_HD void finalize_node(uint32_t node, float root_size, const float4* pqr, const float4* accm,
+                           const TreeArrays& t, const SubtreeEnd& subtree_end) {
   uint4 nb = t.nodeB[node];
   if (nb.w & kNodeLeaf) return;
   const NodeRec r = t.rec[node];
@@ -245,7 +258,7 @@ PSIM_HD void finalize_node(uint32_t node, uint32_t M, uint32_t n_bodies, float r
   if (r.aq > (double)1e-6f) {
     px = (float)(r.aqx / r.aq), py = (float)(r.aqy / r.aq);
   } else if (r.aq > 0.0) {
-    const uint32_t b0 = nb.y, b1 = (c < M) ? t.nodeB[c].y : n_bodies;
+    const uint32_t b0 = nb.y, b1 = subtree_end(c, nb);
     double m = 0.0, mx = 0.0, my = 0.0, x = 0.0, y = 0.0;
     for (uint32_t b = b0; b < b1; ++b) {
       const float4 p = pqr[b];

@@ -44,6 +44,89 @@ def all_gather_slices(full, width: int, rank: int, world: int, dist, scratch=Non
     return full
 
 
+def all_gatherv(full, offsets, rank: int, dist):
+    """In-place all-gather of UNEVEN row segments: rank r contributes rows [offsets[r], offsets[r+1]) of
+    `full`.  One broadcast per non-empty segment (every rank knows all the sizes, so no size exchange)."""
+    for r in range(len(offsets) - 1):
+        a, b = int(offsets[r]), int(offsets[r + 1])
+        if b > a:
+            dist.broadcast(full[a:b], src=r)
+    return full
+
+
+class DistComm:
+    """exchanges of the sharded build over torch.distributed (NCCL on GPUs, gloo in the CPU tests); the
+    lists hold one tensor per LOCAL rank, i.e. one"""
+
+    def __init__(self, dist, rank: int):
+        self.dist, self.rank = dist, rank
+
+    def all_gatherv(self, tensors, offsets):
+        all_gatherv(tensors[0], offsets, self.rank, self.dist)
+
+    def all_reduce(self, tensors):
+        self.dist.all_reduce(tensors[0])
+
+
+class LoopbackComm:
+    """all ranks live in this process (one context each, e.g. on one GPU): the exchanges are copies.  Used
+    by the single-GPU tests of the sharded build."""
+
+    def all_gatherv(self, tensors, offsets):
+        for r, src in enumerate(tensors):
+            a, b = int(offsets[r]), int(offsets[r + 1])
+            for q, dst in enumerate(tensors):
+                if q != r and b > a:
+                    dst[a:b].copy_(src[a:b])
+
+    def all_reduce(self, tensors):
+        total = tensors[0].clone()
+        for t in tensors[1:]:
+            total += t
+        for t in tensors:
+            t.copy_(total)
+
+
+def shard_views(sim, torch):
+    """torch views of the exchange buffers of psim_shard_ptrs (bit containers: int32 / int64)"""
+    p = np.zeros(8, np.uint64)
+    sim._call("psim_shard_ptrs", p.ctypes.data)
+    mk = lambda ptr, shape, ts: torch.as_tensor(_DevArray(ptr, shape, ts), device="cuda")
+    cap = int(p[7])
+    return dict(order=mk(p[0], (int(sim._shard_nb),), "<i4"), xbuf=mk(p[1], (int(p[5]),), "<i8"),
+                heap=mk(p[2], (int(p[6]),), "<i8"), travA=mk(p[3], (cap, 4), "<i4"), travB=mk(p[4], (cap, 4), "<i4"))
+
+
+def sharded_build(sims, mode: int, hw: float, hh: float, comm, torch):
+    """Quadtree::build / build_with_domain across ranks (include/psim_b200.h, psim_shard_phase): `sims`
+    are the contexts of the ranks that live in this process (one under torchrun)."""
+    world = sims[0].world
+    lo = [np.zeros(world + 1, np.uint32) for _ in sims]
+    views = [s._shard_view_cache if getattr(s, "_shard_view_cache", None) else None for s in sims]
+    for k, s in enumerate(sims):
+        if views[k] is None:
+            views[k] = s._shard_view_cache = shard_views(s, torch)
+
+    def phase(k, out=None):
+        for i, s in enumerate(sims):
+            s._call("psim_shard_phase", k, mode, hw, hh, out[i].ctypes.data if out is not None else None)
+
+    phase(0, lo)
+    phase(1)
+    comm.all_gatherv([v["order"] for v in views], lo[0])
+    phase(2)
+    comm.all_reduce([v["xbuf"] for v in views])
+    phase(3)
+    comm.all_reduce([v["heap"] for v in views])
+    phase(4)
+    comm.all_reduce([v["xbuf"] for v in views])
+    tl = [np.zeros(world + 1, np.uint32) for _ in sims]
+    phase(5, tl)
+    comm.all_gatherv([v["travA"] for v in views], tl[0])
+    comm.all_gatherv([v["travB"] for v in views], tl[0])
+    return lo[0], tl[0]
+
+
 class _DevArray:
     """zero-copy view of library-owned device memory for torch (CUDA array interface v2)"""
 
@@ -53,7 +136,7 @@ class _DevArray:
 
 
 class ShardedSimulation(Simulation):
-    def __init__(self, bodies, domain_width, domain_height, *, rank: int, world: int, **kw):
+    def __init__(self, bodies, domain_width, domain_height, *, rank: int, world: int, local_build: bool = True, **kw):
         n, m = len(bodies), len(bodies.ebody)
         self.rank, self.world = rank, world
         self.wb, self.we = shard_width(n, world), shard_width(m, world)
@@ -65,6 +148,11 @@ class ShardedSimulation(Simulation):
         self.torch, self.dist = torch, dist
         self._scratch_b = torch.empty((self.wb, 4), dtype=torch.float32, device="cuda")
         self._scratch_e = torch.empty((self.we, 2), dtype=torch.float32, device="cuda")
+        self._shard_nb = kw["max_bodies"]
+        self.local_build = local_build and world > 1
+        if self.local_build:
+            self._call("psim_shard_init", rank, world)
+            self._comm = DistComm(dist, rank)
         f, c = shard_range(n, world, rank)
         self._call("psim_set_target_range", f, c)
         if m:
@@ -79,6 +167,14 @@ class ShardedSimulation(Simulation):
         mk = lambda ptr, rows, cols: t.as_tensor(_DevArray(ptr, (rows, cols)), device="cuda")
         return dict(pqr=mk(p[0], nb, 4), velz=mk(p[1], nb, 4), erel=mk(p[4], ne, 2) if ne else None,
                     evel=mk(p[5], ne, 2) if ne else None)
+
+    def _build(self, mode, hw, hh):
+        """each rank builds the part of the tree that starts in its key range (local_build), or every rank
+        builds the whole tree (the v1 scheme, kept for comparison)"""
+        if self.local_build:
+            sharded_build([self], mode, hw, hh, self._comm, self.torch)
+        else:
+            self._call("psim_build_async", mode, hw, hh)
 
     def step_device(self, params=None, record=False):
         """Simulation::step's hot path (simulation.rs:1000-1196), sharded.  record=True keeps CUDA events
@@ -95,7 +191,7 @@ class ShardedSimulation(Simulation):
 
         mark()
         C("psim_reset_acc")
-        C("psim_build_async", _lib.BUILD_CONTAINING, 0.0, 0.0)
+        self._build(_lib.BUILD_CONTAINING, 0.0, 0.0)
         mark()
         cell = self.force_cell_size()
         if p.do_short_range and cell > 0.0:
@@ -114,7 +210,7 @@ class ShardedSimulation(Simulation):
             C("psim_mark_positions_changed")
         mark()
         if p.do_electrons:
-            C("psim_build_async", _lib.BUILD_DOMAIN, p.hw, p.hh)
+            self._build(_lib.BUILD_DOMAIN, p.hw, p.hh)
             mark()
             C("psim_update_electrons", p.bg_x, p.bg_y, p.dt, p.k_e)
             if self.we:

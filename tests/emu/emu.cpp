@@ -18,6 +18,9 @@ using namespace psim;
 
 namespace {
 struct HostSink {
+  static constexpr bool kTop = false;
+  void top_leaf(int, uint64_t, uint32_t, const NodeRec&) {}
+  void top_internal(int, uint64_t, uint32_t) {}
   TreeMeta* meta;
   uint32_t level_slot(int d) { return meta->level_start[d] + meta->level_cursor[d]++; }
   void zero_leaf() { meta->num_zero_leaves++; }
@@ -123,7 +126,7 @@ uint32_t emu_build(void* h, uint32_t n, const float* pos_xy, const float* mass, 
   for (int level = kMaxLevels - 1; level >= 0; --level)
     for (uint32_t k = e.meta.level_start[level]; k < e.meta.level_start[level + 1]; ++k)
       aggregate_node_lean(e.level_nodes[k], level, M, e.t);
-  for (uint32_t node = 0; node < M; ++node) finalize_node(node, M, n, r.size, e.pqr.data(), e.accm.data(), e.t);
+  for (uint32_t node = 0; node < M; ++node) finalize_node(node, r.size, e.pqr.data(), e.accm.data(), e.t, SubtreeEndLocal{M, n, e.t.nodeB});
   if (M && (e.nodeB[0].w & kNodeLeaf)) {
     float lm = 0.f;
     if (!(e.nodeB[0].w & kNodeZeroAgg))
