@@ -181,7 +181,9 @@ def workload_config(args, n):
     return {"workload": "configs[3]: uniform electrolyte (Li+/PF6-/EC/DMC 342:342:2393:2394), electron polarization "
                         "field sampling, full hot-path step", "n_bodies": int(n), "theta": args.theta, "epsilon": 2.0,
             "leaf_capacity": 1, "density_per_A2": 0.0625, "seed": "0xC0FFEE", "parity_mode": int(args.ieee),
-            "l2": "working set >> 126 MB L2, no flush needed", "parallelism": f"morton-sharded x{args.gpus}"}
+            "l2": "working set >> 126 MB L2, no flush needed", "parallelism": f"morton-sharded x{args.gpus}",
+            "multi_gpu_build": "n/a" if args.gpus == 1 else ("replicated" if args.replicated_build else
+                                                            "sharded by key range (65536 top-level cells), tree pieces all-gathered")}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -206,7 +208,7 @@ def run_ours(args):
     if world > 1:
         from particlesim_b200.parallel import ShardedSimulation
         sim = ShardedSimulation(b, hw, hh, theta=args.theta, parity_mode=int(args.ieee), device=local_rank,
-                                stream=stream, rank=rank, world=world)
+                                stream=stream, rank=rank, world=world, local_build=not args.replicated_build)
     else:
         sim = Simulation(b, hw, hh, theta=args.theta, parity_mode=int(args.ieee), device=local_rank, stream=stream)
     sim.config.coulomb_constant = float(KE)
@@ -406,6 +408,8 @@ def main():
                          "both are tested against the oracle at the 1e-5 tolerance")
     ap.add_argument("--cpu-n", type=int, default=1_000_000, help="bodies in the CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--replicated-build", action="store_true",
+                    help="multi-GPU: every rank builds the whole tree (the v1 scheme) instead of its key range")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

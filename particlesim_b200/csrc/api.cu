@@ -97,6 +97,7 @@ struct psim_ctx {
     int phase = 0, mode = 0;
     uint32_t halo = 0, n_local = 0, hl = 0, L = 0, s_lo = 0;
     uint32_t* binhist = nullptr;
+    uint16_t* bins = nullptr;
     uint32_t* binprefix = nullptr;
     uint32_t* nb_bin = nullptr;
     uint32_t* trav_bin = nullptr;
@@ -655,7 +656,7 @@ int32_t shard_phase(psim_ctx* ctx, int phase, int mode, float hw, float hh, uint
       }
       root_quad_kernel<<<1, 32, 0, st>>>(ctx->bounds_partial, nb, mode, hw, hh, n, ctx->meta);
       CK(cudaMemsetAsync(S.binhist, 0, kBins * sizeof(uint32_t), st));
-      keygen_bins_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(in.pqr, n, ctx->meta, ctx->keys[0], S.binhist);
+      bins_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(in.pqr, n, ctx->meta, S.bins, S.binhist);
       bin_split_kernel<<<1, 1024, 0, st>>>(S.binhist, n, S.world, S.binprefix, S.plan);
       ctx->launches += 3;
       CK(cudaMemcpyAsync(&S.plan_h, S.plan, sizeof(ShardPlan), cudaMemcpyDeviceToHost, st));
@@ -676,9 +677,11 @@ int32_t shard_phase(psim_ctx* ctx, int phase, int mode, float hw, float hh, uint
     }
     case 1: {
       const uint32_t b0 = S.plan_h.bin_lo[S.rank], b1 = S.plan_h.bin_lo[S.rank + 1];
-      CK(exclusive_scan(InRangeFn{ctx->keys[0], b0, b1}, n, ctx->trav_rank, ctx->scan_partials, nullptr, st));
-      select_owned_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(ctx->keys[0], ctx->trav_rank, n, b0, b1,
-                                                                     ctx->khi[0], ctx->idx[0]);
+      // keys[0]: the owned bodies' keys by compact slot; nodebase (free until phase 2): their body indices
+      CK(exclusive_scan(InRangeFn{S.bins, b0, b1}, n, ctx->trav_rank, ctx->scan_partials, nullptr, st));
+      select_owned_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(ctx->b[ctx->cur].pqr, S.bins, ctx->trav_rank, n,
+                                                                     b0, b1, ctx->meta, ctx->keys[0], ctx->khi[0],
+                                                                     ctx->idx[0], ctx->nodebase);
       ctx->launches += 4;
       ctx->sc.plan = ctx->tree_plan;
       CK(onesweep_sort<uint32_t>(ctx->khi[0], ctx->khi[1], ctx->idx[0], ctx->idx[1], nl, 0, kTreePasses, ctx->sc,
@@ -692,7 +695,8 @@ int32_t shard_phase(psim_ctx* ctx, int phase, int mode, float hw, float hh, uint
       sort_long_runs_kernel<<<ctx->sm_count, 256, 0, st>>>(lk, ctx->idx[0], ctx->idx[1], ctx->tree_plan, kTreePasses,
                                                            nl, ctx->long_runs, ctx->long_runs + 1, ctx->keys[0]);
       copy_sorted_idx_kernel<<<grid_for(ctx, nl, 256, 16), 256, 0, st>>>(ctx->idx[0], ctx->idx[1], ctx->tree_plan,
-                                                                        kTreePasses, nl, ctx->keys_idx_all + S.s_lo);
+                                                                        kTreePasses, nl, ctx->nodebase,
+                                                                        ctx->keys_idx_all + S.s_lo);
       ctx->launches += 4;
       break;
     }
@@ -1021,7 +1025,7 @@ void free_all(psim_ctx* c) {
   }
   F(c->epts), F(c->efld);
   F(c->sc.hist), F(c->sc.status), F(c->sc.ticket), F(c->tree_plan), F(c->cell_plan), F(c->long_runs), F(c->keys_idx_all);
-  F(c->sh.binhist), F(c->sh.binprefix), F(c->sh.nb_bin), F(c->sh.trav_bin), F(c->sh.lkeys), F(c->sh.xbuf), F(c->sh.heap);
+  F(c->sh.binhist), F(c->sh.bins), F(c->sh.binprefix), F(c->sh.nb_bin), F(c->sh.trav_bin), F(c->sh.lkeys), F(c->sh.xbuf), F(c->sh.heap);
   F(c->sh.plan), F(c->sh.meta);
   F(c->meta), F(c->le), F(c->nodebase), F(c->scan_partials), F(c->irank), F(c->bounds_partial);
   F(c->t.nodeA), F(c->t.nodeB), F(c->t.node_mass), F(c->t.parent), F(c->t.sums), F(c->t.level_nodes);
@@ -1863,7 +1867,7 @@ int32_t psim_shard_init(psim_ctx* ctx, uint32_t rank, uint32_t world) {
     auto A = [&](auto** p, size_t cnt) {
       if (ok && dalloc(p, cnt) != cudaSuccess) ok = false;
     };
-    A(&S.binhist, kBins), A(&S.binprefix, kBins + 1), A(&S.nb_bin, kBins + 1), A(&S.trav_bin, kBins + 1);
+    A(&S.binhist, kBins), A(&S.bins, ctx->cap_bodies), A(&S.binprefix, kBins + 1), A(&S.nb_bin, kBins + 1), A(&S.trav_bin, kBins + 1);
     A(&S.lkeys, ctx->cap_bodies + 2 * kHaloMax + 2), A(&S.xbuf, kBins + kMaxRanks), A(&S.heap, kTopSlots);
     A(&S.plan, 1), A(&S.meta, 1), A(&ctx->keys_idx_all, ctx->cap_bodies);
     if (!ok) {

@@ -48,6 +48,22 @@ PSIM_HD float f_mul(float a, float b) {
 // 32-level quadrant key of (x, y): replays the reference's comparisons against the fp32 centre
 // recurrence.  Level 1 sits in bits 63:62; in each digit the y bit is above the x bit.  NaN
 // coordinates compare false and fall into quadrant 3 at every level.
+// first `levels` digits of the key, right-aligned (levels = 8: the shard bin of shard.cuh)
+PSIM_HD uint32_t morton_prefix(float x, float y, RootQuad r, int levels) {
+  float cx = r.cx, cy = r.cy, size = r.size;
+  uint32_t key = 0;
+  for (int l = 0; l < levels; ++l) {
+    const unsigned qx = (x < cx) ? 0u : 1u;
+    const unsigned qy = (y < cy) ? 0u : 1u;
+    key = (key << 2) | ((qy << 1) | qx);
+    size = f_mul(size, 0.5f);
+    const float h = f_mul(0.5f, size);
+    cx = f_add(cx, qx ? h : -h);
+    cy = f_add(cy, qy ? h : -h);
+  }
+  return key;
+}
+
 PSIM_HD uint64_t morton_key(float x, float y, RootQuad r) {
   float cx = r.cx, cy = r.cy, size = r.size;
   uint64_t key = 0;

@@ -59,24 +59,23 @@ struct ShardMeta {  // device side, one per context
   uint32_t node_lo[kMaxRanks + 1], trav_lo[kMaxRanks + 1];
 };
 
-// ---- replicated: keys of all bodies + bin histogram -------------------------------------------------
+// ---- replicated: shard bin (first 8 key levels) of all bodies + bin histogram ----------------------
 __global__ void __launch_bounds__(256)
-    keygen_bins_kernel(const float4* __restrict__ pqr, uint32_t n, const TreeMeta* __restrict__ meta,
-                       uint64_t* __restrict__ keys, uint32_t* __restrict__ binhist) {
+    bins_kernel(const float4* __restrict__ pqr, uint32_t n, const TreeMeta* __restrict__ meta,
+                uint16_t* __restrict__ bins, uint32_t* __restrict__ binhist) {
   const RootQuad r = meta->root;
   const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t lane = threadIdx.x & 31;
   for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {
     const uint32_t i = base + threadIdx.x;
     const bool live = i < n;
-    uint64_t k = 0;
+    uint32_t bin = 0xffffffffu;
     if (live) {
       const float4 p = pqr[i];
-      k = morton_key(p.x, p.y, r);
-      keys[i] = k;
+      bin = morton_prefix(p.x, p.y, r, kShardDepth);
+      bins[i] = (uint16_t)bin;
     }
     // bodies arrive nearly sorted: one atomic per distinct bin in the warp
-    const uint32_t bin = live ? (uint32_t)(k >> 48) : 0xffffffffu;
     const uint32_t m = __match_any_sync(0xffffffffu, bin);
     if (live && lane == (uint32_t)(__ffs(m) - 1)) atomicAdd(&binhist[bin], (uint32_t)__popc(m));
   }
@@ -121,36 +120,44 @@ __global__ void __launch_bounds__(1024)
 }
 
 struct InRangeFn {  // 1 for a body whose bin this rank owns
-  const uint64_t* keys;
+  const uint16_t* bins;
   uint32_t bin_lo, bin_hi;
   __device__ __forceinline__ uint32_t operator()(uint32_t i) const {
-    const uint32_t b = (uint32_t)(keys[i] >> 48);
+    const uint32_t b = bins[i];
     return (b >= bin_lo && b < bin_hi) ? 1u : 0u;
   }
 };
 
-// ordered compaction of the owned bodies: upper key word + global body index, input of the radix passes
+// ordered compaction of the owned bodies with their full 32-level keys: upper key word + compact slot as
+// the input of the radix passes, 64-bit key and global body index by slot
 __global__ void __launch_bounds__(256)
-    select_owned_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ off, uint32_t n,
-                        uint32_t bin_lo, uint32_t bin_hi, uint32_t* __restrict__ khi, uint32_t* __restrict__ idx) {
+    select_owned_kernel(const float4* __restrict__ pqr, const uint16_t* __restrict__ bins,
+                        const uint32_t* __restrict__ off, uint32_t n, uint32_t bin_lo, uint32_t bin_hi,
+                        const TreeMeta* __restrict__ meta, uint64_t* __restrict__ keys,
+                        uint32_t* __restrict__ khi, uint32_t* __restrict__ slot, uint32_t* __restrict__ body) {
+  const RootQuad r = meta->root;
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const uint64_t k = keys[i];
-    const uint32_t b = (uint32_t)(k >> 48);
+    const uint32_t b = bins[i];
     if (b >= bin_lo && b < bin_hi) {
+      const float4 p = pqr[i];
+      const uint64_t k = morton_key(p.x, p.y, r);
       const uint32_t o = off[i];
+      keys[o] = k;
       khi[o] = (uint32_t)(k >> 32);
-      idx[o] = i;
+      slot[o] = o;
+      body[o] = i;
     }
   }
 }
 
 __global__ void __launch_bounds__(256)
     copy_sorted_idx_kernel(const uint32_t* __restrict__ idx0, const uint32_t* __restrict__ idx1,
-                           const SortPlan* __restrict__ plan, int npass, uint32_t n, uint32_t* __restrict__ out) {
-  const uint32_t* __restrict__ idx = plan->src[npass] ? idx1 : idx0;
+                           const SortPlan* __restrict__ plan, int npass, uint32_t n,
+                           const uint32_t* __restrict__ body, uint32_t* __restrict__ out) {
+  const uint32_t* __restrict__ idx = plan->src[npass] ? idx1 : idx0;  // sorted compact slots
   const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = idx[i];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = body[idx[i]];
 }
 
 // bin that holds the body at global sorted position g: binprefix[b] <= g < binprefix[b + 1]

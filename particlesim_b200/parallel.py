@@ -21,8 +21,10 @@ from .simulation import Simulation
 
 
 def shard_width(n: int, world: int) -> int:
-    """bodies per rank (the last rank may own fewer); arrays are padded to world * width"""
-    return (n + world - 1) // world if n else 0
+    """bodies per rank (the last ranks may own fewer); arrays are padded to world * width.  A multiple of
+    32, so that the 32-target groups of the traversal are the ones the single-GPU run forms and the sharded
+    result stays bit-identical (the order of a target's additions depends on its group)"""
+    return ((n + world - 1) // world + 31) // 32 * 32 if n else 0
 
 
 def shard_range(n: int, world: int, rank: int) -> tuple[int, int]:
@@ -97,9 +99,11 @@ def shard_views(sim, torch):
                 heap=mk(p[2], (int(p[6]),), "<i8"), travA=mk(p[3], (cap, 4), "<i4"), travB=mk(p[4], (cap, 4), "<i4"))
 
 
-def sharded_build(sims, mode: int, hw: float, hh: float, comm, torch):
+def sharded_build(sims, mode: int, hw: float, hh: float, comm, torch, mark=None):
     """Quadtree::build / build_with_domain across ranks (include/psim_b200.h, psim_shard_phase): `sims`
-    are the contexts of the ranks that live in this process (one under torchrun)."""
+    are the contexts of the ranks that live in this process (one under torchrun).  `mark(name)`, if given,
+    is called at every phase / exchange boundary (tools/shard_phases.py records CUDA events there)."""
+    mark = mark or (lambda name: None)
     world = sims[0].world
     lo = [np.zeros(world + 1, np.uint32) for _ in sims]
     views = [s._shard_view_cache if getattr(s, "_shard_view_cache", None) else None for s in sims]
@@ -111,19 +115,31 @@ def sharded_build(sims, mode: int, hw: float, hh: float, comm, torch):
         for i, s in enumerate(sims):
             s._call("psim_shard_phase", k, mode, hw, hh, out[i].ctypes.data if out is not None else None)
 
+    mark("start")
     phase(0, lo)
+    mark("p0 keys+bins (replicated)")
     phase(1)
+    mark("p1 select+sort")
     comm.all_gatherv([v["order"] for v in views], lo[0])
+    mark("x1 order all-gather")
     phase(2)
+    mark("p2 gather (replicated)+levels")
     comm.all_reduce([v["xbuf"] for v in views])
+    mark("x2 table")
     phase(3)
+    mark("p3 emit+sweeps")
     comm.all_reduce([v["heap"] for v in views])
+    mark("x3 heap")
     phase(4)
+    mark("p4 top+finalize+scan")
     comm.all_reduce([v["xbuf"] for v in views])
+    mark("x4 table")
     tl = [np.zeros(world + 1, np.uint32) for _ in sims]
     phase(5, tl)
+    mark("p5 compact")
     comm.all_gatherv([v["travA"] for v in views], tl[0])
     comm.all_gatherv([v["travB"] for v in views], tl[0])
+    mark("x5 traversal all-gather")
     return lo[0], tl[0]
 
 
@@ -193,7 +209,7 @@ class ShardedSimulation(Simulation):
         C("psim_reset_acc")
         self._build(_lib.BUILD_CONTAINING, 0.0, 0.0)
         mark()
-        cell = self.force_cell_size()
+        cell = self.step_cell_size(bool(getattr(p, "do_polar", 0)))  # what psim_step uses: same addition order
         if p.do_short_range and cell > 0.0:
             C("psim_cell_build", p.hw, p.hh, cell)
         mark()

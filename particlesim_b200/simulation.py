@@ -291,6 +291,19 @@ class Simulation:
                 rep = max(rep, np.float32(r["repulsion_cutoff"]))
         return float(max(np.float32(3.0) * lj, rep, lj))
 
+    def step_cell_size(self, do_polar: bool = False) -> float:
+        """the cell size psim_step bins at: the largest cutoff its short-range passes use (the pair sets of
+        the LJ / repulsion passes do not depend on the cell size; only a polar pass needs 3 x the LJ cutoff)"""
+        t = self.species_table
+        lj = np.float32(0.0)
+        rep = np.float32(0.0)
+        for r in t:
+            if r["lj_enabled"]:
+                lj = max(lj, np.float32(r["lj_cutoff"]) * np.float32(r["lj_sigma"]))
+            if r["repulsion_enabled"]:
+                rep = max(rep, np.float32(r["repulsion_cutoff"]))
+        return float(max(np.float32(3.0) * lj, rep, lj)) if do_polar else float(max(rep, lj))
+
     def stats(self) -> dict:
         st = _lib.Stats()
         self._call("psim_stats_get", C.byref(st))

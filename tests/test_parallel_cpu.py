@@ -61,3 +61,66 @@ def test_all_gather_slices_gloo_world2(n):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _worker_v(rank, world, port, q):
+    """the exchanges of the sharded build (DistComm): uneven all-gather and the sum all-reduce whose slots
+    have exactly one non-zero writer"""
+    from particlesim_b200.parallel import DistComm
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        comm = DistComm(dist, rank)
+        ok = True
+        for offsets in ([0, 3, 10], [0, 0, 10], [0, 10, 10], [0, 7, 7]):
+            full = torch.full((10, 4), -1, dtype=torch.int32)
+            a, b = offsets[rank], offsets[rank + 1]
+            full[a:b] = 100 * (rank + 1) + torch.arange(b - a, dtype=torch.int32)[:, None]
+            comm.all_gatherv([full], offsets)
+            expect = torch.full((10, 4), -1, dtype=torch.int32)
+            for r in range(world):
+                aa, bb = offsets[r], offsets[r + 1]
+                expect[aa:bb] = 100 * (r + 1) + torch.arange(bb - aa, dtype=torch.int32)[:, None]
+            ok &= bool(torch.equal(full, expect))
+        words = torch.zeros(64, dtype=torch.int64)
+        words[rank::world] = torch.arange(64, dtype=torch.int64)[rank::world] * 0x0123456789 + 1
+        comm.all_reduce([words])
+        ok &= bool(torch.equal(words, torch.arange(64, dtype=torch.int64) * 0x0123456789 + 1))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_build_exchanges_gloo_world2():
+    world = 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_v, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_loopback_comm_matches_the_collectives():
+    from particlesim_b200.parallel import LoopbackComm
+    comm = LoopbackComm()
+    offsets = [0, 2, 2, 9]
+    ts = []
+    for r in range(3):
+        t = torch.full((9,), -1, dtype=torch.int32)
+        t[offsets[r]:offsets[r + 1]] = r
+        ts.append(t)
+    comm.all_gatherv(ts, offsets)
+    for t in ts:
+        assert t.tolist() == [0, 0, 2, 2, 2, 2, 2, 2, 2]
+    ws = [torch.tensor([1, 0, 0], dtype=torch.int64), torch.tensor([0, 5, 0], dtype=torch.int64)]
+    comm.all_reduce(ws)
+    assert ws[0].tolist() == ws[1].tolist() == [1, 5, 0]

@@ -18,7 +18,8 @@ torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 200_001
 bd = electrolyte(n)
-bd["species"][: n // 10] = 1  # some LJ bodies
+if os.environ.get("NO_LJ") != "1":
+    bd["species"][: n // 10] = 1  # some LJ bodies
 
 
 def mk(cls, **kw):
@@ -40,7 +41,7 @@ def state(sim):
     return pos, vel, orig, eb, er, ev
 
 
-sh = mk(ShardedSimulation, rank=rank, world=world)
+sh = mk(ShardedSimulation, rank=rank, world=world, local_build=not (len(sys.argv) > 2 and sys.argv[2] == "repl"))
 for _ in range(3):
     sh.step_device()
 torch.cuda.synchronize()
@@ -55,7 +56,12 @@ if rank == 0:
     for nm, x, y in zip(names, a, b):
         same = np.array_equal(x, y)
         ok &= same
-        print(f"{nm}: identical={same}")
+        extra = ""
+        if not same:
+            d = np.abs(x.astype(np.float64) - y.astype(np.float64))
+            rows = np.unique(np.argwhere(d > 0)[:, 0])
+            extra = f"  differing rows {len(rows)} of {len(x)} (first {rows[:4].tolist()}, last {rows[-1]}), max |diff| {d.max():.3e}"
+        print(f"{nm}: identical={same}{extra}")
     print("SHARDED == SINGLE:", ok, flush=True)
 dist.barrier()
 dist.destroy_process_group()
