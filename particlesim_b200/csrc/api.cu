@@ -734,7 +734,8 @@ int32_t shard_phase(psim_ctx* ctx, int phase, int mode, float hw, float hh, uint
     }
     case 4: {
       BodyArrays& b = ctx->b[ctx->cur];
-      heap_sweep_kernel<<<1, 1024, 0, st>>>(S.heap);
+      for (int d = kShardDepth - 1; d >= 0; --d)
+        heap_sweep_kernel<<<grid_for(ctx, 1u << (2 * d), 256, 1), 256, 0, st>>>(S.heap, d);
       heap_writeback_kernel<<<grid_for(ctx, kTopSlots, 256, 2), 256, 0, st>>>(S.meta, S.heap, ctx->t);
       finalize_nodes_shard_kernel<<<grid_for(ctx, (uint64_t)nl * 2 + 1, 256, 16), 256, 0, st>>>(
           ctx->meta, S.meta, b.pqr, b.accm, S.lkeys, S.binprefix, ctx->t);
@@ -743,7 +744,7 @@ int32_t shard_phase(psim_ctx* ctx, int phase, int mode, float hw, float hh, uint
       CK(cudaMemsetAsync(S.xbuf, 0, (kBins + kMaxRanks) * sizeof(unsigned long long), st));
       table_trav_kernel<<<grid_for(ctx, kBins, 256, 2), 256, 0, st>>>(S.binhist, S.plan, S.meta, S.nb_bin, ctx->trav_rank,
                                                                      &S.meta->T_local, S.xbuf);
-      ctx->launches += 7;
+      ctx->launches += 6 + kShardDepth;
       break;
     }
     case 5: {

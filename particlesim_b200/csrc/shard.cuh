@@ -378,11 +378,11 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// after the all-reduce, one CTA: the cells above the bins, deepest level first
-__global__ void __launch_bounds__(1024) heap_sweep_kernel(TopRec* __restrict__ heap) {
-  for (int d = kShardDepth - 1; d >= 0; --d) {
+// after the all-reduce: the cells above the bins, one launch per level, deepest level first
+__global__ void __launch_bounds__(256) heap_sweep_kernel(TopRec* __restrict__ heap, int d) {
+  {
     const uint32_t cells = 1u << (2 * d);
-    for (uint32_t p = threadIdx.x; p < cells; p += blockDim.x) {
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < cells; p += gridDim.x * blockDim.x) {
       TopRec* me = &heap[top_base(d) + p];
       if (me->state != kTopInternal) continue;
       double aq = 0.0, aqx = 0.0, aqy = 0.0;
@@ -403,7 +403,6 @@ __global__ void __launch_bounds__(1024) heap_sweep_kernel(TopRec* __restrict__ h
       me->r.next = next | (last ? kLastSibling : 0u);
       me->state = kTopComputed;
     }
-    __syncthreads();
   }
 }
 

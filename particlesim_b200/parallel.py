@@ -56,15 +56,48 @@ def all_gatherv(full, offsets, rank: int, dist):
     return full
 
 
+def all_gatherv_padded(full, offsets, rank: int, dist, stage_cache: dict):
+    """The same exchange as ONE all-gather: every rank contributes a block of max-segment rows starting at
+    its segment (rows past its count are padding), the blocks land in a staging tensor and the valid rows
+    are copied into place.  One ncclAllGather at full NVSwitch bandwidth instead of world broadcasts."""
+    world = len(offsets) - 1
+    counts = [int(offsets[r + 1]) - int(offsets[r]) for r in range(world)]
+    seg = max(counts)
+    if seg == 0:
+        return full
+    seg = (seg + 1023) // 1024 * 1024  # few distinct staging sizes across builds
+    key = (full.dtype, tuple(full.shape[1:]), full.device)
+    need = world * seg
+    stage = stage_cache.get(key)
+    if stage is None or stage.shape[0] < need + seg:
+        stage = full.new_empty((int((need + seg) * 1.25),) + tuple(full.shape[1:]))
+        stage_cache[key] = stage
+    a = int(offsets[rank])
+    if a + seg <= full.shape[0]:
+        mine = full[a:a + seg]
+    else:  # the padded block would run past the end of the array: go through the spare block
+        mine = stage[need:need + seg]
+        mine[:counts[rank]].copy_(full[a:a + counts[rank]])
+    dist.all_gather_into_tensor(stage[:need], mine)
+    for r in range(world):
+        if r != rank and counts[r]:
+            full[int(offsets[r]):int(offsets[r + 1])].copy_(stage[r * seg:r * seg + counts[r]])
+    return full
+
+
 class DistComm:
     """exchanges of the sharded build over torch.distributed (NCCL on GPUs, gloo in the CPU tests); the
     lists hold one tensor per LOCAL rank, i.e. one"""
 
-    def __init__(self, dist, rank: int):
-        self.dist, self.rank = dist, rank
+    def __init__(self, dist, rank: int, padded: bool = True):
+        self.dist, self.rank, self.padded = dist, rank, padded
+        self._stage = {}
 
     def all_gatherv(self, tensors, offsets):
-        all_gatherv(tensors[0], offsets, self.rank, self.dist)
+        if self.padded:
+            all_gatherv_padded(tensors[0], offsets, self.rank, self.dist, self._stage)
+        else:
+            all_gatherv(tensors[0], offsets, self.rank, self.dist)
 
     def all_reduce(self, tensors):
         self.dist.all_reduce(tensors[0])

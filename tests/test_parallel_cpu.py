@@ -71,9 +71,9 @@ def _worker_v(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        comm = DistComm(dist, rank)
         ok = True
-        for offsets in ([0, 3, 10], [0, 0, 10], [0, 10, 10], [0, 7, 7]):
+        for padded, offsets in [(p, o) for p in (False, True) for o in ([0, 3, 10], [0, 0, 10], [0, 10, 10], [0, 7, 7])]:
+            comm = DistComm(dist, rank, padded=padded)
             full = torch.full((10, 4), -1, dtype=torch.int32)
             a, b = offsets[rank], offsets[rank + 1]
             full[a:b] = 100 * (rank + 1) + torch.arange(b - a, dtype=torch.int32)[:, None]
@@ -83,6 +83,7 @@ def _worker_v(rank, world, port, q):
                 aa, bb = offsets[r], offsets[r + 1]
                 expect[aa:bb] = 100 * (r + 1) + torch.arange(bb - aa, dtype=torch.int32)[:, None]
             ok &= bool(torch.equal(full, expect))
+        comm = DistComm(dist, rank)
         words = torch.zeros(64, dtype=torch.int64)
         words[rank::world] = torch.arange(64, dtype=torch.int64)[rank::world] * 0x0123456789 + 1
         comm.all_reduce([words])
