@@ -265,14 +265,15 @@ int32_t psim_device_ptrs(psim_ctx *ctx, uint64_t *out8);
 /* Sharded build (replaces the single work queue of Quadtree::build_internal,
  * src/quadtree/quadtree.rs:197-345, across ranks).  Every rank holds all bodies; rank r sorts the keys of
  * a contiguous range of 65 536 top-level cells and emits the tree nodes that start in it.  The pieces
- * concatenate into exactly the single-GPU tree.  psim_shard_phase runs phase 0..5 in order; between
+ * concatenate into exactly the single-GPU tree.  psim_shard_phase runs phase 0..6 in order; between
  * phases the caller performs the exchange on the device buffers psim_shard_ptrs names:
  *   after 0: nothing (out = first sorted body of each rank, world + 1 entries; synchronises)
  *   after 1: all-gather of the sorted-order segments  [out[r], out[r+1]) of ptrs[0] (uint32 per body)
  *   after 2, after 4: all-reduce (sum) of ptrs[1], ptrs[5] uint64 words
  *   after 3: all-reduce (sum) of ptrs[2], ptrs[6] uint64 words
  *   after 5: all-gather of the traversal segments [out[r], out[r+1]) of ptrs[3] and ptrs[4] (16 bytes
- *            per node each; out = first traversal node of each rank; synchronises)
+ *            per node each; out = first traversal node of each rank; synchronises), then phase 6
+ *            (children links over the gathered array; the tree is usable after it)
  * ptrs[7] = node capacity.  The tree export (psim_download_nodes) and parity_mode 2 need the whole node
  * array and are single-GPU only. */
 int32_t psim_shard_init(psim_ctx *ctx, uint32_t rank, uint32_t world);

@@ -618,6 +618,8 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
       ctx->meta, ctx->t.nodeA, ctx->t.nodeB, ctx->trav_rank, ctx->trav_count, ctx->node_cap, ctx->travA,
       ctx->travB);
   LAUNCHED(ctx);
+  link_children_kernel<<<grid_for(ctx, (uint64_t)n, 256, 16), 256, 0, st>>>(ctx->trav_count, ctx->travA, ctx->travB);
+  LAUNCHED(ctx);
   ctx->tree_valid = true;
   ctx->perm_valid = true;
   return PSIM_OK;
@@ -632,6 +634,7 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
 //   4  top sweep, centres, charged scan, table 2                   -> all-reduce xbuf
 //   5  traversal offsets, compaction into the rank's segment       -> sync, out = trav_lo[world + 1];
 //                                                                    all-gather travA / travB segments
+//   6  children links over the gathered traversal array
 int32_t shard_phase(psim_ctx* ctx, int phase, int mode, float hw, float hh, uint32_t* out) {
   auto& S = ctx->sh;
   if (!S.on) return fail(ctx, PSIM_E_STATE, "psim_shard_phase: call psim_shard_init first");
@@ -759,14 +762,20 @@ int32_t shard_phase(psim_ctx* ctx, int phase, int mode, float hw, float hh, uint
       if (S.meta_h.M_local > ctx->node_cap || S.meta_h.T_total > ctx->node_cap)
         return fail(ctx, PSIM_E_NODE_OVERFLOW, "sharded build: node arena overflow (raise node_factor)");
       if (out) memcpy(out, S.meta_h.trav_lo, (S.world + 1) * sizeof(uint32_t));
-      ctx->tree_valid = true;   // once the caller has all-gathered the traversal segments
+      break;
+    }
+    case 6: {
+      // the traversal segments of all ranks are in place: children links over the whole array
+      link_children_kernel<<<grid_for(ctx, (uint64_t)n, 256, 16), 256, 0, st>>>(ctx->trav_count, ctx->travA, ctx->travB);
+      LAUNCHED(ctx);
+      ctx->tree_valid = true;
       ctx->perm_valid = true;
       break;
     }
     default:
-      return fail(ctx, PSIM_E_ARG, "psim_shard_phase: phase 0..5");
+      return fail(ctx, PSIM_E_ARG, "psim_shard_phase: phase 0..6");
   }
-  S.phase = phase == 5 ? 0 : phase + 1;
+  S.phase = phase == 6 ? 0 : phase + 1;
   const cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) return fail(ctx, PSIM_E_CUDA, "sharded build launch", le);
   return PSIM_OK;
@@ -845,11 +854,11 @@ int32_t field_async(psim_ctx* ctx, float k_e, float bg_x, float bg_y, int write_
     if (ctx->cfg.parity_mode)
       bh_group_bodies_kernel<true><<<blocks, 128, 0, ctx->stream>>>(
           ctx->travA, ctx->travB, ctx->trav_count, b.pqr, b.accm, first, count, P, b.efield, b.accm, write_acc,
-          ctx->step_counter);
+          ctx->step_counter, ctx->meta);
     else
       bh_group_bodies_kernel<false><<<blocks, 128, 0, ctx->stream>>>(
           ctx->travA, ctx->travB, ctx->trav_count, b.pqr, b.accm, first, count, P, b.efield, b.accm, write_acc,
-          ctx->step_counter);
+          ctx->step_counter, ctx->meta);
   }
   LAUNCHED(ctx);
   return PSIM_OK;
@@ -869,10 +878,10 @@ int32_t points_async(psim_ctx* ctx, const float2* pts, const float* q, const flo
         radius ? radius + first : nullptr, m, P, out + first, ctx->step_counter);
   else if (ctx->cfg.parity_mode)
     bh_group_points_kernel<true><<<blocks, 128, 0, ctx->stream>>>(
-        ctx->travA, ctx->travB, ctx->trav_count, b.pqr, pts, q, radius, first, m, P, out, ctx->step_counter);
+        ctx->travA, ctx->travB, ctx->trav_count, b.pqr, pts, q, radius, first, m, P, out, ctx->step_counter, ctx->meta);
   else
     bh_group_points_kernel<false><<<blocks, 128, 0, ctx->stream>>>(
-        ctx->travA, ctx->travB, ctx->trav_count, b.pqr, pts, q, radius, first, m, P, out, ctx->step_counter);
+        ctx->travA, ctx->travB, ctx->trav_count, b.pqr, pts, q, radius, first, m, P, out, ctx->step_counter, ctx->meta);
   LAUNCHED(ctx);
   return PSIM_OK;
 }

@@ -279,7 +279,7 @@ __device__ __forceinline__ float2 bh_group_walk(const float4* __restrict__ nodeA
                                                 const float4* __restrict__ pqr, uint32_t M, float px,
                                                 float py, float q, float radius, bool live,
                                                 const FieldParams P, WarpShared& ws,
-                                                uint32_t& nodes_out) {
+                                                uint32_t& nodes_out, float root_size) {
   using A = Arith<PARITY>;
   const uint32_t FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -335,11 +335,16 @@ __device__ __forceinline__ float2 bh_group_walk(const float4* __restrict__ nodeA
     float4 na = make_float4(0.f, 0.f, 0.f, 0.f);
     uint4 nb = make_uint4(0, 0, 0, 0);
     bool leaf = false;
+    uint32_t c3 = 0;
     int cls = 2;  // 0 ambiguous, 1 every target accepts, 2 every target rejects
     if (has) {
       na = __ldg(&nodeA[node]);
       nb = __ldg(&nodeB[node]);
       leaf = (nb.w & kNodeLeaf) != 0;
+      // traversal records of internal nodes carry their children (link_children_kernel): B.y, B.z and the
+      // bits of A.w are children 1..3; the cell size is the root's halved `depth` times, exactly
+      c3 = __float_as_uint(na.w);
+      na.w = ldexpf(root_size, -(int)(nb.w & kNodeDepthMask));
       cls = 0;
       if (box_ok) {
         const float s_t = na.w * P.inv_theta;
@@ -430,14 +435,14 @@ __device__ __forceinline__ float2 bh_group_walk(const float4* __restrict__ nodeA
     uint32_t kid[4] = {0u, 0u, 0u, 0u};
     int nk = 0;
     if (has && rem != 0 && !leaf) {
-      uint32_t c = node + 1;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        kid[j] = c;
-        nk = j + 1;
-        const uint32_t cn = __ldg(&nodeB[c].x);
-        if (cn == nb.x) break;  // c was the last child: its skip pointer is the parent's
-        c = cn;
+      // a missing child is marked by the parent's own skip pointer
+      kid[0] = node + 1, nk = 1;
+      if (nb.y != nb.x) {
+        kid[1] = nb.y, nk = 2;
+        if (nb.z != nb.x) {
+          kid[2] = nb.z, nk = 3;
+          if (c3 != nb.x) kid[3] = c3, nk = 4;
+        }
       }
     }
     int incl = nk;  // inclusive prefix of the child counts over the lanes
@@ -493,9 +498,10 @@ __global__ void __launch_bounds__(128)
                            const float4* __restrict__ acc_mass, uint32_t first, uint32_t n,
                            FieldParams P, float2* __restrict__ e_field,
                            float4* __restrict__ acc_mass_out, int write_acc,
-                           unsigned long long* __restrict__ step_counter) {
+                           unsigned long long* __restrict__ step_counter, const TreeMeta* __restrict__ meta) {
   __shared__ WarpShared ws[4];
   const uint32_t M = *num_nodes;
+  const float root_size = meta->root.size;
   const uint32_t g = blockIdx.x * 4 + (threadIdx.x >> 5);
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t i = first + g * 32 + lane;
@@ -504,7 +510,7 @@ __global__ void __launch_bounds__(128)
   if (live) me = pqr[i];
   uint32_t visited;
   float2 e = bh_group_walk<PARITY>(nodeA, nodeB, pqr, M, me.x, me.y, 1.0f, me.w, live, P,
-                                   ws[threadIdx.x >> 5], visited);
+                                   ws[threadIdx.x >> 5], visited, root_size);
   if (live) {
     e.x = __fadd_rn(e.x, P.bg_x);
     e.y = __fadd_rn(e.y, P.bg_y);
@@ -525,9 +531,11 @@ __global__ void __launch_bounds__(128)
                            const uint32_t* __restrict__ num_nodes, const float4* __restrict__ pqr,
                            const float2* __restrict__ pts, const float* __restrict__ q,
                            const float* __restrict__ radius, uint32_t first, uint32_t m, FieldParams P,
-                           float2* __restrict__ out, unsigned long long* __restrict__ step_counter) {
+                           float2* __restrict__ out, unsigned long long* __restrict__ step_counter,
+                           const TreeMeta* __restrict__ meta) {
   __shared__ WarpShared ws[4];
   const uint32_t M = *num_nodes;
+  const float root_size = meta->root.size;
   const uint32_t g = blockIdx.x * 4 + (threadIdx.x >> 5);
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t i = first + g * 32 + lane;
@@ -541,7 +549,7 @@ __global__ void __launch_bounds__(128)
   }
   uint32_t visited;
   const float2 e = bh_group_walk<PARITY>(nodeA, nodeB, pqr, M, p.x, p.y, qq, rr, live, P,
-                                         ws[threadIdx.x >> 5], visited);
+                                         ws[threadIdx.x >> 5], visited, root_size);
   if (live) out[i] = e;
   if (step_counter && lane == 0 && visited) atomicAdd(step_counter, (unsigned long long)visited);
 }

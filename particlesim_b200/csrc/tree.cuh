@@ -312,6 +312,28 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Children of every internal traversal node, so that the walk finds them without chasing skip pointers
+// through dependent loads: child 0 is r + 1, children 1..3 go into B.y, B.z and the bits of A.w (body
+// range and cell size of an internal node are not read by the walk; the size is recomputed from the depth).
+// A missing child is marked by the node's own skip pointer.  Only .y / .z / A.w are written, .x is only read.
+__global__ void __launch_bounds__(256)
+    link_children_kernel(const uint32_t* __restrict__ total, float4* __restrict__ travA, uint4* __restrict__ travB) {
+  const uint32_t T = *total;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < T; r += stride) {
+    const uint32_t w = travB[r].w;
+    if (w & kNodeLeaf) continue;
+    const uint32_t skip = travB[r].x;
+    uint32_t c1 = skip, c2 = skip, c3 = skip;
+    if (r + 1 < T) c1 = travB[r + 1].x;
+    if (c1 != skip && c1 < T) c2 = travB[c1].x;
+    if (c2 != skip && c2 < T) c3 = travB[c2].x;
+    travB[r].y = c1;
+    travB[r].z = c2;
+    travA[r].w = __uint_as_float(c3);
+  }
+}
+
 struct InternalFlagFn {
   const uint4* nodeB;
   __device__ __forceinline__ uint32_t operator()(uint32_t i) const {

@@ -173,6 +173,8 @@ def sharded_build(sims, mode: int, hw: float, hh: float, comm, torch, mark=None)
     comm.all_gatherv([v["travA"] for v in views], tl[0])
     comm.all_gatherv([v["travB"] for v in views], tl[0])
     mark("x5 traversal all-gather")
+    phase(6)
+    mark("p6 children links")
     return lo[0], tl[0]
 
 
