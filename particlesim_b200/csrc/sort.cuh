@@ -104,7 +104,7 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
 // One digit pass.  keys/vals are the two ping-pong buffers; the plan says which one is the source.
 // status: [num_tiles][256] words, zeroed before the sort; ticket: one counter per pass, zeroed.
 template <typename K>
-__global__ void __launch_bounds__(kSortThreads)
+__global__ void __launch_bounds__(kSortThreads, 4)
     onesweep_pass_kernel(K* __restrict__ keys0, K* __restrict__ keys1, uint32_t* __restrict__ vals0,
                          uint32_t* __restrict__ vals1, uint32_t n, int pass, int shift,
                          const uint32_t* __restrict__ digit_base /*[256] exclusive, this pass*/,
@@ -135,12 +135,14 @@ __global__ void __launch_bounds__(kSortThreads)
 
   // ---- load (warp-striped: warp w owns a contiguous run, item j of lane l is element j*32+l of it)
   K key[kSortItems];
+  uint32_t val[kSortItems];  // payloads travel with the keys: one round of global loads per tile
   uint32_t rank[kSortItems];
   const uint32_t warp_off = warp * (32 * kSortItems);
 #pragma unroll
   for (int j = 0; j < kSortItems; ++j) {
     const uint32_t loc = warp_off + j * 32 + lane;
     key[j] = (loc < count) ? kin[tile_base + loc] : (K)0;
+    val[j] = (loc < count) ? vin[tile_base + loc] : 0u;
   }
 
   // ---- rank within the warp, in element order
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(kSortThreads)
       const uint32_t p = s_digit_start[d] + s_whist[warp][d] + rank[j];
       rank[j] = p;
       s_keys[p] = key[j];
-      s_vals[p] = vin[tile_base + loc];
+      s_vals[p] = val[j];
     }
   }
   __syncthreads();

@@ -22,9 +22,9 @@ from .simulation import Simulation
 
 def shard_width(n: int, world: int) -> int:
     """bodies per rank (the last ranks may own fewer); arrays are padded to world * width.  A multiple of
-    32, so that the 32-target groups of the traversal are the ones the single-GPU run forms and the sharded
+    64 (two groups), so that the 32-target groups of the traversal are the ones the single-GPU run forms and the sharded
     result stays bit-identical (the order of a target's additions depends on its group)"""
-    return ((n + world - 1) // world + 31) // 32 * 32 if n else 0
+    return ((n + world - 1) // world + 63) // 64 * 64 if n else 0
 
 
 def shard_range(n: int, world: int, rank: int) -> tuple[int, int]:
