@@ -266,7 +266,7 @@ def run_ours(args):
                 "gpu_launches": int(launches), "clocks": clocks, "phase_ms": phase}
 
     if world == 1:
-        # ---- roofline of the dominant kernel (bh_field_bodies_kernel = phase quadtree_field) --------
+        # ---- roofline of the dominant kernel (bh_group_bodies_kernel = phase quadtree_field) --------
         sim._call("psim_build", 0, 0.0, 0.0)
         cnt = np.zeros(4, np.uint64)
         sim._call("psim_field_counters", cnt.ctypes.data)
@@ -280,7 +280,7 @@ def run_ours(args):
         achieved = flops / t_field / 1e12
         st = sim.stats()
         line["roofline"] = {
-            "kernel": "bh_field_bodies_kernel", "bound": "fp32",
+            "kernel": "bh_group_bodies_kernel", "bound": "fp32",
             "achieved": achieved, "peak": float(tf.value), "unit": "TFLOP/s", "frac": achieved / float(tf.value),
             "traffic": ncu_traffic(n),
             "peak_source": "measured live: FP32 FMA microbenchmark on this GPU (MEASURED_PEAKS.json holds HBM and bf16 "
@@ -296,7 +296,9 @@ def run_ours(args):
         peaks = measured_peaks()
         hbm = float(peaks.get("hbm_gbs", 6650.0))
         M = st["compact_nodes"]
-        build_bytes = n * (16 + 8 + 8 * 24 + 2 * 61 + 2 + 4 + 16) + M * (32 + 4 + 4 + 64 + 48)
+        # keys 16 r + 16 w; radix passes on the upper key word 4 + 4 x 16; sorted keys + run fix-up 28; body
+        # gather 2 x 61; levels 2 + node scan 4 + emit 16 r; per node: records 32 + 4 + 4, sums 64, compaction 48
+        build_bytes = n * (16 + 16 + 4 + 4 * 16 + 28 + 2 * 61 + 2 + 4 + 16) + M * (32 + 4 + 4 + 64 + 48)
         line["roofline_build"] = {"bound": "hbm", "achieved": build_bytes / (phase["quadtree_build"] * 1e-3) / 1e9,
                                   "peak": hbm, "unit": "GB/s",
                                   "frac": build_bytes / (phase["quadtree_build"] * 1e-3) / 1e9 / hbm,

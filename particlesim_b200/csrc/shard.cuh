@@ -290,6 +290,7 @@ struct ShardSink {
   uint32_t* s_cursor;
   TopRec* heap;
   __device__ __forceinline__ uint32_t level_slot(int d) { return atomicAdd(&s_cursor[d], 1u); }
+  __device__ __forceinline__ void local_node(int, uint32_t) {}
   __device__ __forceinline__ void zero_leaf() { atomicAdd(&meta->num_zero_leaves, 1u); }
   __device__ __forceinline__ void cap_leaf() { atomicAdd(&meta->num_cap_leaves, 1u); }
   __device__ __forceinline__ void top_leaf(int d, uint64_t key, uint32_t node, const NodeRec& r) {

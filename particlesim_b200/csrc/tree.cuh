@@ -100,17 +100,19 @@ __global__ void __launch_bounds__(256)
 }
 
 // ------------------------------------------------------------------------------------------------
-// per body: λ_i and ℓ_i (packed), plus per-depth internal-node counts and the maximum depth
+// per body: λ_i and ℓ_i (packed), the maximum depth, and per-depth counts of the internal cells the level
+// sweeps will visit: those that straddle a boundary of the emit kernel's slabs of `per_block` bodies (a
+// cell that lies inside one slab is summed by that slab's CTA, see tree_emit_kernel)
 __global__ void __launch_bounds__(256)
     tree_count_kernel(const uint64_t* __restrict__ keys0, const uint64_t* __restrict__ keys1,
                       const SortPlan* __restrict__ plan, int npass, const float4* __restrict__ pqr,
-                      uint32_t n, uint32_t c_eff, TreeMeta* __restrict__ meta,
+                      uint32_t n, uint32_t c_eff, uint32_t per_block, TreeMeta* __restrict__ meta,
                       uint16_t* __restrict__ le) {
   const uint64_t* __restrict__ keys = plan->src[npass] ? keys1 : keys0;
   __shared__ uint32_t s_cnt[kLevels];
-  __shared__ uint32_t s_maxd;
+  __shared__ uint32_t s_maxd, s_internal;
   if (threadIdx.x < kLevels) s_cnt[threadIdx.x] = 0;
-  if (threadIdx.x == 0) s_maxd = 0;
+  if (threadIdx.x == 0) s_maxd = 0, s_internal = 0;
   __syncthreads();
   const int dcap = (int)meta->dcap;
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -119,13 +121,20 @@ __global__ void __launch_bounds__(256)
     le[i] = lev;
     const int lam = le_lambda(lev), ell = le_ell(lev);
     if (lam < ell) {
-      for (int d = lam + 1; d < ell; ++d) atomicAdd(&s_cnt[d], 1u);
+      if (ell - lam > 1) {
+        atomicAdd(&s_internal, (uint32_t)(ell - lam - 1));
+        const uint64_t slab_end = ((uint64_t)(i / per_block) + 1) * per_block;
+        const int straddle = slab_end < n ? lcp_levels(keys[i], keys[slab_end]) : -1;
+        const int top = (ell - 1 < straddle) ? ell - 1 : straddle;
+        for (int d = lam + 1; d <= top; ++d) atomicAdd(&s_cnt[d], 1u);
+      }
       atomicMax(&s_maxd, (uint32_t)ell);
     }
   }
   __syncthreads();
   if (threadIdx.x < kLevels && s_cnt[threadIdx.x]) atomicAdd(&meta->level_count[threadIdx.x], s_cnt[threadIdx.x]);
   if (threadIdx.x == 0 && s_maxd) atomicMax(&meta->max_depth, s_maxd);
+  if (threadIdx.x == 0 && s_internal) atomicAdd(&meta->internal_total, s_internal);
 }
 
 struct LeCountFn {
@@ -136,6 +145,7 @@ struct LeCountFn {
 __global__ void level_scan_kernel(TreeMeta* __restrict__ meta, uint32_t node_cap) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   level_scan(meta, node_cap);
+  meta->num_internal = meta->internal_total;  // the buckets only hold the cells the level sweeps visit
 }
 
 // level-bucket slots.  A CTA first counts, from the packed (λ, ℓ) bytes alone, how many internal nodes
@@ -147,14 +157,23 @@ struct DeviceSink {
   __device__ __forceinline__ void top_internal(int, uint64_t, uint32_t) {}
   TreeMeta* meta;
   uint32_t* s_cursor;  // [kLevels] next free slot per depth (absolute index into level_nodes)
+  uint32_t* s_local;   // [kLevels] next free slot per depth of the CTA's own list
+  uint32_t* local_nodes;
   __device__ __forceinline__ uint32_t level_slot(int d) { return atomicAdd(&s_cursor[d], 1u); }
+  __device__ __forceinline__ void local_node(int d, uint32_t node) { local_nodes[atomicAdd(&s_local[d], 1u)] = node; }
   __device__ __forceinline__ void zero_leaf() { atomicAdd(&meta->num_zero_leaves, 1u); }
   __device__ __forceinline__ void cap_leaf() { atomicAdd(&meta->num_cap_leaves, 1u); }
 };
 
+// Emit + in-CTA sums.  Each CTA owns a contiguous slab of bodies and emits the nodes that start in it.
+// An internal cell that lies inside the slab (it does not contain the first body of the next slab) has
+// all its descendants among the CTA's own nodes, so the CTA also runs the bottom-up sweep for those cells
+// itself, level by level, right after writing the leaves - the records are still in L1 / L2 - and finishes
+// their centres (finalize_node).  Only the cells that straddle a slab boundary (about depth x 2 per CTA)
+// are left to the level sweeps.
 __global__ void __launch_bounds__(128)
     tree_emit_kernel(const uint64_t* __restrict__ keys0, const uint64_t* __restrict__ keys1,
-                     const SortPlan* __restrict__ plan, int npass, uint32_t n,
+                     const SortPlan* __restrict__ plan, int npass, uint32_t n, uint32_t per_block,
                      const uint16_t* __restrict__ le, const uint32_t* __restrict__ nodebase,
                      const float4* __restrict__ pqr, const float4* __restrict__ accm,
                      uint32_t leaf_capacity, uint32_t thread_capacity, TreeMeta* __restrict__ meta,
@@ -162,43 +181,73 @@ __global__ void __launch_bounds__(128)
   const uint64_t* __restrict__ keys = plan->src[npass] ? keys1 : keys0;
   const uint32_t M = meta->num_nodes;
   if (M > t.node_cap) return;  // arena overflow, flagged by level_scan_kernel
-  __shared__ uint32_t s_cnt[kLevels];
-  __shared__ uint32_t s_cursor[kLevels];
-  if (threadIdx.x < kLevels) s_cnt[threadIdx.x] = 0;
+  __shared__ uint32_t s_cnt[kLevels], s_cursor[kLevels];
+  __shared__ uint32_t s_in[kLevels], s_in_off[kLevels + 1], s_local[kLevels];
+  if (threadIdx.x < kLevels) s_cnt[threadIdx.x] = 0, s_in[threadIdx.x] = 0;
   __syncthreads();
-  // each CTA owns a contiguous slab of bodies (keeps its nodes, and the level buckets, local)
-  const uint32_t per_block = (n + gridDim.x - 1) / gridDim.x;
   const uint32_t lo = blockIdx.x * per_block;
+  if (lo >= n) return;
   const uint32_t hi = (lo + per_block < n) ? lo + per_block : n;
+  const bool has_next = hi < n;
+  const uint64_t key_hi = has_next ? keys[hi] : 0ull;
   for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const uint16_t lev = le[i];
     const int lam = le_lambda(lev), ell = le_ell(lev);
-    for (int d = lam + 1; d < ell; ++d) atomicAdd(&s_cnt[d], 1u);
+    if (ell - lam > 1) {
+      const int straddle = has_next ? lcp_levels(keys[i], key_hi) : -1;
+      for (int d = lam + 1; d < ell; ++d) atomicAdd(d <= straddle ? &s_cnt[d] : &s_in[d], 1u);
+    }
   }
   __syncthreads();
+  const uint32_t local_base = nodebase[lo];  // the CTA's list lives where its own nodes' indices start
   if (threadIdx.x < kLevels) {
     const uint32_t c = s_cnt[threadIdx.x];
     s_cursor[threadIdx.x] =
         meta->level_start[threadIdx.x] + (c ? atomicAdd(&meta->level_cursor[threadIdx.x], c) : 0u);
   }
+  if (threadIdx.x == 0) {
+    uint32_t run = local_base;
+    for (int l = 0; l < kLevels; ++l) s_in_off[l] = run, s_local[l] = run, run += s_in[l];
+    s_in_off[kLevels] = run;
+  }
   __syncthreads();
   const float root_size = meta->root.size;
   const int dcap = (int)meta->dcap;
-  DeviceSink sink{meta, s_cursor};
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
+  DeviceSink sink{meta, s_cursor, s_local, t.local_nodes};
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const int straddle = has_next ? lcp_levels(keys[i], key_hi) : -1;
     emit_nodes_for_body(keys, n, i, le[i], nodebase, M, pqr, accm, leaf_capacity, thread_capacity,
-                        root_size, dcap, t, sink);
+                        root_size, dcap, t, sink, 0u, 0, straddle, true);
+  }
+  // the slab's own cells, deepest level first
+  for (int level = kLevels - 1; level >= 0; --level) {
+    const uint32_t begin = s_in_off[level], end = s_in_off[level + 1];
+    if (begin == end) continue;  // uniform over the CTA
+    __threadfence_block();
+    __syncthreads();
+    for (uint32_t k = begin + threadIdx.x; k < end; k += blockDim.x) {
+      const uint32_t node = t.local_nodes[k];
+      aggregate_node_ranged(node, level, t);
+      finalize_node(node, root_size, pqr, accm, t, SubtreeEndCount{});
+    }
+  }
 }
 
-// one level of the build's bottom-up sweep (deepest level first)
+// one level of the build's bottom-up sweep (deepest level first) over the cells that straddle slab
+// boundaries; their centres are finished in the same visit
 __global__ void __launch_bounds__(128)
-    aggregate_level_kernel(int level, const TreeMeta* __restrict__ meta, TreeArrays t) {
+    aggregate_level_kernel(int level, const TreeMeta* __restrict__ meta, const float4* __restrict__ pqr,
+                           const float4* __restrict__ accm, TreeArrays t) {
   const uint32_t M = meta->num_nodes;
   if (M > t.node_cap) return;
   const uint32_t begin = meta->level_start[level], end = meta->level_start[level + 1];
+  const float root_size = meta->root.size;
   const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t k = begin + blockIdx.x * blockDim.x + threadIdx.x; k < end; k += stride)
-    aggregate_node_lean(t.level_nodes[k], level, M, t);
+  for (uint32_t k = begin + blockIdx.x * blockDim.x + threadIdx.x; k < end; k += stride) {
+    const uint32_t node = t.level_nodes[k];
+    aggregate_node_ranged(node, level, t);
+    finalize_node(node, root_size, pqr, accm, t, SubtreeEndCount{});
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -211,6 +260,44 @@ __global__ void __launch_bounds__(256)
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t node = blockIdx.x * blockDim.x + threadIdx.x; node < M; node += stride)
     finalize_node(node, root_size, pqr, accm, t, SubtreeEndLocal{M, n_bodies, t.nodeB});
+}
+
+// psim_download_nodes only: the export sweep visits EVERY internal node level by level, so the buckets are
+// rebuilt to hold them all (the build only buckets the cells its level sweeps visit)
+__global__ void __launch_bounds__(256)
+    export_count_levels_kernel(TreeMeta* __restrict__ meta, const uint4* __restrict__ nodeB) {
+  const uint32_t M = meta->num_nodes;
+  __shared__ uint32_t s_cnt[kLevels];
+  if (threadIdx.x < kLevels) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t node = blockIdx.x * blockDim.x + threadIdx.x; node < M; node += stride) {
+    const uint32_t w = nodeB[node].w;
+    if (!(w & kNodeLeaf)) atomicAdd(&s_cnt[w & kNodeDepthMask], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < kLevels && s_cnt[threadIdx.x]) atomicAdd(&meta->level_count[threadIdx.x], s_cnt[threadIdx.x]);
+}
+__global__ void export_reset_levels_kernel(TreeMeta* __restrict__ meta, int stage, uint32_t node_cap) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (stage == 0) {
+    for (int l = 0; l < kLevels; ++l) meta->level_count[l] = 0, meta->level_cursor[l] = 0;
+  } else {
+    const uint32_t keep = meta->num_internal;
+    level_scan(meta, node_cap);
+    meta->num_internal = keep;
+  }
+}
+__global__ void __launch_bounds__(256)
+    export_fill_levels_kernel(TreeMeta* __restrict__ meta, TreeArrays t) {
+  const uint32_t M = meta->num_nodes;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t node = blockIdx.x * blockDim.x + threadIdx.x; node < M; node += stride) {
+    const uint32_t w = t.nodeB[node].w;
+    if (w & kNodeLeaf) continue;
+    const uint32_t d = w & kNodeDepthMask;
+    t.level_nodes[meta->level_start[d] + atomicAdd(&meta->level_cursor[d], 1u)] = node;
+  }
 }
 
 // one level of the export sweep (psim_download_nodes only)
@@ -247,11 +334,11 @@ __global__ void __launch_bounds__(128)
                           const float4* __restrict__ accm, TreeArrays t) {
   const uint32_t M = meta->num_nodes;
   if (M > t.node_cap) return;
-  const uint32_t count = meta->num_internal, n_bodies = meta->n;
+  const uint32_t n_bodies = meta->n;
   const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) {
-    const uint32_t node = t.level_nodes[k];
+  for (uint32_t node = blockIdx.x * blockDim.x + threadIdx.x; node < M; node += stride) {
     const uint4 nb = t.nodeB[node];
+    if (nb.w & kNodeLeaf) continue;
     const uint32_t b0 = nb.y, b1 = nb.x < M ? t.nodeB[nb.x].y : n_bodies;
     float total_mass = 0.0f, total_abs = 0.0f;
     for (uint32_t b = b0; b < b1; ++b) total_mass = f_add(total_mass, accm[b].w);

@@ -27,6 +27,7 @@ struct TreeMeta {
   uint32_t level_count[kLevels];
   uint32_t level_start[kLevels + 1];
   uint32_t level_cursor[kLevels];
+  uint32_t internal_total;  // all internal nodes (level_count only covers the ones the level sweeps visit)
 };
 
 struct NodeSums {  // per internal node: running sums over its body range
@@ -57,7 +58,8 @@ struct TreeArrays {
   float* node_mass;   // export sweep only
   uint32_t* parent;   // export sweep only: compact index of the parent (root: 0xffffffff)
   NodeSums* sums;     // export sweep only
-  uint32_t* level_nodes;  // internal nodes bucketed by depth
+  uint32_t* level_nodes;  // internal nodes bucketed by depth (those the level sweeps visit)
+  uint32_t* local_nodes;  // internal nodes an emit CTA sums itself, at [first node of its slab ...)
   uint32_t node_cap;
 };
 
@@ -113,6 +115,7 @@ PSIM_HD void meta_reset(TreeMeta* meta, RootQuad r, uint32_t n) {
   meta->err = 0;
   meta->num_zero_leaves = 0;
   meta->num_cap_leaves = 0;
+  meta->internal_total = 0;
   for (int l = 0; l < kLevels; ++l) meta->level_count[l] = 0, meta->level_cursor[l] = 0;
 }
 
@@ -154,7 +157,8 @@ PSIM_HD void emit_nodes_for_body(const uint64_t* keys, uint32_t n, uint32_t i, u
                                  const uint32_t* nodebase, uint32_t M, const float4* pqr,
                                  const float4* accm, uint32_t leaf_capacity, uint32_t thread_capacity,
                                  float root_size, int dcap, const TreeArrays& t, Sink& sink,
-                                 uint32_t body_base = 0, int min_bucket_depth = 0) {
+                                 uint32_t body_base = 0, int min_bucket_depth = 0,
+                                 int straddle_depth = kMaxLevels + 1, bool internal_ranges = false) {
   // body_base / min_bucket_depth / Sink::kTop serve the sharded build (shard.cuh): `keys`, `pqr` and
   // `nodebase` are then a rank's slice of the sorted order plus a halo, i + body_base is the global body
   // index, cells above the shard depth are reported to the sink instead of the level buckets
@@ -201,11 +205,27 @@ PSIM_HD void emit_nodes_for_body(const uint64_t* keys, uint32_t n, uint32_t i, u
     t.ndepth[node] = (uint8_t)((uint32_t)d | (aq > 0.0 ? kDepthCharged : 0u));
     if (Sink::kTop && d <= min_bucket_depth) sink.top_leaf(d, keys[i], node, r);
   }
+  // internal_ranges (single-GPU build): an internal cell's body range, and with it its skip pointer, is
+  // found here by extending the galloping search outwards from the deeper cell (ranges nest), so the
+  // bottom-up sums never read another CTA's nodes: a CTA sums the cells that lie inside its own slab
+  // of bodies itself (depth > straddle_depth -> sink.local_node), only cells that straddle a slab
+  // boundary go to the level sweeps.
+  uint32_t jprev = i + 1;
+  if (internal_ranges) jprev = run_end(keys, n, i, i + 1, ell);
   for (int d = ell - 1; d > lam; --d) {
     const uint32_t node = base + (uint32_t)(d - lam - 1);
-    t.nodeB[node] = make_uint4(0u, i + body_base, 0u, (uint32_t)d);
+    uint32_t nx = 0u, cnt = 0u;
+    if (internal_ranges) {
+      jprev = run_end(keys, n, i, jprev, d);
+      nx = (jprev < n) ? nodebase[jprev] : M;
+      cnt = jprev - i;
+    }
+    t.nodeB[node] = make_uint4(nx, i + body_base, cnt, (uint32_t)d);
     t.ndepth[node] = (uint8_t)d;
-    if (d >= min_bucket_depth) t.level_nodes[sink.level_slot(d)] = node;
+    if (d >= min_bucket_depth) {
+      if (d <= straddle_depth) t.level_nodes[sink.level_slot(d)] = node;
+      else sink.local_node(d, node);
+    }
     if (Sink::kTop && d <= min_bucket_depth) sink.top_internal(d, keys[i], node);
   }
 }
@@ -233,6 +253,30 @@ PSIM_HD void aggregate_node_lean(uint32_t node, int depth, uint32_t M, const Tre
   t.rec[node] = out;
   if (aq > 0.0) t.ndepth[node] = (uint8_t)((uint32_t)depth | kDepthCharged);
 }
+
+// The same for a node whose skip pointer is already known (emit with internal_ranges): the children are
+// the nodes from node + 1 up to the skip pointer, hopping over each child's subtree; no sibling flags and
+// no read beyond the node's own subtree.
+PSIM_HD void aggregate_node_ranged(uint32_t node, int depth, const TreeArrays& t) {
+  const uint32_t end = t.nodeB[node].x;
+  double aq = 0.0, aqx = 0.0, aqy = 0.0;
+  float charge = 0.0f;
+  uint32_t c = node + 1;
+  while (c < end) {
+    const NodeRec r = t.rec[c];
+    charge = f_add(charge, r.charge);
+    aq += r.aq, aqx += r.aqx, aqy += r.aqy;
+    c = r.next & kNextMask;
+  }
+  NodeRec out;
+  out.aq = aq, out.aqx = aqx, out.aqy = aqy, out.charge = charge, out.next = end;
+  t.rec[node] = out;
+  if (aq > 0.0) t.ndepth[node] = (uint8_t)((uint32_t)depth | kDepthCharged);
+}
+
+struct SubtreeEndCount {  // internal nodes carry their body count (emit with internal_ranges)
+  PSIM_HD uint32_t operator()(uint32_t, const uint4& nb) const { return nb.y + nb.z; }
+};
 
 // Streaming pass over all nodes in pre-order after the sweep: topology record and centre of every
 // internal node from its sums.  A node whose Σ|q| is <= 1e-6 takes the reference's mass / centroid

@@ -21,6 +21,7 @@ struct HostSink {
   static constexpr bool kTop = false;
   void top_leaf(int, uint64_t, uint32_t, const NodeRec&) {}
   void top_internal(int, uint64_t, uint32_t) {}
+  void local_node(int, uint32_t) {}
   TreeMeta* meta;
   uint32_t level_slot(int d) { return meta->level_start[d] + meta->level_cursor[d]++; }
   void zero_leaf() { meta->num_zero_leaves++; }
@@ -117,16 +118,17 @@ uint32_t emu_build(void* h, uint32_t n, const float* pos_xy, const float* mass, 
   e.rec.assign(M, NodeRec{0, 0, 0, 0.f, 0});
   e.ndepth.assign(M, 0);
   e.t = TreeArrays{e.nodeA.data(), e.nodeB.data(), e.rec.data(), e.ndepth.data(), e.node_mass.data(),
-                   e.parent.data(), e.sums.data(), e.level_nodes.data(), M};
+                   e.parent.data(), e.sums.data(), e.level_nodes.data(), nullptr, M};
   HostSink sink{&e.meta};
   for (uint32_t i = 0; i < n; ++i)
     emit_nodes_for_body(e.keys.data(), n, i, le[i], nodebase.data(), M, e.pqr.data(), e.accm.data(),
-                        leaf_capacity, thread_capacity, r.size, dcap, e.t, sink);
+                        leaf_capacity, thread_capacity, r.size, dcap, e.t, sink, 0, 0, kMaxLevels + 1,
+                        /*internal_ranges=*/true);
   // build sweep, then the export sweep (parents, masses, counts, chargeless centres)
   for (int level = kMaxLevels - 1; level >= 0; --level)
     for (uint32_t k = e.meta.level_start[level]; k < e.meta.level_start[level + 1]; ++k)
-      aggregate_node_lean(e.level_nodes[k], level, M, e.t);
-  for (uint32_t node = 0; node < M; ++node) finalize_node(node, r.size, e.pqr.data(), e.accm.data(), e.t, SubtreeEndLocal{M, n, e.t.nodeB});
+      aggregate_node_ranged(e.level_nodes[k], level, e.t);
+  for (uint32_t node = 0; node < M; ++node) finalize_node(node, r.size, e.pqr.data(), e.accm.data(), e.t, SubtreeEndCount{});
   if (M && (e.nodeB[0].w & kNodeLeaf)) {
     float lm = 0.f;
     if (!(e.nodeB[0].w & kNodeZeroAgg))
