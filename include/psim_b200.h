@@ -262,6 +262,24 @@ int32_t psim_set_electron_range(psim_ctx *ctx, uint64_t first, uint64_t count);
  * e_field (float2), electron rel_pos (float2), electron vel (float2); out[6] = body capacity,
  * out[7] = electron capacity */
 int32_t psim_device_ptrs(psim_ctx *ctx, uint64_t *out8);
+/* Simulation::update_surrounded_flags (src/simulation/simulation.rs:1893-1918): rebins the cell list at
+ * max_lj_cutoff and, for every body that moved more than SURROUND_MOVE_THRESHOLD * radius or was last
+ * checked SURROUND_CHECK_INTERVAL frames ago (body/types.rs:243-286, config.rs:186-188), recounts its
+ * LithiumMetal / FoilMetal neighbours within radius * radius_factor (CellList::metal_neighbor_count,
+ * cell_list.rs:92-127) and sets surrounded_by_metal = count >= neighbor_threshold.  radius_factor and
+ * neighbor_threshold are the reference's runtime-mutable values (renderer/state.rs:30-36; defaults 4.0, 8).
+ * The per-body state (flag, last position, last frame) lives on the device, keyed by original index, and is
+ * initialised by psim_upload_bodies like Body::new (last position = position, frame 0). */
+int32_t psim_update_surrounded_flags(psim_ctx *ctx, float hw, float hh, uint64_t frame, float radius_factor,
+                                     uint64_t neighbor_threshold);
+/* the state in the CURRENT body order; any pointer may be NULL.  Synchronises. */
+int32_t psim_get_surrounded(psim_ctx *ctx, uint8_t *flags, float *last_pos_xy, uint64_t *last_frame);
+/* enforce_metal_z_boundaries (src/simulation/out_of_plane.rs:140-254): rebins at 4 x the metal radius and
+ * clamps z / zeroes vz of every non-metal body against its first five metal neighbours in the reference's
+ * cell order, then Body::clamp_z(max_z).  (The reference walks the tree instead when the density is below
+ * the cell-list threshold; the neighbour sets agree, the order of the first five may not.) */
+int32_t psim_enforce_metal_z_boundaries(psim_ctx *ctx, float max_z, float hw, float hh);
+
 /* Sharded build (replaces the single work queue of Quadtree::build_internal,
  * src/quadtree/quadtree.rs:197-345, across ranks).  Every rank holds all bodies; rank r sorts the keys of
  * a contiguous range of 65 536 top-level cells and emits the tree nodes that start in it.  The pieces

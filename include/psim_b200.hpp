@@ -228,6 +228,20 @@ class Simulation {
                        config.enable_out_of_plane ? 1 : 0));
     download_fields(true, false, false);
   }
+  // simulation.rs:1893-1918 (+ body/types.rs:243-286, cell_list.rs:92-127); flags in the current body order
+  std::vector<uint8_t> update_surrounded_flags(uint64_t frame, float radius_factor = 4.0f,
+                                               uint64_t neighbor_threshold = 8) {
+    ensure_uploaded();
+    check(psim_update_surrounded_flags(ctx_, domain_width, domain_height, frame, radius_factor, neighbor_threshold));
+    std::vector<uint8_t> flags(bodies.size());
+    check(psim_get_surrounded(ctx_, flags.data(), nullptr, nullptr));
+    return flags;
+  }
+  void enforce_metal_z_boundaries(float max_z) {  // simulation/out_of_plane.rs:140-254
+    ensure_uploaded();
+    check(psim_enforce_metal_z_boundaries(ctx_, max_z, domain_width, domain_height));
+    download_fields(true, false, false);
+  }
   void update_electrons() {  // simulation.rs:1186-1196 + body/electron.rs:19-46
     ensure_uploaded();
     check(psim_update_electrons(ctx_, background_e_field.x, background_e_field.y, dt, config.coulomb_constant));

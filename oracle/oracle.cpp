@@ -721,7 +721,14 @@ void orc_set_bodies(OrcSim *s, uint64_t n, const float *pos_xy, const float *z, 
     b.species = species ? species[i] : 0;
     b.id = i;
     b.species_lock_until = -INFINITY;
+    b.last_surround_pos = b.pos;  // Body::new, body/types.rs:111-113
+    b.last_surround_frame = 0;
   }
+}
+
+// positions only (the rest of the state, e.g. the surround bookkeeping, is kept)
+void orc_set_positions(OrcSim *s, const float *pos_xy) {
+  for (size_t i = 0; i < s->bodies.size(); ++i) s->bodies[i].pos = v2(pos_xy[2 * i], pos_xy[2 * i + 1]);
 }
 
 void orc_set_electrons(OrcSim *s, uint64_t m, const uint32_t *body, const float *rel_xy,
@@ -1202,6 +1209,119 @@ void orc_update_electrons(OrcSim *s, float bg_x, float bg_y, float dt, float k_e
       float max_dist = sp(s, self.species).polar_offset * self.radius;
       if (mag(e.rel_pos) > max_dist) e.rel_pos = normalized(e.rel_pos) * max_dist;
     }
+  }
+}
+
+// simulation.rs:1893-1918 (update_surrounded_flags) with body/types.rs:243-286 (maybe_update_surrounded)
+// and cell_list.rs:92-127 (metal_neighbor_count).  radius_factor / neighbor_threshold are the runtime
+// values of renderer/state.rs:30-36 (defaults config.rs:182-184); the move threshold and the check
+// interval are config.rs:186-188.
+void orc_update_surrounded_flags(OrcSim *s, float hw, float hh, float density_threshold, uint64_t frame,
+                                 float radius_factor, uint64_t neighbor_threshold) {
+  const float SURROUND_MOVE_THRESHOLD = 0.5f;
+  const uint64_t SURROUND_CHECK_INTERVAL = 10;
+  if (s->bodies.empty()) return;
+  const int use_cell = orc_use_cell_list(s, hw, hh, density_threshold);
+  const float neighbor_radius = max_lj_cutoff(s);
+  if (use_cell) {
+    s->cl.domain_width = hw;
+    s->cl.domain_height = hh;
+    s->cl.cell_size = neighbor_radius;
+    s->cl.rebuild(s->bodies);
+  } else {
+    s->qt.build(s->bodies, 1, hw, hh, 1);
+  }
+  std::vector<size_t> nb;
+  for (size_t i = 0; i < s->bodies.size(); ++i) {
+    Body &self = s->bodies[i];
+    const bool moved = mag(self.pos - self.last_surround_pos) > SURROUND_MOVE_THRESHOLD * self.radius;
+    const uint64_t frame_diff =
+        frame >= self.last_surround_frame ? frame - self.last_surround_frame : SURROUND_CHECK_INTERVAL;
+    if (moved || frame_diff >= SURROUND_CHECK_INTERVAL) {
+      const float radius = self.radius * radius_factor;
+      uint64_t count = 0;
+      if (use_cell) {
+        s->cl.find_neighbors_within(s->bodies, i, radius, nb, true);
+        count = nb.size();
+      } else {
+        s->qt.find_neighbors_within(s->bodies, i, radius, nb);
+        for (size_t j : nb)
+          if (s->bodies[j].species == 1 || s->bodies[j].species == 2) ++count;
+      }
+      self.surrounded_by_metal = count >= neighbor_threshold;
+      self.last_surround_pos = self.pos;
+      self.last_surround_frame = frame;
+    }
+  }
+}
+void orc_get_surrounded(const OrcSim *s, uint8_t *flags, float *last_pos_xy, uint64_t *last_frame) {
+  for (size_t i = 0; i < s->bodies.size(); ++i) {
+    if (flags) flags[i] = s->bodies[i].surrounded_by_metal ? 1 : 0;
+    if (last_pos_xy) last_pos_xy[2 * i] = s->bodies[i].last_surround_pos.x, last_pos_xy[2 * i + 1] = s->bodies[i].last_surround_pos.y;
+    if (last_frame) last_frame[i] = s->bodies[i].last_surround_frame;
+  }
+}
+
+// simulation/out_of_plane.rs:140-254 (enforce_metal_z_boundaries)
+void orc_enforce_metal_z_boundaries(OrcSim *s, float max_z, float hw, float hh, float density_threshold) {
+  if (!std::isfinite(max_z) || max_z <= 0.0f) return;
+  bool any_metal = false;
+  for (const Body &b : s->bodies)
+    if (b.species == 1 || b.species == 2) any_metal = true;
+  if (!any_metal) return;
+  const int use_cell = orc_use_cell_list(s, hw, hh, density_threshold);
+  const float metal_max_r = rmax(sp(s, 1).radius, sp(s, 2).radius);
+  if (use_cell) {
+    s->cl.domain_width = hw;
+    s->cl.domain_height = hh;
+    s->cl.cell_size = 4.0f * metal_max_r;
+    s->cl.rebuild(s->bodies);
+  } else {
+    s->qt.build(s->bodies, 0, 0, 0, 1);
+  }
+  std::vector<size_t> neighbors;
+  for (size_t i = 0; i < s->bodies.size(); ++i) {
+    if (s->bodies[i].species == 1 || s->bodies[i].species == 2) continue;
+    const V2 body_pos = s->bodies[i].pos;
+    const float body_radius = s->bodies[i].radius;
+    const float cutoff = 3.0f * body_radius + metal_max_r;
+    neighbors_of(s, use_cell, i, cutoff, neighbors);
+    float min_z_constraint = -max_z, max_z_constraint = max_z;
+    int constraints_applied = 0;
+    for (size_t j : neighbors) {
+      if (!(s->bodies[j].species == 1 || s->bodies[j].species == 2)) continue;
+      if (j == i) continue;
+      constraints_applied += 1;
+      if (constraints_applied > 5) break;
+      const V2 metal_pos = s->bodies[j].pos;
+      const float metal_radius = s->bodies[j].radius;
+      const float dx = body_pos.x - metal_pos.x, dy = body_pos.y - metal_pos.y;
+      const float distance_sq = dx * dx + dy * dy;
+      const float reach = body_radius + metal_radius + 2.0f * body_radius;
+      const float thresh = reach * reach;  // powi(2)
+      if (distance_sq > thresh) continue;
+      const float distance_2d = std::sqrt(distance_sq);
+      if (distance_2d < body_radius + metal_radius + 2.0f * body_radius) {
+        const float metal_z = s->bodies[j].z;
+        const float lower_bound = metal_z - metal_radius - 0.01f, upper_bound = metal_z + metal_radius + 0.01f;
+        if (lower_bound < upper_bound) {
+          min_z_constraint = rmax(min_z_constraint, lower_bound);
+          max_z_constraint = rmin(max_z_constraint, upper_bound);
+        }
+      }
+    }
+    if (min_z_constraint > max_z_constraint) min_z_constraint = 0.0f - 0.1f, max_z_constraint = 0.0f + 0.1f;
+    Body &body = s->bodies[i];
+    if (body.z < min_z_constraint) {
+      body.z = min_z_constraint;
+      if (body.vz < 0.0f) body.vz = 0.0f;
+    }
+    if (body.z > max_z_constraint) {
+      body.z = max_z_constraint;
+      if (body.vz > 0.0f) body.vz = 0.0f;
+    }
+    if (body.z > max_z) body.z = max_z, body.vz = 0.0f;  // Body::clamp_z, body/types.rs:296-304
+    else if (body.z < -max_z) body.z = -max_z, body.vz = 0.0f;
   }
 }
 

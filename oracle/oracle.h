@@ -86,6 +86,7 @@ void orc_set_bodies(OrcSim *, uint64_t n, const float *pos_xy, const float *z, c
                     const float *vz, const float *mass, const float *radius, const float *charge,
                     const uint8_t *species);
 /* electrons, flattened: body index (in CURRENT order), rel_pos, vel */
+void orc_set_positions(OrcSim *, const float *pos_xy);
 void orc_set_electrons(OrcSim *, uint64_t m, const uint32_t *body, const float *rel_xy,
                        const float *vel_xy);
 uint64_t orc_num_bodies(const OrcSim *);
@@ -144,6 +145,11 @@ void orc_iterate(OrcSim *, float dt, float damping_base, float hw, float hh, flo
                  int enable_out_of_plane, int threads);
 /* the serial loop at simulation.rs:1186-1196 (threads>1 = the "all-parallel" variant) */
 void orc_update_electrons(OrcSim *, float bg_x, float bg_y, float dt, float k_e, int threads);
+/* simulation.rs:1893-1918 + body/types.rs:243-286; out_of_plane.rs:140-254 */
+void orc_update_surrounded_flags(OrcSim *, float hw, float hh, float density_threshold, uint64_t frame,
+                                 float radius_factor, uint64_t neighbor_threshold);
+void orc_get_surrounded(const OrcSim *, uint8_t *flags, float *last_pos_xy, uint64_t *last_frame);
+void orc_enforce_metal_z_boundaries(OrcSim *, float max_z, float hw, float hh, float density_threshold);
 
 /* ---- FP64 direct O(N^2) field with the same softening (physics_invariants.rs:2430-2450) ----
  * target_radius NULL => 0.  Sources are the current bodies. */

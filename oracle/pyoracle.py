@@ -88,6 +88,7 @@ def load(variant: str = "") -> C.CDLL:
         "orc_default_species_table": (None, [vp]),
         "orc_set_bodies": (None, [vp, u64, pf, pf, pf, pf, pf, pf, pf, pu8]),
         "orc_set_electrons": (None, [vp, u64, pu32, pf, pf]),
+        "orc_set_positions": (None, [vp, pf]),
         "orc_num_bodies": (u64, [vp]),
         "orc_num_electrons": (u64, [vp]),
         "orc_get_bodies": (None, [vp, pu64, pf, pf, pf, pf, pf, pf, pf, pf, pf, pu8, pf]),
@@ -118,6 +119,9 @@ def load(variant: str = "") -> C.CDLL:
         "orc_apply_stack_pressure": (None, [vp, i, f, f, f]),
         "orc_iterate": (None, [vp, f, f, f, f, f, i, i]),
         "orc_update_electrons": (None, [vp, f, f, f, f, i]),
+        "orc_update_surrounded_flags": (None, [vp, f, f, f, u64, f, u64]),
+        "orc_get_surrounded": (None, [vp, vp, vp, vp]),
+        "orc_enforce_metal_z_boundaries": (None, [vp, f, f, f, f]),
         "orc_direct_f64": (None, [vp, u64, pf, pf, C.c_double, C.c_double, pd, i]),
         "orc_max_threads": (i, []),
         "orc_uv_fma": (i, []),
@@ -162,6 +166,11 @@ class OracleSim:
         sp = None if species is None else np.ascontiguousarray(species, dtype=np.uint8)
         self.lib.orc_set_bodies(self.h, n, _ptr(pos), _ptr(z), _ptr(vel), _ptr(vz), _ptr(mass),
                                 _ptr(radius), _ptr(charge), _ptr(sp, C.c_uint8))
+
+    def set_positions(self, pos):
+        pos = _f32(pos, (-1, 2))
+        assert len(pos) == self.n
+        self.lib.orc_set_positions(self.h, _ptr(pos))
 
     def set_electrons(self, body, rel, vel=None):
         body = np.ascontiguousarray(body, dtype=np.uint32)
@@ -316,3 +325,17 @@ class OracleSim:
 
     def update_electrons(self, bg, dt, k_e, threads=1):
         self.lib.orc_update_electrons(self.h, bg[0], bg[1], dt, k_e, threads)
+
+    # ---- neighbour-count consumers
+    def update_surrounded_flags(self, hw, hh, frame, radius_factor=4.0, neighbor_threshold=8, threshold=0.001):
+        self.lib.orc_update_surrounded_flags(self.h, hw, hh, threshold, int(frame), radius_factor, int(neighbor_threshold))
+
+    def surrounded(self):
+        n = self.n
+        flags, pos, frame = np.zeros(n, np.uint8), np.zeros((n, 2), np.float32), np.zeros(n, np.uint64)
+        self.lib.orc_get_surrounded(self.h, flags.ctypes.data_as(C.c_void_p), pos.ctypes.data_as(C.c_void_p),
+                                    frame.ctypes.data_as(C.c_void_p))
+        return flags, pos, frame
+
+    def enforce_metal_z_boundaries(self, max_z, hw, hh, threshold=0.001):
+        self.lib.orc_enforce_metal_z_boundaries(self.h, max_z, hw, hh, threshold)

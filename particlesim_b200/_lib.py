@@ -108,6 +108,9 @@ SIGNATURES = {
     "psim_short_range": (_i32, [_vp, _u32]),
     "psim_apply_polar_forces": (_i32, [_vp, _f, _i32]),
     "psim_iterate": (_i32, [_vp, _f, _f, _f, _f, _f, _i32]),
+    "psim_update_surrounded_flags": (_i32, [_vp, _f, _f, _u64, _f, _u64]),
+    "psim_get_surrounded": (_i32, [_vp, _vp, _vp, _vp]),
+    "psim_enforce_metal_z_boundaries": (_i32, [_vp, _f, _f, _f]),
     "psim_shard_init": (_i32, [_vp, _u32, _u32]),
     "psim_shard_phase": (_i32, [_vp, _i32, _i32, _f, _f, _vp]),
     "psim_shard_ptrs": (_i32, [_vp, _vp]),

@@ -16,6 +16,7 @@
 #include "polar.cuh"
 #include "sort.cuh"
 #include "traverse.cuh"
+#include "neighbors.cuh"
 #include "shard.cuh"
 #include "tree.cuh"
 
@@ -90,6 +91,7 @@ struct psim_ctx {
   uint32_t* inv = nullptr;
   bool tree_valid = false;
   bool perm_valid = false;
+  SurroundState surround = {nullptr, nullptr, nullptr};  // by original body id
 
   // sharded build (shard.cuh): allocated by psim_shard_init
   struct Shard {
@@ -1046,6 +1048,7 @@ void free_all(psim_ctx* c) {
   F(c->t.rec), F(c->t.ndepth);
   F(c->travA), F(c->travB), F(c->trav_rank), F(c->trav_count);
   F(c->perm), F(c->inv);
+  F(c->surround.last_pos), F(c->surround.last_frame), F(c->surround.flag);
   F(c->cell_start), F(c->cell_end), F(c->order), F(c->body_cell), F(c->cpos), F(c->polarB), F(c->polar_cutoff), F(c->cell_off);
   F(c->table_d), F(c->stage), F(c->qstage), F(c->step_counter);
 }
@@ -1126,6 +1129,7 @@ int32_t psim_create(int32_t device, uint64_t max_bodies, uint64_t max_electrons,
   A(&ctx->travA, ctx->node_cap), A(&ctx->travB, ctx->node_cap), A(&ctx->trav_rank, ctx->node_cap), A(&ctx->trav_count, 1);
   ctx->t.node_cap = ctx->node_cap;
   A(&ctx->perm, nb), A(&ctx->inv, nb);
+  A(&ctx->surround.last_pos, nb), A(&ctx->surround.last_frame, nb), A(&ctx->surround.flag, nb);
   A(&ctx->order, nb), A(&ctx->body_cell, nb), A(&ctx->cpos, nb);
   A(&ctx->polarB, nb), A(&ctx->polar_cutoff, 1);
   A(&ctx->table_d, kMaxSpecies), A(&ctx->step_counter, 1);
@@ -1319,6 +1323,9 @@ int32_t psim_upload_bodies(psim_ctx* ctx, uint64_t n, const float* pos_xy, const
   CK(cudaGetLastError());
   if (!r.pos) return fail(ctx, PSIM_E_CUDA, "psim_upload_bodies: host to device copy failed");
   pack_bodies_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(r, (uint32_t)n, ctx->b[ctx->cur]);
+  LAUNCHED(ctx);
+  surround_init_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(ctx->b[ctx->cur].pqr, ctx->b[ctx->cur].orig,
+                                                                 (uint32_t)n, ctx->surround);
   LAUNCHED(ctx);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(st));  // the caller may reuse its buffers
@@ -1876,6 +1883,63 @@ int32_t psim_device_ptrs(psim_ctx* ctx, uint64_t* out8) {
   out8[6] = ctx->cap_bodies, out8[7] = ctx->cap_elec;
   return PSIM_OK;
 }
+// ---- neighbour-count consumers (neighbors.cuh) --------------------------------
+int32_t psim_update_surrounded_flags(psim_ctx* ctx, float hw, float hh, uint64_t frame, float radius_factor,
+                                     uint64_t neighbor_threshold) {
+  if (!ctx) return PSIM_E_ARG;
+  if (ctx->n == 0) return PSIM_OK;  // simulation.rs:1894-1896
+  const float neighbor_radius = max_lj_cutoff(ctx);
+  if (!(neighbor_radius > 0.0f)) return fail(ctx, PSIM_E_ARG, "psim_update_surrounded_flags: no LJ species (cell size 0)");
+  // the reference bins at max_lj_cutoff when the density is above the cell-list threshold and walks the
+  // tree otherwise (simulation.rs:1898-1909); the neighbour SETS are the same, so the grid serves both
+  int32_t rc = cell_build_async(ctx, hw, hh, neighbor_radius);
+  if (rc) return rc;
+  BodyArrays& b = ctx->b[ctx->cur];
+  SurroundParams P;
+  P.frame = frame, P.interval = 10ull, P.neighbor_threshold = neighbor_threshold;  // config.rs:186-188
+  P.radius_factor = radius_factor, P.move_threshold = 0.5f;
+  surrounded_kernel<<<(int)((ctx->n + 127) / 128), 128, 0, ctx->stream>>>(
+      b.pqr, b.species, b.orig, ctx->n, ctx->cell_start, ctx->cell_end, ctx->order, ctx->grid, P, ctx->surround);
+  LAUNCHED(ctx);
+  CK(cudaGetLastError());
+  return PSIM_OK;
+}
+
+int32_t psim_get_surrounded(psim_ctx* ctx, uint8_t* flags, float* last_pos_xy, uint64_t* last_frame) {
+  if (!ctx) return PSIM_E_ARG;
+  const uint64_t n = ctx->n;
+  if (n == 0) return PSIM_OK;
+  const size_t o_f = 0, o_p = o_f + align256(n), o_l = o_p + align256(8 * n), total = o_l + align256(8 * n);
+  int32_t rc = ensure_stage(ctx, total);
+  if (rc) return rc;
+  char* sb = static_cast<char*>(ctx->stage);
+  cudaStream_t st = ctx->stream;
+  surround_export_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(
+      ctx->b[ctx->cur].orig, (uint32_t)n, ctx->surround, reinterpret_cast<uint8_t*>(sb + o_f),
+      reinterpret_cast<float2*>(sb + o_p), reinterpret_cast<unsigned long long*>(sb + o_l));
+  LAUNCHED(ctx);
+  if (flags) CK(cudaMemcpyAsync(flags, sb + o_f, n, cudaMemcpyDeviceToHost, st));
+  if (last_pos_xy) CK(cudaMemcpyAsync(last_pos_xy, sb + o_p, 8 * n, cudaMemcpyDeviceToHost, st));
+  if (last_frame) CK(cudaMemcpyAsync(last_frame, sb + o_l, 8 * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return PSIM_OK;
+}
+
+int32_t psim_enforce_metal_z_boundaries(psim_ctx* ctx, float max_z, float hw, float hh) {
+  if (!ctx) return PSIM_E_ARG;
+  if (!isfinite(max_z) || max_z <= 0.0f) return PSIM_OK;            // out_of_plane.rs:142-145
+  if (ctx->n == 0 || !(ctx->species_present & 0x6u)) return PSIM_OK;  // no metals: :147-154
+  const float metal_max_r = fmaxf(ctx->table_h[1].radius, ctx->table_h[2].radius);
+  int32_t rc = cell_build_async(ctx, hw, hh, 4.0f * metal_max_r);  // :160-163
+  if (rc) return rc;
+  BodyArrays& b = ctx->b[ctx->cur];
+  metal_z_kernel<<<(int)((ctx->n + 127) / 128), 128, 0, ctx->stream>>>(
+      b.pqr, b.velz, b.species, ctx->n, ctx->cell_start, ctx->cell_end, ctx->order, ctx->grid, metal_max_r, max_z);
+  LAUNCHED(ctx);
+  CK(cudaGetLastError());
+  return PSIM_OK;
+}
+
 int32_t psim_shard_init(psim_ctx* ctx, uint32_t rank, uint32_t world) {
   if (!ctx || world < 1 || world > (uint32_t)kMaxRanks || rank >= world)
     return fail(ctx, PSIM_E_ARG, "psim_shard_init: rank / world (at most 64 ranks)");

@@ -332,6 +332,25 @@ class Simulation:
                    self.domain_depth, int(self.config.enable_out_of_plane))
         self.download(("pos", "vel", "z", "vz"))
 
+    def update_surrounded_flags(self, radius_factor=4.0, neighbor_threshold=8):
+        """simulation.rs:1893-1918 (+ Body::maybe_update_surrounded, CellList::metal_neighbor_count).  Uses
+        self.frame like the reference; returns the flags in the current body order."""
+        self._call("psim_update_surrounded_flags", self.domain_width, self.domain_height,
+                   int(getattr(self, "frame", 0)), np.float32(radius_factor), int(neighbor_threshold))
+        return self.surrounded()[0]
+
+    def surrounded(self):
+        """(surrounded_by_metal, last_surround_pos, last_surround_frame) per body, current order"""
+        n = len(self.bodies)
+        flags, pos, frame = np.zeros(n, np.uint8), np.zeros((n, 2), np.float32), np.zeros(n, np.uint64)
+        self._call("psim_get_surrounded", _p(flags), _p(pos), _p(frame))
+        return flags, pos, frame
+
+    def enforce_metal_z_boundaries(self, max_z):
+        """simulation/out_of_plane.rs:140-254"""
+        self._call("psim_enforce_metal_z_boundaries", np.float32(max_z), self.domain_width, self.domain_height)
+        self.download(("z", "vz"))
+
     def update_electrons(self):
         """the loop at simulation.rs:1186-1196 over Body::update_electrons (body/electron.rs:19-46)"""
         self._call("psim_update_electrons", self.background_e_field[0], self.background_e_field[1], self.dt,

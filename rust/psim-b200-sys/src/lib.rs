@@ -116,6 +116,13 @@ extern "C" {
     pub fn psim_short_range(ctx: *mut psim_ctx, flags: u32) -> i32;
     pub fn psim_apply_polar_forces(ctx: *mut psim_ctx, k_e: f32, dipole_model: i32) -> i32;
     pub fn psim_iterate(ctx: *mut psim_ctx, dt: f32, damping_base: f32, hw: f32, hh: f32, hd: f32, enable_out_of_plane: i32) -> i32;
+    pub fn psim_update_surrounded_flags(ctx: *mut psim_ctx, hw: f32, hh: f32, frame: u64, radius_factor: f32,
+                                        neighbor_threshold: u64) -> i32;
+    pub fn psim_get_surrounded(ctx: *mut psim_ctx, flags: *mut u8, last_pos_xy: *mut f32, last_frame: *mut u64) -> i32;
+    pub fn psim_enforce_metal_z_boundaries(ctx: *mut psim_ctx, max_z: f32, hw: f32, hh: f32) -> i32;
+    pub fn psim_shard_init(ctx: *mut psim_ctx, rank: u32, world: u32) -> i32;
+    pub fn psim_shard_phase(ctx: *mut psim_ctx, phase: i32, mode: i32, hw: f32, hh: f32, out: *mut u32) -> i32;
+    pub fn psim_shard_ptrs(ctx: *mut psim_ctx, out8: *mut u64) -> i32;
     pub fn psim_step(ctx: *mut psim_ctx, p: *const psim_step_params) -> i32;
     pub fn psim_step_host(ctx: *mut psim_ctx, p: *const psim_step_params, n: u64, pos_xy: *const f32,
                           vel_xy: *const f32, charge: *const f32, out_pos_xy: *mut f32, out_vel_xy: *mut f32,
