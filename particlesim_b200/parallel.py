@@ -56,17 +56,18 @@ def all_gatherv(full, offsets, rank: int, dist):
     return full
 
 
-def all_gatherv_padded(full, offsets, rank: int, dist, stage_cache: dict):
+def all_gatherv_padded_begin(full, offsets, rank: int, dist, stage_cache: dict, async_op: bool = False):
     """The same exchange as ONE all-gather: every rank contributes a block of max-segment rows starting at
     its segment (rows past its count are padding), the blocks land in a staging tensor and the valid rows
-    are copied into place.  One ncclAllGather at full NVSwitch bandwidth instead of world broadcasts."""
+    are copied into place by all_gatherv_padded_end.  One ncclAllGather at full NVSwitch bandwidth instead
+    of world broadcasts; with async_op the caller can queue independent work before the end call."""
     world = len(offsets) - 1
     counts = [int(offsets[r + 1]) - int(offsets[r]) for r in range(world)]
     seg = max(counts)
     if seg == 0:
-        return full
+        return None
     seg = (seg + 1023) // 1024 * 1024  # few distinct staging sizes across builds
-    key = (full.dtype, tuple(full.shape[1:]), full.device)
+    key = (full.data_ptr(), full.dtype, tuple(full.shape[1:]))
     need = world * seg
     stage = stage_cache.get(key)
     if stage is None or stage.shape[0] < need + seg:
@@ -78,10 +79,23 @@ def all_gatherv_padded(full, offsets, rank: int, dist, stage_cache: dict):
     else:  # the padded block would run past the end of the array: go through the spare block
         mine = stage[need:need + seg]
         mine[:counts[rank]].copy_(full[a:a + counts[rank]])
-    dist.all_gather_into_tensor(stage[:need], mine)
-    for r in range(world):
+    work = dist.all_gather_into_tensor(stage[:need], mine, async_op=async_op)
+    return full, offsets, rank, counts, seg, stage, work
+
+
+def all_gatherv_padded_end(pending):
+    if pending is None:
+        return
+    full, offsets, rank, counts, seg, stage, work = pending
+    if work is not None:
+        work.wait()
+    for r in range(len(counts)):
         if r != rank and counts[r]:
             full[int(offsets[r]):int(offsets[r + 1])].copy_(stage[r * seg:r * seg + counts[r]])
+
+
+def all_gatherv_padded(full, offsets, rank: int, dist, stage_cache: dict):
+    all_gatherv_padded_end(all_gatherv_padded_begin(full, offsets, rank, dist, stage_cache))
     return full
 
 
@@ -94,10 +108,17 @@ class DistComm:
         self._stage = {}
 
     def all_gatherv(self, tensors, offsets):
+        self.all_gatherv_end(self.all_gatherv_begin(tensors, offsets, async_op=False))
+
+    def all_gatherv_begin(self, tensors, offsets, async_op=True):
+        """start the exchange; with the padded NCCL path it runs beside whatever is queued before _end"""
         if self.padded:
-            all_gatherv_padded(tensors[0], offsets, self.rank, self.dist, self._stage)
-        else:
-            all_gatherv(tensors[0], offsets, self.rank, self.dist)
+            return all_gatherv_padded_begin(tensors[0], offsets, self.rank, self.dist, self._stage, async_op)
+        all_gatherv(tensors[0], offsets, self.rank, self.dist)
+        return None
+
+    def all_gatherv_end(self, pending):
+        all_gatherv_padded_end(pending)
 
     def all_reduce(self, tensors):
         self.dist.all_reduce(tensors[0])
@@ -113,6 +134,13 @@ class LoopbackComm:
             for q, dst in enumerate(tensors):
                 if q != r and b > a:
                     dst[a:b].copy_(src[a:b])
+
+    def all_gatherv_begin(self, tensors, offsets, async_op=True):
+        self.all_gatherv(tensors, offsets)
+        return None
+
+    def all_gatherv_end(self, pending):
+        pass
 
     def all_reduce(self, tensors):
         total = tensors[0].clone()
@@ -132,10 +160,12 @@ def shard_views(sim, torch):
                 heap=mk(p[2], (int(p[6]),), "<i8"), travA=mk(p[3], (cap, 4), "<i4"), travB=mk(p[4], (cap, 4), "<i4"))
 
 
-def sharded_build(sims, mode: int, hw: float, hh: float, comm, torch, mark=None):
+def sharded_build(sims, mode: int, hw: float, hh: float, comm, torch, mark=None, overlap=None):
     """Quadtree::build / build_with_domain across ranks (include/psim_b200.h, psim_shard_phase): `sims`
     are the contexts of the ranks that live in this process (one under torchrun).  `mark(name)`, if given,
-    is called at every phase / exchange boundary (tools/shard_phases.py records CUDA events there)."""
+    is called at every phase / exchange boundary (tools/shard_phases.py records CUDA events there);
+    `overlap()`, if given, queues work that does not need the tree (the cell-list rebuild) while the
+    traversal segments travel."""
     mark = mark or (lambda name: None)
     world = sims[0].world
     lo = [np.zeros(world + 1, np.uint32) for _ in sims]
@@ -170,8 +200,12 @@ def sharded_build(sims, mode: int, hw: float, hh: float, comm, torch, mark=None)
     tl = [np.zeros(world + 1, np.uint32) for _ in sims]
     phase(5, tl)
     mark("p5 compact")
-    comm.all_gatherv([v["travA"] for v in views], tl[0])
-    comm.all_gatherv([v["travB"] for v in views], tl[0])
+    pa = comm.all_gatherv_begin([v["travA"] for v in views], tl[0])
+    pb = comm.all_gatherv_begin([v["travB"] for v in views], tl[0])
+    if overlap is not None:
+        overlap()
+    comm.all_gatherv_end(pa)
+    comm.all_gatherv_end(pb)
     mark("x5 traversal all-gather")
     phase(6)
     mark("p6 children links")
@@ -219,13 +253,15 @@ class ShardedSimulation(Simulation):
         return dict(pqr=mk(p[0], nb, 4), velz=mk(p[1], nb, 4), erel=mk(p[4], ne, 2) if ne else None,
                     evel=mk(p[5], ne, 2) if ne else None)
 
-    def _build(self, mode, hw, hh):
+    def _build(self, mode, hw, hh, overlap=None):
         """each rank builds the part of the tree that starts in its key range (local_build), or every rank
         builds the whole tree (the v1 scheme, kept for comparison)"""
         if self.local_build:
-            sharded_build([self], mode, hw, hh, self._comm, self.torch)
+            sharded_build([self], mode, hw, hh, self._comm, self.torch, overlap=overlap)
         else:
             self._call("psim_build_async", mode, hw, hh)
+            if overlap is not None:
+                overlap()
 
     def step_device(self, params=None, record=False):
         """Simulation::step's hot path (simulation.rs:1000-1196), sharded.  record=True keeps CUDA events
@@ -242,11 +278,12 @@ class ShardedSimulation(Simulation):
 
         mark()
         C("psim_reset_acc")
-        self._build(_lib.BUILD_CONTAINING, 0.0, 0.0)
-        mark()
         cell = self.step_cell_size(bool(getattr(p, "do_polar", 0)))  # what psim_step uses: same addition order
-        if p.do_short_range and cell > 0.0:
-            C("psim_cell_build", p.hw, p.hh, cell)
+        do_cells = bool(p.do_short_range and cell > 0.0)
+        # the cell-list rebuild only needs the sorted bodies: it runs while the tree pieces travel
+        self._build(_lib.BUILD_CONTAINING, 0.0, 0.0,
+                    overlap=(lambda: C("psim_cell_build", p.hw, p.hh, cell)) if do_cells else None)
+        mark()
         mark()
         C("psim_field", p.k_e, p.bg_x, p.bg_y, 1, None, None)
         mark()
