@@ -160,12 +160,13 @@ def shard_views(sim, torch):
                 heap=mk(p[2], (int(p[6]),), "<i8"), travA=mk(p[3], (cap, 4), "<i4"), travB=mk(p[4], (cap, 4), "<i4"))
 
 
-def sharded_build(sims, mode: int, hw: float, hh: float, comm, torch, mark=None, overlap=None):
+def sharded_build(sims, mode: int, hw: float, hh: float, comm, torch, mark=None, overlap=None, before_gather=None):
     """Quadtree::build / build_with_domain across ranks (include/psim_b200.h, psim_shard_phase): `sims`
     are the contexts of the ranks that live in this process (one under torchrun).  `mark(name)`, if given,
     is called at every phase / exchange boundary (tools/shard_phases.py records CUDA events there);
     `overlap()`, if given, queues work that does not need the tree (the cell-list rebuild) while the
-    traversal segments travel."""
+    traversal segments travel; `before_gather()` runs before the phase that permutes the body arrays (the
+    sharded step waits there for the velocities it all-gathers behind the first two phases)."""
     mark = mark or (lambda name: None)
     world = sims[0].world
     lo = [np.zeros(world + 1, np.uint32) for _ in sims]
@@ -185,6 +186,8 @@ def sharded_build(sims, mode: int, hw: float, hh: float, comm, torch, mark=None,
     mark("p1 select+sort")
     comm.all_gatherv([v["order"] for v in views], lo[0])
     mark("x1 order all-gather")
+    if before_gather is not None:
+        before_gather()
     phase(2)
     mark("p2 gather (replicated)+levels")
     comm.all_reduce([v["xbuf"] for v in views])
@@ -232,6 +235,7 @@ class ShardedSimulation(Simulation):
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self._scratch_b = torch.empty((self.wb, 4), dtype=torch.float32, device="cuda")
+        self._scratch_v = torch.empty((self.wb, 4), dtype=torch.float32, device="cuda")
         self._scratch_e = torch.empty((self.we, 2), dtype=torch.float32, device="cuda")
         self._shard_nb = kw["max_bodies"]
         self.local_build = local_build and world > 1
@@ -253,12 +257,14 @@ class ShardedSimulation(Simulation):
         return dict(pqr=mk(p[0], nb, 4), velz=mk(p[1], nb, 4), erel=mk(p[4], ne, 2) if ne else None,
                     evel=mk(p[5], ne, 2) if ne else None)
 
-    def _build(self, mode, hw, hh, overlap=None):
+    def _build(self, mode, hw, hh, overlap=None, before_gather=None):
         """each rank builds the part of the tree that starts in its key range (local_build), or every rank
         builds the whole tree (the v1 scheme, kept for comparison)"""
         if self.local_build:
-            sharded_build([self], mode, hw, hh, self._comm, self.torch, overlap=overlap)
+            sharded_build([self], mode, hw, hh, self._comm, self.torch, overlap=overlap, before_gather=before_gather)
         else:
+            if before_gather is not None:
+                before_gather()
             self._call("psim_build_async", mode, hw, hh)
             if overlap is not None:
                 overlap()
@@ -277,6 +283,7 @@ class ShardedSimulation(Simulation):
                 ev.append(e)
 
         mark()
+        pending_vel = None
         C("psim_reset_acc")
         cell = self.step_cell_size(bool(getattr(p, "do_polar", 0)))  # what psim_step uses: same addition order
         do_cells = bool(p.do_short_range and cell > 0.0)
@@ -294,11 +301,16 @@ class ShardedSimulation(Simulation):
             C("psim_iterate", p.dt, p.damping_base, p.hw, p.hh, p.hd, int(p.enable_out_of_plane))
             v = self._views()
             all_gather_slices(v["pqr"], self.wb, self.rank, self.world, self.dist, self._scratch_b)
-            all_gather_slices(v["velz"], self.wb, self.rank, self.world, self.dist, self._scratch_b)
+            # the velocities are not needed before the next build permutes the bodies: their all-gather runs
+            # behind that build's first two phases (bins, own keys + sort), which only read positions
+            self._scratch_v.copy_(v["velz"][self.rank * self.wb:(self.rank + 1) * self.wb])
+            pending_vel = self.dist.all_gather_into_tensor(v["velz"][:self.world * self.wb], self._scratch_v,
+                                                           async_op=True)
             C("psim_mark_positions_changed")
         mark()
+        wait_vel = (lambda: pending_vel.wait()) if pending_vel is not None else None
         if p.do_electrons:
-            self._build(_lib.BUILD_DOMAIN, p.hw, p.hh)
+            self._build(_lib.BUILD_DOMAIN, p.hw, p.hh, before_gather=wait_vel)
             mark()
             C("psim_update_electrons", p.bg_x, p.bg_y, p.dt, p.k_e)
             if self.we:
@@ -306,6 +318,8 @@ class ShardedSimulation(Simulation):
                 all_gather_slices(v["erel"], self.we, self.rank, self.world, self.dist, self._scratch_e)
                 all_gather_slices(v["evel"], self.we, self.rank, self.world, self.dist, self._scratch_e)
         else:
+            if wait_vel is not None:
+                wait_vel()
             mark()
         mark()
         self._events = ev
