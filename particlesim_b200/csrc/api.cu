@@ -373,13 +373,6 @@ __global__ void __launch_bounds__(256) reset_acc_kernel(float4* accm, uint32_t n
   }
 }
 
-__global__ void __launch_bounds__(256) csr_offsets_kernel(const uint32_t* cell_start, const uint32_t* cell_end,
-                                                         uint64_t ncells, uint32_t* counts) {
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += stride)
-    counts[c] = cell_end[c] - cell_start[c];
-}
-
 struct U32Fn {
   const uint32_t* v;
   __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return v[i]; }
@@ -559,7 +552,6 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
     return PSIM_OK;
   }
   BodyArrays& in = ctx->b[ctx->cur];
-  BodyArrays& out = ctx->b[ctx->cur ^ 1];
   int nb = 1;
   if (mode == PSIM_BUILD_CONTAINING) {
     nb = grid_for(ctx, n, 256, 4);

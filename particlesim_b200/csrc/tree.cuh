@@ -250,18 +250,6 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-__global__ void __launch_bounds__(256)
-    finalize_nodes_kernel(const TreeMeta* __restrict__ meta, const float4* __restrict__ pqr,
-                          const float4* __restrict__ accm, TreeArrays t) {
-  const uint32_t M = meta->num_nodes;
-  if (M > t.node_cap) return;
-  const float root_size = meta->root.size;
-  const uint32_t n_bodies = meta->n;
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t node = blockIdx.x * blockDim.x + threadIdx.x; node < M; node += stride)
-    finalize_node(node, root_size, pqr, accm, t, SubtreeEndLocal{M, n_bodies, t.nodeB});
-}
-
 // psim_download_nodes only: the export sweep visits EVERY internal node level by level, so the buckets are
 // rebuilt to hold them all (the build only buckets the cells its level sweeps visit)
 __global__ void __launch_bounds__(256)

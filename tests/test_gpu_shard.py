@@ -127,3 +127,31 @@ def test_sharded_steps_equal_single_gpu_steps(cuda_device):
             assert np.array_equal(getattr(s.bodies, k), getattr(one.bodies, k)), k
         s.close()
     one.close()
+
+
+def test_sharded_build_at_scale(cuda_device):
+    """BASELINE config 3 size (4 M, clustered: deep unbalanced tree, uneven bins), 5 ranks on one GPU: the
+    pieces must concatenate into the single-GPU traversal tree and give the same field, bit for bit"""
+    import torch
+    from particlesim_b200.parallel import LoopbackComm, sharded_build
+    bodies = clustered(4_000_000)
+    hw, hh = np.float32(bodies["hw"]), np.float32(bodies["hh"])
+    one = make_sim(bodies)
+    one._call("psim_shard_init", 0, 1)
+    one.rank, one.world, one._shard_nb = 0, 1, len(bodies["pos"])
+    one._call("psim_build", 0, hw, hh)
+    ref_perm, ref_e = perm_of(one), field_of(one)
+    sims = make_ranks(bodies, 5)
+    body_lo, trav_lo = sharded_build(sims, 0, hw, hh, LoopbackComm(), torch)
+    counts = np.diff(body_lo.astype(np.int64))
+    assert counts.sum() == len(bodies["pos"]) and counts.max() <= 1.3 * counts.mean(), counts
+    T = int(trav_lo[-1])
+    refA, refB = trav(one, T)
+    for s in sims[::2]:
+        assert np.array_equal(perm_of(s), ref_perm)
+        a, b = trav(s, T)
+        assert np.array_equal(a, refA) and np.array_equal(b, refB)
+        assert np.array_equal(field_of(s).view(np.uint32), ref_e.view(np.uint32))
+    for s in sims:
+        s.close()
+    one.close()
