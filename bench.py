@@ -453,7 +453,8 @@ def main():
                     help="1: traversal with IEEE div/sqrt and no FMA contraction (parity_mode 1) instead of the default "
                          "MUFU rsqrt/rcp arithmetic (parity_mode 0); both sum the reference's interaction sets and "
                          "both are tested against the oracle at the 1e-5 tolerance")
-    ap.add_argument("--cpu-n", type=int, default=1_000_000, help="bodies in the CPU-baseline sample")
+    ap.add_argument("--cpu-n", type=int, default=8_000_000,
+                    help="bodies in the CPU-baseline sample (one step of 8 M bodies is 10-20 s of work on 16 cores)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--replicated-build", action="store_true",
                     help="multi-GPU: every rank builds the whole tree (the v1 scheme) instead of its key range")
