@@ -96,6 +96,7 @@ struct psim_ctx {
   // sharded build (shard.cuh): allocated by psim_shard_init
   struct Shard {
     bool on = false;
+    bool tree_is_sharded = false;  // the node array holds this rank's piece only
     uint32_t rank = 0, world = 1;
     int phase = 0, mode = 0;
     uint32_t halo = 0, n_local = 0, hl = 0, L = 0, s_lo = 0;
@@ -541,6 +542,7 @@ int32_t gather_stage(psim_ctx* ctx, const uint32_t* idx0, const uint32_t* idx1, 
 int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
   const uint32_t n = ctx->n;
   cudaStream_t st = ctx->stream;
+  ctx->sh.tree_is_sharded = false;
   ctx->tree_valid = false;
   ctx->perm_valid = false;
   ctx->host_map_valid = false;
@@ -637,6 +639,8 @@ int32_t shard_phase(psim_ctx* ctx, int phase, int mode, float hw, float hh, uint
   auto& S = ctx->sh;
   if (!S.on) return fail(ctx, PSIM_E_STATE, "psim_shard_phase: call psim_shard_init first");
   if (ctx->cfg.strict_centres) return fail(ctx, PSIM_E_ARG, "sharded build: strict_centres is a single-GPU parity switch");
+  if (ctx->cfg.parity_mode == 2)
+    return fail(ctx, PSIM_E_ARG, "sharded build: parity_mode 2 walks the whole node array, which only a single-GPU build has");
   if (phase != 0 && phase != S.phase) return fail(ctx, PSIM_E_STATE, "psim_shard_phase: phases must run in order");
   const uint32_t n = ctx->n;
   cudaStream_t st = ctx->stream;
@@ -647,6 +651,7 @@ int32_t shard_phase(psim_ctx* ctx, int phase, int mode, float hw, float hh, uint
   switch (phase) {
     case 0: {
       ctx->tree_valid = ctx->perm_valid = ctx->host_map_valid = ctx->grid_valid = false;
+      S.tree_is_sharded = true;
       S.mode = mode;
       BodyArrays& in = ctx->b[ctx->cur];
       int nb = 1;
@@ -833,6 +838,8 @@ int32_t cell_build_async(psim_ctx* ctx, float hw, float hh, float cell_size) {
 
 int32_t field_async(psim_ctx* ctx, float k_e, float bg_x, float bg_y, int write_acc) {
   if (!ctx->tree_valid) return fail(ctx, PSIM_E_STATE, "psim_field: no tree (call psim_build first)");
+  if (ctx->cfg.parity_mode == 2 && ctx->sh.tree_is_sharded)
+    return fail(ctx, PSIM_E_STATE, "psim_field: parity_mode 2 needs the whole node array (the last build was sharded)");
   const uint32_t n = ctx->n;
   if (n == 0) return PSIM_OK;
   BodyArrays& b = ctx->b[ctx->cur];
@@ -865,6 +872,8 @@ int32_t field_async(psim_ctx* ctx, float k_e, float bg_x, float bg_y, int write_
 int32_t points_async(psim_ctx* ctx, const float2* pts, const float* q, const float* radius, uint32_t m,
                      float k_e, float2* out, uint32_t first = 0) {
   if (!ctx->tree_valid) return fail(ctx, PSIM_E_STATE, "acc_pos: no tree (call psim_build first)");
+  if (ctx->cfg.parity_mode == 2 && ctx->sh.tree_is_sharded)
+    return fail(ctx, PSIM_E_STATE, "acc_pos: parity_mode 2 needs the whole node array (the last build was sharded)");
   if (m == 0) return PSIM_OK;
   BodyArrays& b = ctx->b[ctx->cur];
   const FieldParams P = field_params(ctx, k_e, 0.f, 0.f);
@@ -1472,6 +1481,7 @@ int32_t psim_get_permutation(psim_ctx* ctx, uint32_t* out) {
 int32_t psim_get_keys(psim_ctx* ctx, uint64_t* out) {
   if (!ctx || !out) return PSIM_E_ARG;
   if (!ctx->perm_valid && ctx->n) return fail(ctx, PSIM_E_STATE, "psim_get_keys: no build since the last upload");
+  if (ctx->sh.tree_is_sharded) return fail(ctx, PSIM_E_STATE, "psim_get_keys: the last build was sharded (each rank holds its own keys only)");
   if (!ctx->n) return PSIM_OK;
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaMemcpy(out, ctx->keys[1], (size_t)ctx->n * 8, cudaMemcpyDeviceToHost));
@@ -1481,6 +1491,8 @@ int32_t psim_get_keys(psim_ctx* ctx, uint64_t* out) {
 int32_t psim_download_nodes(psim_ctx* ctx, psim_node* out, uint64_t cap, uint64_t* count) {
   if (!ctx) return PSIM_E_ARG;
   if (!ctx->perm_valid && ctx->n) return fail(ctx, PSIM_E_STATE, "psim_download_nodes: no tree");
+  if (ctx->sh.tree_is_sharded)
+    return fail(ctx, PSIM_E_STATE, "psim_download_nodes: the last build was sharded (each rank holds its piece of the node array only)");
   if (count) *count = 0;
   if (ctx->n == 0) return PSIM_OK;
   int32_t rc = fetch_meta(ctx);
