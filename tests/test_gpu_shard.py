@@ -155,3 +155,36 @@ def test_sharded_build_at_scale(cuda_device):
     for s in sims:
         s.close()
     one.close()
+
+
+def test_sharded_tree_refuses_whole_array_calls(cuda_device):
+    """after a sharded build a context holds its own piece of the node array only: the export, the key
+    download and the reference-order walk (parity_mode 2) must say so instead of reading garbage"""
+    import torch
+    from particlesim_b200 import PsimError
+    from particlesim_b200.parallel import LoopbackComm, sharded_build
+    bodies = uniform_pm1(5000)
+    sims = make_ranks(bodies, 2)
+    sharded_build(sims, 0, np.float32(0), np.float32(0), LoopbackComm(), torch)
+    s = sims[0]
+    keys = np.zeros(5000, np.uint64)
+    with pytest.raises(PsimError) as e:
+        s._call("psim_get_keys", keys.ctypes.data)
+    assert e.value.code == -5
+    with pytest.raises(PsimError) as e:
+        _ = s.quadtree.nodes
+    assert e.value.code == -5
+    s._cfg.parity_mode = 2
+    s._call("psim_set_config", __import__("ctypes").byref(s._cfg))
+    with pytest.raises(PsimError) as e:
+        field_of(s)
+    assert e.value.code == -5
+    with pytest.raises(PsimError) as e:   # and a sharded build itself refuses that mode
+        sharded_build(sims[:1] + sims[1:], 0, np.float32(0), np.float32(0), LoopbackComm(), torch)
+    assert e.value.code == -2
+    # a plain build on the same context makes everything available again
+    s._call("psim_build", 0, np.float32(0), np.float32(0))
+    s._call("psim_get_keys", keys.ctypes.data)
+    assert np.all(keys[:-1] <= keys[1:])
+    for x in sims:
+        x.close()
