@@ -24,40 +24,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "shard_logic.cuh"
 #include "sort.cuh"
 #include "tree.cuh"
 
 namespace psim {
-
-constexpr int kShardDepth = 8;
-constexpr uint32_t kBins = 1u << (2 * kShardDepth);
-constexpr uint32_t kTopSlots = ((1u << (2 * (kShardDepth + 1))) - 1u) / 3u;  // cells of depth 0..8
-constexpr int kMaxRanks = 64;
-constexpr uint32_t kHaloMax = 2050;  // >= effective leaf capacity + 1
-
-PSIM_HD uint32_t top_base(int d) { return ((1u << (2 * d)) - 1u) / 3u; }
-PSIM_HD uint32_t top_slot(int d, uint64_t key) { return top_base(d) + (d ? (uint32_t)(key >> (64 - 2 * d)) : 0u); }
-
-struct TopRec {  // 40 bytes = 5 u64 words: exactly one rank writes a slot, the others leave zeros
-  NodeRec r;
-  uint32_t node;   // global pre-order index
-  uint32_t state;  // 0 absent, 1 complete, 2 internal above the bins, 3 internal bin (complete after the local sweep)
-};
-constexpr uint32_t kTopAbsent = 0, kTopComplete = 1, kTopInternal = 2, kTopBin = 3, kTopComputed = 4;
-
-struct ShardPlan {       // device + host copy
-  uint32_t bin_lo[kMaxRanks + 1];
-  uint32_t body_lo[kMaxRanks + 1];
-};
-
-struct ShardMeta {  // device side, one per context
-  uint32_t rank, world;
-  uint32_t n_local, hl, L;  // local bodies, left halo length, hl + n_local + hr
-  uint32_t body_base;       // global body index of local array slot 0
-  uint32_t node_off, M_local, M_total;
-  uint32_t trav_off, T_local, T_total;
-  uint32_t node_lo[kMaxRanks + 1], trav_lo[kMaxRanks + 1];
-};
 
 // ---- replicated: shard bin (first 8 key levels) of all bodies + bin histogram ----------------------
 __global__ void __launch_bounds__(256)
@@ -381,30 +352,9 @@ __global__ void __launch_bounds__(256)
 
 // after the all-reduce: the cells above the bins, one launch per level, deepest level first
 __global__ void __launch_bounds__(256) heap_sweep_kernel(TopRec* __restrict__ heap, int d) {
-  {
-    const uint32_t cells = 1u << (2 * d);
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < cells; p += gridDim.x * blockDim.x) {
-      TopRec* me = &heap[top_base(d) + p];
-      if (me->state != kTopInternal) continue;
-      double aq = 0.0, aqx = 0.0, aqy = 0.0;
-      float charge = 0.0f;
-      uint32_t next = 0;
-      for (uint32_t q = 0; q < 4; ++q) {
-        const TopRec* c = &heap[top_base(d + 1) + 4 * p + q];
-        if (c->state == kTopAbsent) continue;
-        charge = f_add(charge, c->r.charge);
-        aq += c->r.aq, aqx += c->r.aqx, aqy += c->r.aqy;
-        next = c->r.next & kNextMask;
-      }
-      bool last = true;  // no later sibling under my parent
-      if (d > 0)
-        for (uint32_t q = (p & 3u) + 1; q < 4; ++q)
-          if (heap[top_base(d) + (p & ~3u) + q].state != kTopAbsent) last = false;
-      me->r.aq = aq, me->r.aqx = aqx, me->r.aqy = aqy, me->r.charge = charge;
-      me->r.next = next | (last ? kLastSibling : 0u);
-      me->state = kTopComputed;
-    }
-  }
+  const uint32_t cells = 1u << (2 * d);
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < cells; p += gridDim.x * blockDim.x)
+    heap_sweep_cell(heap, d, p);
 }
 
 __global__ void __launch_bounds__(256)
@@ -418,21 +368,6 @@ __global__ void __launch_bounds__(256)
     if (h.r.aq > 0.0) t.ndepth[h.node - noff] |= (uint8_t)kDepthCharged;
   }
 }
-
-struct SubtreeEndShard {  // the subtree ends where a remote node starts: at a bin boundary
-  uint32_t node_lo, node_hi, M, n_bodies, body_base;
-  const uint4* nodeB;  // pre-offset
-  const uint64_t* lkeys;
-  const uint32_t* binprefix;
-  __device__ __forceinline__ uint32_t operator()(uint32_t c, const uint4& nb) const {
-    if (c >= M) return n_bodies;
-    if (c < node_hi) return nodeB[c].y;
-    const int d = (int)(nb.w & kNodeDepthMask), de = d < kShardDepth ? d : kShardDepth;
-    const uint64_t key = lkeys[nb.y - body_base];
-    const uint32_t prefix = de ? (uint32_t)(key >> (64 - 2 * de)) : 0u;
-    return binprefix[(prefix + 1u) << (2 * (kShardDepth - de))];
-  }
-};
 
 __global__ void __launch_bounds__(256)
     finalize_nodes_shard_kernel(const TreeMeta* __restrict__ meta, const ShardMeta* __restrict__ sm,

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../particlesim_b200/csrc/tree_logic.cuh"
+#include "../../particlesim_b200/csrc/shard_logic.cuh"
 
 using namespace psim;
 
@@ -234,6 +235,238 @@ void emu_walk(void* h, uint32_t m, const float* pts_xy, const float* q, const fl
   }
   if (warp_steps) *warp_steps = steps;
   if (pairs) *pairs = P;
+}
+
+// ---- serial replay of a `world`-rank sharded build (csrc/shard.cuh) on the sorted bodies
+// of the last emu_build: bin-aligned key ranges, virtual halo keys, per-bin tables, top heap, per-rank
+// compaction.  The device kernels' glue is restated here; the per-body / per-node logic is the shared
+// host+device code.  out[0..7] = mismatches against the single build: nodeA, nodeB, rec, ndepth (per
+// node), sentinel depths, heap slots with more than one writer, travA, travB.  Returns the node total.
+struct HostShardSink {
+  static constexpr bool kTop = true;
+  TopRec* heap;
+  uint32_t* multi_writer;
+  uint32_t level_slot(int) { return 0; }  // the level buckets are collected from the (lambda, ell) levels
+  void local_node(int, uint32_t) {}
+  void zero_leaf() {}
+  void cap_leaf() {}
+  void top_leaf(int d, uint64_t key, uint32_t node, const NodeRec& r) {
+    TopRec& h = heap[top_slot(d, key)];
+    if (h.state != kTopAbsent) ++*multi_writer;
+    h.r = r, h.node = node, h.state = kTopComplete;
+  }
+  void top_internal(int d, uint64_t key, uint32_t node) {
+    TopRec& h = heap[top_slot(d, key)];
+    if (h.state != kTopAbsent) ++*multi_writer;
+    h.node = node, h.state = d == kShardDepth ? kTopBin : kTopInternal;
+  }
+};
+
+uint32_t emu_shard_check(void* hd, uint32_t world, uint32_t leaf_capacity, uint32_t thread_capacity, uint64_t* out) {
+  Emu& e = *static_cast<Emu*>(hd);
+  for (int k = 0; k < 8; ++k) out[k] = 0;
+  const uint32_t n = e.n;
+  if (n == 0) return 0;
+  const uint32_t M = e.meta.num_nodes;
+  const uint32_t c_eff = effective_capacity(leaf_capacity, thread_capacity);
+  const int dcap = (int)e.meta.dcap;
+  const float root_size = e.meta.root.size;
+  // bins, prefix, splitters (bin_split_kernel)
+  std::vector<uint32_t> binhist(kBins, 0), binprefix(kBins + 1, 0);
+  for (uint32_t i = 0; i < n; ++i) binhist[(uint32_t)(e.keys[i] >> 48)]++;
+  for (uint32_t b = 0; b < kBins; ++b) binprefix[b + 1] = binprefix[b] + binhist[b];
+  std::vector<uint32_t> bin_lo(world + 1), body_lo(world + 1);
+  for (uint32_t r = 0; r <= world; ++r) {
+    const uint64_t target = (uint64_t)n * r / world;
+    uint32_t lo = (uint32_t)(std::lower_bound(binprefix.begin(), binprefix.begin() + kBins, (uint32_t)target) - binprefix.begin());
+    if (r == 0) lo = 0;
+    if (r == world) lo = kBins;
+    bin_lo[r] = lo, body_lo[r] = binprefix[lo];
+  }
+  auto bin_of_body = [&](uint32_t g) {
+    return (uint32_t)(std::upper_bound(binprefix.begin(), binprefix.begin() + kBins + 1, g) - binprefix.begin()) - 1;
+  };
+  const uint32_t H = c_eff + 1;
+  struct Rank {
+    uint32_t s_lo, nl, hl, L, body_base, M_local, node_off, T_local, trav_off;
+    std::vector<uint64_t> lkeys;
+    std::vector<uint16_t> le;
+    std::vector<uint32_t> nodebase;
+    std::vector<std::vector<uint32_t>> buckets;
+  };
+  std::vector<Rank> R(world);
+  // phases 0-2: halo keys, levels, local node scan
+  for (uint32_t r = 0; r < world; ++r) {
+    Rank& k = R[r];
+    k.s_lo = body_lo[r], k.nl = body_lo[r + 1] - body_lo[r];
+    k.hl = std::min(k.s_lo, H);
+    const uint32_t after = n - body_lo[r + 1];
+    k.L = k.hl + k.nl + std::min(after, H);
+    k.body_base = k.s_lo - k.hl;
+    k.lkeys.resize(k.L), k.le.assign(k.L, 1), k.nodebase.assign(k.L + 1, 0);
+    for (uint32_t a = 0; a < k.L; ++a) {
+      const bool local = a >= k.hl && a < k.hl + k.nl;
+      k.lkeys[a] = local ? e.keys[k.body_base + a] : (uint64_t)bin_of_body(k.body_base + a) << 48;
+    }
+    for (uint32_t a = k.hl; a < k.hl + k.nl; ++a)
+      k.le[a] = body_levels(k.lkeys.data(), e.pqr.data() + k.body_base, k.L, a, c_eff, dcap);
+    uint32_t run = 0;
+    for (uint32_t a = 0; a < k.L; ++a) k.nodebase[a] = run, run += le_nodes(k.le[a]);
+    k.nodebase[k.L] = run;
+    k.M_local = run;
+  }
+  // table 1 + offsets (table_nodes_kernel, resolve_table_kernel)
+  uint32_t off = 0;
+  for (uint32_t r = 0; r < world; ++r) R[r].node_off = off, off += R[r].M_local;
+  const uint32_t M_total = off;
+  auto owner_of = [&](uint32_t b) {
+    uint32_t o = 0;
+    while (o + 1 < world && bin_lo[o + 1] <= b) ++o;
+    return o;
+  };
+  std::vector<uint32_t> nb_bin(kBins + 1, M_total);
+  for (uint32_t b = 0; b < kBins; ++b) {
+    const uint32_t g = binprefix[b];
+    if (g >= n) continue;
+    const uint32_t bb = binhist[b] ? b : bin_of_body(g);
+    const Rank& k = R[owner_of(bb)];
+    nb_bin[b] = k.node_off + k.nodebase[binprefix[bb] - k.body_base];
+  }
+  // global arrays every rank writes its own index range of
+  std::vector<float4> nodeA(M_total, make_float4(0, 0, 0, 0));
+  std::vector<uint4> nodeB(M_total, make_uint4(0, 0, 0, 0));
+  std::vector<NodeRec> rec(M_total, NodeRec{0, 0, 0, 0.f, 0});
+  std::vector<uint8_t> ndepth(M_total + 1, 0);
+  std::vector<uint32_t> dummy_levels(1);
+  TreeArrays t{nodeA.data(), nodeB.data(), rec.data(), ndepth.data(), nullptr, nullptr, nullptr, nullptr, nullptr, M_total};
+  std::vector<TopRec> heap(kTopSlots);
+  memset(heap.data(), 0, heap.size() * sizeof(TopRec));
+  uint32_t multi_writer = 0;
+  // phase 3: globalize nodebase, emit
+  std::vector<uint8_t> sentinel(world, 0);
+  for (uint32_t r = 0; r < world; ++r) {
+    Rank& k = R[r];
+    for (uint32_t a = k.hl; a < k.hl + k.nl; ++a) k.nodebase[a] += k.node_off;
+    for (uint32_t a = k.hl + k.nl; a < k.L; ++a) k.nodebase[a] = nb_bin[(uint32_t)(k.lkeys[a] >> 48)];
+    if (k.nl > 0 && k.hl + k.nl < k.L) sentinel[r] = (uint8_t)(lcp_levels(k.lkeys[k.hl + k.nl - 1], k.lkeys[k.hl + k.nl]) + 1);
+    k.buckets.assign(kLevels, {});
+    for (uint32_t a = k.hl; a < k.hl + k.nl; ++a) {
+      const int lam = le_lambda(k.le[a]), ell = le_ell(k.le[a]);
+      for (int d = lam + 1; d < ell; ++d)
+        if (d >= kShardDepth) k.buckets[d].push_back(k.nodebase[a] + (uint32_t)(d - lam - 1));
+    }
+    HostShardSink sink{heap.data(), &multi_writer};
+    TreeArrays te = t;
+    te.level_nodes = dummy_levels.data();
+    for (uint32_t a = k.hl; a < k.hl + k.nl; ++a)
+      emit_nodes_for_body(k.lkeys.data(), k.L, a, k.le[a], k.nodebase.data(), M_total, e.pqr.data() + k.body_base,
+                          (const float4*)nullptr, leaf_capacity, thread_capacity, root_size, dcap, te, sink,
+                          k.body_base, kShardDepth);
+  }
+  out[5] = multi_writer;
+  // The sentinel depth must be the real depth of the first node after the rank's piece whenever a local
+  // sweep can read it, i.e. when the last local body sits in a leaf of its own rank (a leaf that straddles
+  // the boundary lies above the bins: no cell of the local sweeps ends there, the heap handles it).
+  for (uint32_t r = 0; r < world; ++r) {
+    const Rank& k = R[r];
+    const uint32_t first_remote = k.node_off + k.M_local;
+    if (k.nl == 0 || first_remote >= M_total || k.hl + k.nl >= k.L) continue;
+    const uint32_t last = k.hl + k.nl - 1;
+    uint32_t head = last;  // the body that starts the last local body's leaf
+    while (head > k.hl && !(le_lambda(k.le[head]) < le_ell(k.le[head]))) --head;
+    const bool own_leaf = le_ell(k.le[head]) > lcp_levels(k.lkeys[last], k.lkeys[last + 1]);
+    if (own_leaf && sentinel[r] != (ndepth[first_remote] & kDepthMask8)) out[4]++;
+  }
+  // local sweeps (levels >= kShardDepth), owned internal bins into the heap
+  for (uint32_t r = 0; r < world; ++r)
+    for (int level = kMaxLevels - 1; level >= kShardDepth; --level)
+      for (uint32_t node : R[r].buckets[level]) aggregate_node_lean(node, level, M_total, t);
+  for (uint32_t b = 0; b < kBins; ++b) {
+    TopRec& hslot = heap[top_base(kShardDepth) + b];
+    if (hslot.state == kTopBin) hslot.r = rec[hslot.node], hslot.state = kTopComplete;
+  }
+  // phase 4: heap sweep, write-back, finalize
+  for (int d = kShardDepth - 1; d >= 0; --d)
+    for (uint32_t p = 0; p < (1u << (2 * d)); ++p) heap_sweep_cell(heap.data(), d, p);
+  for (uint32_t s = 0; s < top_base(kShardDepth); ++s)
+    if (heap[s].state == kTopComputed) {
+      rec[heap[s].node] = heap[s].r;
+      if (heap[s].r.aq > 0.0) ndepth[heap[s].node] |= (uint8_t)kDepthCharged;
+    }
+  for (uint32_t r = 0; r < world; ++r) {
+    const Rank& k = R[r];
+    const SubtreeEndShard end{k.node_off, k.node_off + k.M_local, M_total, n, k.body_base, nodeB.data(), k.lkeys.data(),
+                              binprefix.data()};
+    for (uint32_t node = k.node_off; node < k.node_off + k.M_local; ++node)
+      finalize_node(node, root_size, e.pqr.data(), e.accm.data(), t, end);
+  }
+  // compare with the single build
+  if (M_total != M) out[0] = out[1] = out[2] = out[3] = 1u << 30;
+  for (uint32_t i = 0; i < M && i < M_total; ++i) {
+    const bool leaf = (e.nodeB[i].w & kNodeLeaf) != 0;
+    // (the single emulation also ran the export sweep, which gives chargeless internal cells their mass /
+    // centroid centre; the build leaves those at (0, 0) and no field sum ever reads them)
+    if ((leaf || e.rec[i].aq > 0.0) && memcmp(&nodeA[i], &e.nodeA[i], sizeof(float4)) != 0) out[0]++;
+    const uint4 a = nodeB[i], b = e.nodeB[i];
+    if (a.x != b.x || a.y != b.y || a.w != b.w || (leaf && a.z != b.z)) out[1]++;
+    const NodeRec &ra = rec[i], &rb = e.rec[i];
+    if (ra.aq != rb.aq || ra.aqx != rb.aqx || ra.aqy != rb.aqy || memcmp(&ra.charge, &rb.charge, 4) != 0 ||
+        (ra.next & kNextMask) != (rb.next & kNextMask))
+      out[2]++;
+    if (ndepth[i] != e.ndepth[i]) out[3]++;
+  }
+  // phase 5: per-rank compaction with the traversal table, against a plain compaction of the single tree
+  std::vector<uint32_t> rank_single(M + 1, 0);
+  for (uint32_t i = 0; i < M; ++i) rank_single[i + 1] = rank_single[i] + (e.ndepth[i] >> 7);
+  const uint32_t T = rank_single[M];
+  std::vector<float4> sA(T);
+  std::vector<uint4> sB(T);
+  for (uint32_t i = 0; i < M; ++i)
+    if (e.nodeB[i].w & kNodeCharged) {
+      uint4 nb = e.nodeB[i];
+      nb.x = nb.x < M ? rank_single[nb.x] : T;
+      if (!(nb.w & kNodeLeaf)) nb.z = 0;
+      sA[rank_single[i]] = e.nodeA[i], sB[rank_single[i]] = nb;
+    }
+  std::vector<std::vector<uint32_t>> lrank(world);
+  uint32_t toff = 0;
+  for (uint32_t r = 0; r < world; ++r) {
+    Rank& k = R[r];
+    lrank[r].assign(k.M_local + 1, 0);
+    for (uint32_t j = 0; j < k.M_local; ++j) lrank[r][j + 1] = lrank[r][j] + (ndepth[k.node_off + j] >> 7);
+    k.T_local = lrank[r][k.M_local], k.trav_off = toff, toff += k.T_local;
+  }
+  const uint32_t T_total = toff;
+  std::vector<uint32_t> trav_bin(kBins + 1, T_total);
+  for (uint32_t b = 0; b < kBins; ++b) {
+    const uint32_t g = binprefix[b];
+    if (g >= n) continue;
+    const uint32_t bb = binhist[b] ? b : bin_of_body(g);
+    const uint32_t o = owner_of(bb);
+    const uint32_t j = nb_bin[bb] - R[o].node_off;
+    trav_bin[b] = R[o].trav_off + (j < R[o].M_local ? lrank[o][j] : R[o].T_local);
+  }
+  if (T_total != T) out[6] = out[7] = 1u << 30;
+  std::vector<float4> dA(T_total);
+  std::vector<uint4> dB(T_total);
+  for (uint32_t r = 0; r < world; ++r) {
+    const Rank& k = R[r];
+    for (uint32_t j = 0; j < k.M_local; ++j) {
+      uint4 nb = nodeB[k.node_off + j];
+      if (!(nb.w & kNodeCharged)) continue;
+      const uint32_t x = nb.x;
+      if (x >= M_total) nb.x = T_total;
+      else if (x - k.node_off < k.M_local) nb.x = k.trav_off + lrank[r][x - k.node_off];
+      else nb.x = trav_bin[(uint32_t)(std::lower_bound(nb_bin.begin(), nb_bin.begin() + kBins, x) - nb_bin.begin())];
+      const uint32_t rr = k.trav_off + lrank[r][j];
+      dA[rr] = nodeA[k.node_off + j], dB[rr] = nb;
+    }
+  }
+  for (uint32_t i = 0; i < T && i < T_total; ++i) {
+    if (memcmp(&dA[i], &sA[i], sizeof(float4)) != 0) out[6]++;
+    if (memcmp(&dB[i], &sB[i], sizeof(uint4)) != 0) out[7]++;
+  }
+  return M_total;
 }
 
 void emu_sorted_bodies(void* h, float* pqr_out) {

@@ -245,12 +245,22 @@ class Emu:
         L.emu_set_params.argtypes = [C.c_void_p, C.c_float, C.c_float]
         L.emu_walk.argtypes = [C.c_void_p, C.c_uint32, pf, pf, pf, C.c_float, pf, C.c_void_p, C.c_void_p]
         L.emu_sorted_bodies.argtypes = [C.c_void_p, C.c_void_p]
+        L.emu_shard_check.restype = C.c_uint32
+        L.emu_shard_check.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         self.h = L.emu_create()
 
     def __del__(self):
         if getattr(self, "h", None):
             self.lib.emu_destroy(self.h)
             self.h = None
+
+    def shard_check(self, world, leaf=1, thread=1024):
+        """replay a `world`-rank sharded build of the last build's bodies; returns (node total, mismatch
+        counts against the single build: nodeA, nodeB, rec, ndepth, sentinel depth, multi-writer heap slots,
+        travA, travB)"""
+        out = np.zeros(8, np.uint64)
+        total = self.lib.emu_shard_check(self.h, world, leaf, thread, out.ctypes.data)
+        return int(total), out
 
     def build(self, bodies, mode=0, leaf=1, thread=1024):
         pos = np.ascontiguousarray(bodies["pos"], np.float32)

@@ -77,3 +77,18 @@ def test_degenerate_inputs():
         b["hw"] = b["hh"] = half
         emu, o, ec, oc = run(b, 1)
         assert o.max_depth() >= 25
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("gen,n,mode,leaf,thread", [
+    (uniform_pm1, 30000, 0, 1, 1024), (electrolyte, 20000, 1, 1, 1024), (clustered, 30000, 0, 1, 1024),
+    (clustered, 20000, 1, 8, 32), (clustered, 20000, 0, 16, 5), (uniform_pm1, 33, 0, 1, 1024), (uniform_pm1, 2, 1, 1, 1024)])
+def test_sharded_build_replay_equals_single_build(gen, n, mode, leaf, thread, world):
+    """The algorithm of csrc/shard.cuh replayed serially with the shared host+device logic: key ranges
+    aligned to the 65 536 top-level cells, virtual halo keys, per-bin tables, top heap, per-rank compaction
+    must concatenate into exactly the single build's arrays (the GPU tests check the kernels themselves)."""
+    emu = Emu()
+    emu.build(gen(n), mode, leaf, thread)
+    total, bad = emu.shard_check(world, leaf, thread)
+    assert total == emu.M
+    assert not bad.any(), dict(zip(["nodeA", "nodeB", "rec", "ndepth", "sentinel", "multi_writer", "travA", "travB"], bad.tolist()))
