@@ -22,7 +22,8 @@ struct HostSink {
   static constexpr bool kTop = false;
   void top_leaf(int, uint64_t, uint32_t, const NodeRec&) {}
   void top_internal(int, uint64_t, uint32_t) {}
-  void local_node(int, uint32_t) {}
+  std::vector<std::vector<uint32_t>>* local = nullptr;  // per depth: the current slab's own cells
+  void local_node(int d, uint32_t node) { (*local)[d].push_back(node); }
   TreeMeta* meta;
   uint32_t level_slot(int d) { return meta->level_start[d] + meta->level_cursor[d]++; }
   void zero_leaf() { meta->num_zero_leaves++; }
@@ -44,6 +45,7 @@ struct Emu {
   std::vector<uint8_t> ndepth;
   TreeArrays t;
   float t_sq = 1, e_sq = 4;
+  uint32_t slab = 0;  // > 0: replay the emit kernel's slabs (in-slab sums first, level sweeps for the rest)
 };
 }  // namespace
 
@@ -102,9 +104,21 @@ uint32_t emu_build(void* h, uint32_t n, const float* pos_xy, const float* mass, 
     run += le_nodes(le[i]);
     const int lam = le_lambda(le[i]), ell = le_ell(le[i]);
     if (lam < ell) {
-      for (int d = lam + 1; d < ell; ++d) e.meta.level_count[d]++;
       if ((uint32_t)ell > e.meta.max_depth) e.meta.max_depth = ell;
+      e.meta.internal_total += (uint32_t)(ell - lam - 1);
     }
+  }
+  // level buckets: every internal cell, or (slab mode, like tree_count_kernel) only those that straddle a
+  // slab boundary
+  auto straddle_of = [&](uint32_t i) {
+    if (!e.slab) return kMaxLevels + 1;
+    const uint64_t slab_end = ((uint64_t)(i / e.slab) + 1) * e.slab;
+    return slab_end < n ? lcp_levels(e.keys[i], e.keys[slab_end]) : -1;
+  };
+  for (uint32_t i = 0; i < n; ++i) {
+    const int lam = le_lambda(le[i]), ell = le_ell(le[i]), st = straddle_of(i);
+    for (int d = lam + 1; d < ell; ++d)
+      if (d <= st) e.meta.level_count[d]++;
   }
   nodebase[n] = run;
   e.meta.num_nodes = run;
@@ -120,16 +134,42 @@ uint32_t emu_build(void* h, uint32_t n, const float* pos_xy, const float* mass, 
   e.ndepth.assign(M, 0);
   e.t = TreeArrays{e.nodeA.data(), e.nodeB.data(), e.rec.data(), e.ndepth.data(), e.node_mass.data(),
                    e.parent.data(), e.sums.data(), e.level_nodes.data(), nullptr, M};
-  HostSink sink{&e.meta};
-  for (uint32_t i = 0; i < n; ++i)
-    emit_nodes_for_body(e.keys.data(), n, i, le[i], nodebase.data(), M, e.pqr.data(), e.accm.data(),
-                        leaf_capacity, thread_capacity, r.size, dcap, e.t, sink, 0, 0, kMaxLevels + 1,
-                        /*internal_ranges=*/true);
-  // build sweep, then the export sweep (parents, masses, counts, chargeless centres)
+  std::vector<std::vector<uint32_t>> local(kLevels);
+  HostSink sink{&local, &e.meta};
+  const uint32_t slab = e.slab ? e.slab : n;
+  for (uint32_t lo = 0; lo < n; lo += slab) {
+    // one emit CTA: its bodies' nodes, then the sums of the cells inside the slab, deepest level first
+    const uint32_t hi = std::min<uint64_t>(n, (uint64_t)lo + slab);
+    for (auto& v : local) v.clear();
+    for (uint32_t i = lo; i < hi; ++i)
+      emit_nodes_for_body(e.keys.data(), n, i, le[i], nodebase.data(), M, e.pqr.data(), e.accm.data(),
+                          leaf_capacity, thread_capacity, r.size, dcap, e.t, sink, 0, 0, straddle_of(i),
+                          /*internal_ranges=*/true);
+    for (int level = kLevels - 1; level >= 0; --level)
+      for (uint32_t node : local[level]) {
+        aggregate_node_ranged(node, level, e.t);
+        finalize_node(node, r.size, e.pqr.data(), e.accm.data(), e.t, SubtreeEndCount{});
+      }
+  }
+  // level sweeps over the bucketed cells, then the export sweep (parents, masses, counts, chargeless centres)
   for (int level = kMaxLevels - 1; level >= 0; --level)
-    for (uint32_t k = e.meta.level_start[level]; k < e.meta.level_start[level + 1]; ++k)
+    for (uint32_t k = e.meta.level_start[level]; k < e.meta.level_start[level + 1]; ++k) {
       aggregate_node_ranged(e.level_nodes[k], level, e.t);
-  for (uint32_t node = 0; node < M; ++node) finalize_node(node, r.size, e.pqr.data(), e.accm.data(), e.t, SubtreeEndCount{});
+      finalize_node(e.level_nodes[k], r.size, e.pqr.data(), e.accm.data(), e.t, SubtreeEndCount{});
+    }
+  e.meta.num_internal = e.meta.internal_total;
+  if (e.slab) {
+    // the export sweep visits every internal cell: rebuild the buckets to hold them all (as psim_download_nodes does)
+    for (int l = 0; l < kLevels; ++l) e.meta.level_count[l] = 0;
+    for (uint32_t node = 0; node < M; ++node)
+      if (!(e.nodeB[node].w & kNodeLeaf)) e.meta.level_count[e.nodeB[node].w & kNodeDepthMask]++;
+    level_scan(&e.meta, M);
+    for (uint32_t node = 0; node < M; ++node)
+      if (!(e.nodeB[node].w & kNodeLeaf)) {
+        const uint32_t d = e.nodeB[node].w & kNodeDepthMask;
+        e.level_nodes[e.meta.level_start[d] + e.meta.level_cursor[d]++] = node;
+      }
+  }
   if (M && (e.nodeB[0].w & kNodeLeaf)) {
     float lm = 0.f;
     if (!(e.nodeB[0].w & kNodeZeroAgg))
@@ -168,6 +208,7 @@ void emu_export_nodes(void* h, PsimNodeOut* out, uint64_t cap) {
 
 // Serial emulation of bh_walk (traverse.cuh) for groups of 32 consecutive targets: the same
 // per-lane skip index and warp-level descend vote, in the reference's arithmetic order.
+void emu_set_slab(void* h, uint32_t slab) { static_cast<Emu*>(h)->slab = slab; }
 void emu_set_params(void* h, float theta, float epsilon) {
   Emu& e = *static_cast<Emu*>(h);
   e.t_sq = theta * theta;

@@ -243,6 +243,7 @@ class Emu:
         L.emu_meta.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_export_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.emu_set_params.argtypes = [C.c_void_p, C.c_float, C.c_float]
+        L.emu_set_slab.argtypes = [C.c_void_p, C.c_uint32]
         L.emu_walk.argtypes = [C.c_void_p, C.c_uint32, pf, pf, pf, C.c_float, pf, C.c_void_p, C.c_void_p]
         L.emu_sorted_bodies.argtypes = [C.c_void_p, C.c_void_p]
         L.emu_shard_check.restype = C.c_uint32
@@ -262,7 +263,10 @@ class Emu:
         total = self.lib.emu_shard_check(self.h, world, leaf, thread, out.ctypes.data)
         return int(total), out
 
-    def build(self, bodies, mode=0, leaf=1, thread=1024):
+    def build(self, bodies, mode=0, leaf=1, thread=1024, slab=0):
+        """slab > 0 replays tree_emit_kernel's slabs: every `slab` bodies sum the cells inside their slab
+        right after emitting them, the level sweeps only see the cells that straddle a slab boundary"""
+        self.lib.emu_set_slab(self.h, slab)
         pos = np.ascontiguousarray(bodies["pos"], np.float32)
         n = len(pos)
         f = lambda k: None if bodies.get(k) is None else np.ascontiguousarray(bodies[k], np.float32)

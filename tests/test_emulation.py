@@ -8,11 +8,11 @@ from helpers import (KE, Emu, assert_same_topology, canonical_from_nodes, check_
                      electrolyte, oracle_for, rel_l2, uniform_pm1)
 
 
-def run(bodies, mode, leaf=1, thread=1024, theta=1.0, variant="hp"):
+def run(bodies, mode, leaf=1, thread=1024, theta=1.0, variant="hp", slab=0):
     emu = Emu()
     o = oracle_for(bodies, theta=theta, leaf=leaf, thread=thread, variant=variant)
     o.build() if mode == 0 else o.build_with_domain(bodies["hw"], bodies["hh"])
-    emu.build(bodies, mode, leaf, thread)
+    emu.build(bodies, mode, leaf, thread, slab)
     nodes = emu.nodes()
     check_next_pointers(nodes)
     ec, oc = canonical_from_nodes(nodes), o.canonical()
@@ -92,3 +92,20 @@ def test_sharded_build_replay_equals_single_build(gen, n, mode, leaf, thread, wo
     total, bad = emu.shard_check(world, leaf, thread)
     assert total == emu.M
     assert not bad.any(), dict(zip(["nodeA", "nodeB", "rec", "ndepth", "sentinel", "multi_writer", "travA", "travB"], bad.tolist()))
+
+
+@pytest.mark.parametrize("slab", [7, 512, 4096])
+@pytest.mark.parametrize("gen,n,mode,leaf,thread", [(uniform_pm1, 20000, 0, 1, 1024), (electrolyte, 20000, 1, 1, 1024),
+                                                    (clustered, 30000, 0, 1, 1024), (clustered, 20000, 1, 8, 32),
+                                                    (clustered, 5000, 0, 16, 5), (uniform_pm1, 3, 0, 1, 1024)])
+def test_in_slab_sums_equal_the_level_sweeps(gen, n, mode, leaf, thread, slab):
+    """tree_emit_kernel's scheme replayed serially: each slab of bodies sums the cells that lie inside it
+    right after emitting them (skip pointers and body counts of internal cells from the keys), the level
+    sweeps only visit the cells that straddle a slab boundary.  Topology, charge, mass and centres must equal
+    the oracle's exactly as with one global sweep."""
+    bodies = gen(n)
+    emu, o, ec, oc = run(bodies, mode, leaf, thread, slab=slab)
+    ref, _, rc, _ = run(bodies, mode, leaf, thread, slab=0)
+    assert np.array_equal(ec["pos"], rc["pos"]) and np.array_equal(ec["mass"], rc["mass"])
+    a, b = emu.meta(), ref.meta()
+    assert all(a[k] == b[k] for k in a if k != "root") and np.array_equal(a["root"], b["root"])
