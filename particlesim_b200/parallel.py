@@ -1,16 +1,21 @@
 """Multi-GPU hot path: one process per GPU (torch.distributed, NCCL over NVLink / NVSwitch).
 
-Every rank holds the whole body set and builds the same tree (the sort is deterministic, so all
-ranks see the same Morton order); rank r owns a CONTIGUOUS RANGE OF THE MORTON ORDER and computes
-field / short-range forces / integrator only for those targets, plus an equal slice of the bound
-electrons.  Two exchanges per step, both all-gathers issued straight on the library's device arrays:
-  after the integrator      positions+charges+radii and velocities of the owned range
-  after the electron update  electron offsets and velocities of the owned slice
-No force reduction is needed: a target's field depends only on the (replicated) source tree.
-The replicated build is the scaling limit of this scheme; a per-rank local build with a
-locally-essential-tree exchange replaces it next (multi-GPU).
+Body state is replicated; the WORK is sharded two ways:
+  targets  rank r owns a contiguous slice of the Morton order (a multiple of 64 bodies) and computes field /
+           short-range forces / integrator only for those targets, plus an equal slice of the bound
+           electrons; the owned slices are all-gathered in place on the library's device arrays after the
+           integrator (velocities behind the next build's position-only phases) and after the electron update.
+           No force reduction is needed: a target's field depends only on the read-only source tree.
+  build    rank r owns a contiguous range of the KEY order (bins of 65 536 top-level cells) and builds the
+           part of the tree that starts in it (csrc/shard.cuh, psim_shard_phase); `sharded_build` runs the
+           phases and the exchanges between them: sorted-index segments and traversal-node segments
+           (uneven all-gathers through one padded ncclAllGather each), two per-bin tables and the top heap
+           (all-reduce).  The pieces concatenate into exactly the single-GPU arrays.
+`local_build=False` keeps the first scheme (every rank builds the whole tree) for comparison.
 
-The partition helpers are pure functions so the plumbing is testable with the gloo backend on CPU.
+The partition and exchange helpers are pure functions / small classes so that the plumbing is testable with
+the gloo backend on the CPU (tests/test_parallel_cpu.py); LoopbackComm runs all ranks in one process for the
+single-GPU tests of the sharded build (tests/test_gpu_shard.py).
 """
 from __future__ import annotations
 
@@ -101,7 +106,7 @@ def all_gatherv_padded(full, offsets, rank: int, dist, stage_cache: dict):
 
 class DistComm:
     """exchanges of the sharded build over torch.distributed (NCCL on GPUs, gloo in the CPU tests); the
-    lists hold one tensor per LOCAL rank, i.e. one"""
+    lists hold one tensor per rank that lives in this process, i.e. exactly one"""
 
     def __init__(self, dist, rank: int, padded: bool = True):
         self.dist, self.rank, self.padded = dist, rank, padded
