@@ -109,3 +109,28 @@ def test_metal_z_boundaries_match_the_oracle(cuda_device):
     assert np.array_equal(sim.bodies.z, ob["z"]) and np.array_equal(sim.bodies.vz, ob["vz"])
     assert np.any(ob["z"] != np.clip(z, -2.5, 2.5))   # some body was constrained by a metal, not just by max_z
     sim.close()
+
+
+def test_oracle_matches_the_committed_fixture():
+    """tests/golden/make_golden.py 'consumers': catches silent drift of the oracle's restatement"""
+    import json
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    meta = json.load(open(os.path.join(gold, "golden.json")))["consumers"]
+    z = np.load(os.path.join(gold, "golden.npz"))
+    g = lambda k: z[f"consumers/{k}"]
+    b = dict(pos=g("pos"), radius=g("radius"), species=g("species"), mass=g("mass"), charge=g("charge"),
+             hw=meta["hw"], hh=meta["hh"])
+    o = oracle_for(b)
+    o.update_surrounded_flags(meta["hw"], meta["hh"], frame=meta["frames"][0])
+    o.set_positions(g("nudged"))
+    o.update_surrounded_flags(meta["hw"], meta["hh"], frame=meta["frames"][1])
+    flags, last_pos, last_frame = o.surrounded()
+    assert np.array_equal(flags, g("flags")) and np.array_equal(last_pos, g("last_pos"))
+    assert np.array_equal(last_frame, g("last_frame"))
+    assert 0 < flags.sum() < len(flags) and set(np.unique(last_frame)) == {10, 13}
+    o = oracle_for(b)
+    o.set_bodies(b["pos"], z=g("z0"), vz=g("vz0"), mass=b["mass"], radius=b["radius"], charge=b["charge"], species=b["species"])
+    o.enforce_metal_z_boundaries(meta["max_z"], meta["hw"], meta["hh"])
+    ob = o.get_bodies()
+    assert np.array_equal(ob["z"], g("z")) and np.array_equal(ob["vz"], g("vz"))
