@@ -49,7 +49,8 @@ def ncu_traffic(n):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the committed
     ncu --set full capture of the same workload (profiles/); null for other sizes"""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        import glob
+        t = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))[-1]))  # latest round
         if int(t["n_bodies"]) == int(n):
             return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
     except Exception:
