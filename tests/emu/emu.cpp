@@ -510,6 +510,178 @@ uint32_t emu_shard_check(void* hd, uint32_t world, uint32_t leaf_capacity, uint3
   return M_total;
 }
 
+// ---- per-target interaction signatures -----------------------------------------------------------
+// sig[3 i + 0] = sum of hash(node) over the monopoles target i accepted, [1] = sum of hash(body) over its
+// direct terms, [2] = number of internal nodes it opened.  Two walks that give equal signatures summed the
+// same interaction sets (up to a 2^-64 hash collision), whatever the order.
+static inline uint64_t mix64(uint64_t x) {
+  x += 0x9e3779b97f4a7c15ull;
+  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+  x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+  return x ^ (x >> 31);
+}
+
+// the reference-order walk (emu_walk's logic, one target at a time: the warp vote only changes which nodes
+// the WARP visits, not what a target sums)
+void emu_walk_signatures(void* h, uint32_t m, const float* pts_xy, const float* radius, uint64_t* sig) {
+  Emu& e = *static_cast<Emu*>(h);
+  const uint32_t M = e.meta.num_nodes;
+  for (uint32_t i = 0; i < m; ++i) {
+    const float px = pts_xy[2 * i], py = pts_xy[2 * i + 1], rad = radius ? radius[i] : 0.f;
+    uint64_t sa = 0, sp = 0, so = 0;
+    uint32_t n = 0;
+    while (n < M) {
+      const float4 na = e.nodeA[n];
+      const uint4 nb = e.nodeB[n];
+      const float dx = px - na.x, dy = py - na.y;
+      const float dist = sqrtf((dx * dx) + (dy * dy));
+      const float dist_adj = fmaxf(dist - rad, 0.0f);
+      if ((na.w * na.w) < ((dist_adj * dist_adj) * e.t_sq)) {
+        sa += mix64(n);
+        n = nb.x;
+      } else if (nb.w & kNodeLeaf) {
+        for (uint32_t b = nb.y; b < nb.y + nb.z; ++b) {
+          const float ex = e.pqr[b].x - px, ey = e.pqr[b].y - py;
+          if ((ex * ex) + (ey * ey) < 1e-6f) continue;
+          sp += mix64(b);
+        }
+        n = nb.x;
+      } else {
+        ++so;
+        n = n + 1;
+      }
+    }
+    sig[3 * i] = sa, sig[3 * i + 1] = sp, sig[3 * i + 2] = so;
+  }
+}
+
+// Serial port of bh_group_walk (traverse.cuh): 32 consecutive targets share one walk; nodes are classified
+// against the group's bounding box with the same conservative margins, undecided nodes take the reference's
+// test per target, the ring buffer switches to last-in-first-out above kLifoAbove like the device's.
+// Fields in the reference's per-term arithmetic (the order of the additions differs from acc_pos).
+void emu_group_walk(void* h, uint32_t m, const float* pts_xy, const float* q, const float* radius, float k_e,
+                    float theta, float* out_xy, uint64_t* sig, uint64_t* stats /* [0] nodes visited, [1] lifo rounds */) {
+  Emu& e = *static_cast<Emu*>(h);
+  const uint32_t M = e.meta.num_nodes;
+  constexpr int kCap = 640, kLifo = kCap - 288;
+  const float inv_theta = 1.0f / theta;
+  const float INF = INFINITY;
+  uint64_t visited = 0, lifo_rounds = 0;
+  for (uint32_t g = 0; g < (m + 31) / 32; ++g) {
+    float px[32], py[32], rad[32], kq[32], ax[32] = {0}, ay[32] = {0};
+    uint64_t sa[32] = {0}, sp[32] = {0}, so[32] = {0};
+    uint32_t live_mask = 0;
+    float bx0 = INF, bx1 = -INF, by0 = INF, by1 = -INF, rmin = INF, rmax = -INF;
+    bool box_ok = true;
+    for (int l = 0; l < 32; ++l) {
+      const uint32_t i = g * 32 + l;
+      if (i >= m) continue;
+      live_mask |= 1u << l;
+      px[l] = pts_xy[2 * i], py[l] = pts_xy[2 * i + 1], rad[l] = radius ? radius[i] : 0.f, kq[l] = k_e * (q ? q[i] : 1.f);
+      bx0 = fminf(bx0, px[l]), bx1 = fmaxf(bx1, px[l]), by0 = fminf(by0, py[l]), by1 = fmaxf(by1, py[l]);
+      rmin = fminf(rmin, rad[l]), rmax = fmaxf(rmax, rad[l]);
+      if (!(fabsf(px[l]) < INF && fabsf(py[l]) < INF && fabsf(rad[l]) < INF)) box_ok = false;
+    }
+    if (!live_mask || !M) continue;
+    std::vector<uint32_t> st_node(kCap), st_mask(kCap);
+    st_node[0] = 0, st_mask[0] = live_mask;
+    int head = 0, size = 1;
+    while (size > 0) {
+      const bool lifo = size > kLifo;
+      const int k = lifo ? 1 : std::min(size, 32);
+      lifo_rounds += lifo;
+      uint32_t node[32], mask[32];
+      for (int l = 0; l < k; ++l) {
+        int idx = lifo ? head + size - 1 : head + l;
+        if (idx >= kCap) idx -= kCap;
+        node[l] = st_node[idx], mask[l] = st_mask[idx];
+      }
+      if (!lifo) head = (head + k) % kCap;
+      size -= k;
+      visited += k;
+      std::vector<std::pair<uint32_t, uint32_t>> push;  // (child, mask), in lane order like the device's prefix scan
+      for (int l = 0; l < k; ++l) {
+        const float4 na = e.nodeA[node[l]];
+        const uint4 nb = e.nodeB[node[l]];
+        const bool leaf = (nb.w & kNodeLeaf) != 0;
+        int cls = 0;
+        if (box_ok) {
+          const float s_t = na.w * inv_theta;
+          const float ddx = fmaxf(fmaxf(bx0 - na.x, na.x - bx1), 0.0f), ddy = fmaxf(fmaxf(by0 - na.y, na.y - by1), 0.0f);
+          const float fx = fmaxf(na.x - bx0, bx1 - na.x), fy = fmaxf(na.y - by0, by1 - na.y);
+          const float dmin2 = ddx * ddx + ddy * ddy, dmax2 = fx * fx + fy * fy;
+          const float la = s_t + rmax, lr = s_t + rmin;
+          if (dmin2 > la * la * 1.00002f) cls = 1;
+          else if (dmax2 < lr * lr * 0.99998f) cls = 2;
+        }
+        uint32_t acc_mask = 0;
+        for (int t = 0; t < 32; ++t) {
+          if (!((mask[l] >> t) & 1u)) continue;
+          const float dx = px[t] - na.x, dy = py[t] - na.y;
+          const float d_sq = (dx * dx) + (dy * dy);
+          bool acc;
+          if (cls == 1) acc = true;          // the "sure" list: no test
+          else if (cls == 2) acc = false;    // every target rejects: no test
+          else {
+            const float lim = fmaf(na.w, inv_theta, rad[t]), lim2 = lim * lim;
+            acc = d_sq > lim2 * 1.00002f;
+            if (!acc && !(d_sq < lim2 * 0.99998f)) {
+              const float dist_adj = fmaxf(sqrtf(d_sq) - rad[t], 0.0f);
+              acc = (na.w * na.w) < ((dist_adj * dist_adj) * e.t_sq);
+            }
+          }
+          if (!acc) continue;
+          acc_mask |= 1u << t;
+          sa[t] += mix64(node[l]);
+          const float dist = sqrtf(d_sq);
+          const float r_eff = fmaxf(dist, rad[t] + na.w * 0.5f);
+          const float denom = (r_eff * r_eff + e.e_sq) * r_eff;
+          const float sc = (kq[t] * na.z) / denom;
+          ax[t] += dx * sc, ay[t] += dy * sc;
+        }
+        const uint32_t rem = mask[l] & ~acc_mask;
+        if (!rem) continue;
+        if (!leaf) {
+          for (int t = 0; t < 32; ++t) so[t] += (rem >> t) & 1u;
+          for (uint32_t c = node[l] + 1; c != nb.x; c = e.nodeB[c].x) push.emplace_back(c, rem);
+        } else {
+          for (int t = 0; t < 32; ++t) {
+            if (!((rem >> t) & 1u)) continue;
+            for (uint32_t b = nb.y; b < nb.y + nb.z; ++b) {
+              const float4 s4 = e.pqr[b];
+              const float ex = s4.x - px[t], ey = s4.y - py[t];
+              if ((ex * ex) + (ey * ey) < 1e-6f) continue;
+              sp[t] += mix64(b);
+              const float bx = px[t] - s4.x, by = py[t] - s4.y;
+              const float bd = sqrtf((bx * bx) + (by * by));
+              const float r_eff = fmaxf(bd, rad[t] + s4.w);
+              const float denom = (r_eff * r_eff + e.e_sq) * r_eff;
+              const float sc = fminf((kq[t] * s4.z) / denom, 3.402823466e+38f);
+              ax[t] += bx * sc, ay[t] += by * sc;
+            }
+          }
+        }
+      }
+      for (auto& pm : push) {
+        int o2 = (head + size) % kCap;
+        if (size >= kCap) {  // the device's capacity argument says this cannot happen
+          stats[0] = ~0ull;
+          return;
+        }
+        st_node[o2] = pm.first, st_mask[o2] = pm.second;
+        ++size;
+      }
+    }
+    for (int l = 0; l < 32; ++l) {
+      const uint32_t i = g * 32 + l;
+      if (i >= m) continue;
+      out_xy[2 * i] = ax[l], out_xy[2 * i + 1] = ay[l];
+      sig[3 * i] = sa[l], sig[3 * i + 1] = sp[l], sig[3 * i + 2] = so[l];
+    }
+  }
+  stats[0] = visited, stats[1] = lifo_rounds;
+}
+
 void emu_sorted_bodies(void* h, float* pqr_out) {
   Emu& e = *static_cast<Emu*>(h);
   memcpy(pqr_out, e.pqr.data(), (size_t)e.n * 16);

@@ -246,6 +246,9 @@ class Emu:
         L.emu_set_slab.argtypes = [C.c_void_p, C.c_uint32]
         L.emu_walk.argtypes = [C.c_void_p, C.c_uint32, pf, pf, pf, C.c_float, pf, C.c_void_p, C.c_void_p]
         L.emu_sorted_bodies.argtypes = [C.c_void_p, C.c_void_p]
+        L.emu_walk_signatures.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.emu_group_walk.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_shard_check.restype = C.c_uint32
         L.emu_shard_check.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         self.h = L.emu_create()
@@ -254,6 +257,30 @@ class Emu:
         if getattr(self, "h", None):
             self.lib.emu_destroy(self.h)
             self.h = None
+
+    def walk_signatures(self, pts, radius=None, theta=1.0, epsilon=2.0):
+        """per-target interaction signatures of the reference-order walk (see emu.cpp)"""
+        pts = np.ascontiguousarray(pts, np.float32)
+        m = len(pts)
+        rad = None if radius is None else np.ascontiguousarray(radius, np.float32)
+        self.lib.emu_set_params(self.h, np.float32(theta), np.float32(epsilon))
+        sig = np.zeros((m, 3), np.uint64)
+        self.lib.emu_walk_signatures(self.h, m, pts.ctypes.data, None if rad is None else rad.ctypes.data, sig.ctypes.data)
+        return sig
+
+    def group_walk(self, pts, q=None, radius=None, k_e=KE, theta=1.0, epsilon=2.0):
+        """serial port of the device's group walk: (fields, signatures, nodes visited, lifo rounds)"""
+        pts = np.ascontiguousarray(pts, np.float32)
+        m = len(pts)
+        f = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+        q, rad = f(q), f(radius)
+        p = lambda a: None if a is None else a.ctypes.data
+        self.lib.emu_set_params(self.h, np.float32(theta), np.float32(epsilon))
+        out, sig, stats = np.zeros((m, 2), np.float32), np.zeros((m, 3), np.uint64), np.zeros(2, np.uint64)
+        self.lib.emu_group_walk(self.h, m, pts.ctypes.data, p(q), p(rad), np.float32(k_e), np.float32(theta),
+                                out.ctypes.data, sig.ctypes.data, stats.ctypes.data)
+        assert stats[0] != np.uint64(0xFFFFFFFFFFFFFFFF), "ring buffer overflow"
+        return out, sig, int(stats[0]), int(stats[1])
 
     def shard_check(self, world, leaf=1, thread=1024):
         """replay a `world`-rank sharded build of the last build's bodies; returns (node total, mismatch

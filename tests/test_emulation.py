@@ -109,3 +109,29 @@ def test_in_slab_sums_equal_the_level_sweeps(gen, n, mode, leaf, thread, slab):
     assert np.array_equal(ec["pos"], rc["pos"]) and np.array_equal(ec["mass"], rc["mass"])
     a, b = emu.meta(), ref.meta()
     assert all(a[k] == b[k] for k in a if k != "root") and np.array_equal(a["root"], b["root"])
+
+
+@pytest.mark.parametrize("gen,n,mode,theta,leaf,thread", [
+    (uniform_pm1, 20000, 0, 1.0, 1, 1024), (uniform_pm1, 20000, 0, 0.5, 1, 1024), (electrolyte, 20000, 1, 1.0, 1, 1024),
+    (clustered, 30000, 0, 1.0, 1, 1024), (clustered, 20000, 1, 0.7, 8, 32)])
+def test_group_walk_sums_exactly_the_reference_interaction_sets(gen, n, mode, theta, leaf, thread):
+    """The device's default traversal shares one walk among 32 targets and classifies nodes against the
+    group's bounding box.  Its serial port must give every target EXACTLY the interaction set of the
+    reference-order walk (hash signatures of the accepted nodes and of the direct-term bodies, number of
+    opened nodes) - the box tests only ever decide cases that are not borderline - and the same field up
+    to the order of the additions."""
+    bodies = gen(n)
+    emu = Emu()
+    emu.build(bodies, mode, leaf, thread)
+    sb = emu.sorted_bodies()
+    pts, rad = sb[:, :2], sb[:, 3]
+    ref_sig = emu.walk_signatures(pts, rad, theta=theta)
+    ref_f, _, _ = emu.walk(pts, radius=rad, theta=theta)
+    f, sig, visited, lifo = emu.group_walk(pts, radius=rad, theta=theta)
+    assert np.array_equal(sig, ref_sig)
+    assert rel_l2(f, ref_f) <= 2e-6
+    assert visited > 0
+    # electron-like sample points (radius 0, off the bodies): the self-skip rule must include the own body
+    rng = np.random.default_rng(1)
+    pts2 = (pts + rng.normal(0, 0.4, pts.shape)).astype(np.float32)
+    assert np.array_equal(emu.group_walk(pts2, theta=theta)[1], emu.walk_signatures(pts2, theta=theta))
