@@ -18,6 +18,7 @@
 #include "traverse.cuh"
 #include "neighbors.cuh"
 #include "shard.cuh"
+#include "strict.cuh"
 #include "tree.cuh"
 
 using namespace psim;
@@ -91,6 +92,8 @@ struct psim_ctx {
   uint32_t* inv = nullptr;
   bool tree_valid = false;
   bool perm_valid = false;
+  StrictArrays strict = {};  // psim_config.strict_centres scratch, allocated by the first strict build
+  bool strict_ready = false;
   SurroundState surround = {nullptr, nullptr, nullptr};  // by original body id
 
   // sharded build (shard.cuh): allocated by psim_shard_init
@@ -539,6 +542,54 @@ int32_t gather_stage(psim_ctx* ctx, const uint32_t* idx0, const uint32_t* idx1, 
   return PSIM_OK;
 }
 
+// scratch of strict.cuh, sized for the context's body capacity (grow-only, first strict build)
+int32_t ensure_strict(psim_ctx* ctx) {
+  if (ctx->strict_ready) return PSIM_OK;
+  StrictArrays& S = ctx->strict;
+  const size_t nb = ctx->cap_bodies ? ctx->cap_bodies : 1;
+  S.long_cap = (uint32_t)(nb / 256 + 1024);
+  S.item_cap = (uint32_t)(nb / 16 + nb / 256 + 1024);
+  S.blk_cap = (uint32_t)(nb / kStrictBlock + 2);
+  bool ok = true;
+  auto A = [&](auto** p, size_t cnt) {
+    if (ok && dalloc(p, cnt) != cudaSuccess) ok = false;
+  };
+  A(&S.cidx, nb + 1), A(&S.cw, nb), A(&S.chains, nb), A(&S.hist, 96), A(&S.longs, S.long_cap), A(&S.counters, 4);
+  A(&S.item_first, (size_t)S.long_cap + 1), A(&S.pblk, 3 * ((size_t)S.blk_cap + 1)), A(&S.fns, 3 * (size_t)S.item_cap);
+  if (!ok) {
+    cudaGetLastError();
+    return fail(ctx, PSIM_E_OOM, "strict_centres scratch");
+  }
+  ctx->strict_ready = true;
+  return PSIM_OK;
+}
+
+// psim_config.strict_centres: overwrite the centres of all charged internal nodes with the reference's
+// serial f32 sums (strict.cuh); runs after the tree is complete and before the traversal compaction
+int32_t strict_stage(psim_ctx* ctx) {
+  const int32_t rc = ensure_strict(ctx);
+  if (rc) return rc;
+  const uint32_t n = ctx->n;
+  cudaStream_t st = ctx->stream;
+  BodyArrays& b = ctx->b[ctx->cur];
+  StrictArrays& S = ctx->strict;
+  CK(exclusive_scan(ChargedBodyFn{b.pqr}, n, S.cidx, ctx->scan_partials, S.cidx + n, st));
+  strict_addends_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(b.pqr, n, S.cidx, S.cw, S.hist, S.counters);
+  strict_chain_count_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(n, ctx->le, ctx->nodebase, ctx->meta, ctx->t,
+                                                                       S.cidx, S.hist);
+  const uint32_t per_block = 2048;
+  strict_chain_scatter_kernel<<<(n + per_block - 1) / per_block, 256, 0, st>>>(n, per_block, ctx->le, ctx->nodebase,
+                                                                               ctx->meta, ctx->t, S.cidx, S.hist, S.chains);
+  strict_chain_kernel<<<grid_for(ctx, n, 128, 16), 128, 0, st>>>(ctx->le, ctx->nodebase, ctx->meta, ctx->t, S);
+  strict_blocksum_kernel<<<grid_for(ctx, (uint64_t)n / 16 + 1, 256, 8), 256, 0, st>>>(S.cw, S.cidx + n, S.blk_cap, S.pblk);
+  strict_long_setup_kernel<<<1, 1024, 0, st>>>(S.cidx + n, S);
+  strict_blockfn_kernel<<<grid_for(ctx, (uint64_t)n / 16 + 1, 128, 16), 128, 0, st>>>(S);
+  strict_compose_kernel<<<ctx->sm_count * 4, 96, 0, st>>>(ctx->meta, ctx->t, S);
+  strict_slow_kernel<<<grid_for(ctx, (uint64_t)n * 2, 128, 16), 128, 0, st>>>(ctx->meta, b.pqr, b.accm, ctx->t, S.counters);
+  ctx->launches += 12;
+  return PSIM_OK;
+}
+
 int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
   const uint32_t n = ctx->n;
   cudaStream_t st = ctx->stream;
@@ -607,8 +658,8 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
     LAUNCHED(ctx);
   }
   if (ctx->cfg.strict_centres) {
-    strict_centres_kernel<<<grid_for(ctx, n, 128, 16), 128, 0, st>>>(ctx->meta, b.pqr, b.accm, ctx->t);
-    LAUNCHED(ctx);
+    const int32_t rc = strict_stage(ctx);
+    if (rc) return rc;
   }
   // traversal arrays (charged nodes only)
   CK(exclusive_scan_dyn(ChargedFlagFn{ctx->t.ndepth}, &ctx->meta->num_nodes, ctx->node_cap, ctx->trav_rank,
@@ -1027,6 +1078,10 @@ int32_t check_build(psim_ctx* ctx) {
              ctx->meta_h.num_nodes, ctx->node_cap);
     return fail(ctx, PSIM_E_NODE_OVERFLOW, msg);
   }
+  if (ctx->meta_h.err & 2u) {
+    ctx->tree_valid = false;
+    return fail(ctx, PSIM_E_NODE_OVERFLOW, "strict_centres: long-chain scratch overflow");
+  }
   return PSIM_OK;
 }
 
@@ -1052,6 +1107,8 @@ void free_all(psim_ctx* c) {
   F(c->surround.last_pos), F(c->surround.last_frame), F(c->surround.flag);
   F(c->cell_start), F(c->cell_end), F(c->order), F(c->body_cell), F(c->cpos), F(c->polarB), F(c->polar_cutoff), F(c->cell_off);
   F(c->table_d), F(c->stage), F(c->qstage), F(c->step_counter);
+  F(c->strict.cidx), F(c->strict.cw), F(c->strict.chains), F(c->strict.hist), F(c->strict.longs), F(c->strict.counters);
+  F(c->strict.item_first), F(c->strict.pblk), F(c->strict.fns);
 }
 
 }  // namespace
@@ -1511,6 +1568,10 @@ int32_t psim_download_nodes(psim_ctx* ctx, psim_node* out, uint64_t cap, uint64_
     export_reset_levels_kernel<<<1, 32, 0, st>>>(ctx->meta, 1, ctx->node_cap);
     export_fill_levels_kernel<<<grid_for(ctx, M, 256, 8), 256, 0, st>>>(ctx->meta, ctx->t);
     ctx->launches += 5;
+    if (ctx->cfg.strict_centres) {  // chargeless nodes: the reference's mass / centroid sums (strict.cuh)
+      strict_chargeless_kernel<<<grid_for(ctx, M, 128, 16), 128, 0, st>>>(ctx->meta, b.pqr, b.accm, ctx->t);
+      LAUNCHED(ctx);
+    }
     for (int level = kMaxLevels - 1; level >= 0; --level) {
       export_level_kernel<<<ctx->sm_count * 8, 128, 0, st>>>(level, ctx->meta, b.pqr, b.accm, ctx->t,
                                                               !ctx->cfg.strict_centres);

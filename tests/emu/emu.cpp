@@ -688,3 +688,73 @@ void emu_sorted_bodies(void* h, float* pqr_out) {
 }
 
 }  // extern "C"
+
+// ---- strict_logic.cuh: the reference's serial f32 running sum, evaluated block-wise (test only) ----
+#include "../../particlesim_b200/csrc/strict_logic.cuh"
+
+extern "C" {
+// Runs the sum of a[0..n) from s0 three ways: (0) the plain serial loop; (1) per-block functions under a
+// binade speculated from an f64 prefix (middle of the block), applied in order with the serial fall-back for
+// blocks that are not valid; (2) like (1) but runs of valid blocks are first composed pairwise (the scan
+// operator) and applied once.  out[0..2] = the three results, stats[0] = blocks, [1] = serial fall-backs.
+void emu_strict_sum(const float* a, uint32_t n, uint32_t block, float s0, float* out, uint64_t* stats) {
+  float serial = s0;
+  for (uint32_t i = 0; i < n; ++i) serial = serial + a[i];
+  out[0] = serial;
+  const uint32_t nb = (n + block - 1) / block;
+  std::vector<double> pre(nb + 1);
+  pre[0] = (double)s0;
+  for (uint32_t b = 0; b < nb; ++b) {
+    double t = 0;
+    for (uint32_t i = b * block; i < std::min(n, (b + 1) * block); ++i) t += (double)a[i];
+    pre[b + 1] = pre[b] + t;
+  }
+  std::vector<BlockFn> fn(nb);
+  for (uint32_t b = 0; b < nb; ++b) {
+    const int e = spec_exponent(0.5 * (pre[b] + pre[b + 1]));
+    blockfn_init(fn[b], e);
+    if (e == kBadExp) continue;
+    const float iu = inv_ulp(e);
+    for (uint32_t i = b * block; i < std::min(n, (b + 1) * block) && fn[b].e != kBadExp; ++i) blockfn_step(fn[b], a[i], iu);
+  }
+  uint64_t fallbacks = 0;
+  float s = s0;
+  for (uint32_t b = 0; b < nb; ++b) {
+    int e;
+    int32_t M;
+    if (f32_split(s, e, M) && blockfn_valid(fn[b], e, M)) {
+      s = f32_join(e, blockfn_apply(fn[b], M));
+    } else {
+      ++fallbacks;
+      for (uint32_t i = b * block; i < std::min(n, (b + 1) * block); ++i) s = s + a[i];
+    }
+  }
+  out[1] = s;
+  // composed application
+  s = s0;
+  for (uint32_t b = 0; b < nb;) {
+    int e;
+    int32_t M;
+    if (f32_split(s, e, M) && blockfn_valid(fn[b], e, M)) {
+      // extend the run while the blocks stay valid given the exact entering mantissa
+      int32_t c0 = fn[b].o[0], c1 = fn[b].o[1];
+      uint32_t r = b + 1;
+      while (r < nb) {
+        const int32_t Mr = M + ((M & 1) ? c1 : c0);
+        if (!blockfn_valid(fn[r], e, Mr)) break;
+        int32_t n0, n1;
+        blockfn_compose(n0, n1, c0, c1, fn[r].o[0], fn[r].o[1]);
+        c0 = n0, c1 = n1;
+        ++r;
+      }
+      s = f32_join(e, M + ((M & 1) ? c1 : c0));
+      b = r;
+    } else {
+      for (uint32_t i = b * block; i < std::min(n, (b + 1) * block); ++i) s = s + a[i];
+      ++b;
+    }
+  }
+  out[2] = s;
+  stats[0] = nb, stats[1] = fallbacks;
+}
+}  // extern "C"

@@ -19,6 +19,7 @@ ap.add_argument("--gen", default="electrolyte")
 ap.add_argument("--theta", type=float, default=1.0)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--fast", type=int, default=0)
+ap.add_argument("--strict", type=int, default=0)
 ap.add_argument("--cells", default="11.88", help="comma-separated cell sizes to time the short-range pass on")
 args = ap.parse_args()
 
@@ -29,7 +30,7 @@ print(f"generated {args.n} bodies in {time.time()-t0:.1f}s", flush=True)
 b = Bodies(bd["pos"], vel=bd.get("vel"), mass=bd["mass"], radius=bd["radius"], charge=bd["charge"],
            species=bd["species"], ebody=bd.get("ebody"), erel=bd.get("erel"))
 stream = torch.cuda.current_stream().cuda_stream
-sim = Simulation(b, bd["hw"], bd["hh"], theta=args.theta, parity_mode=not args.fast, stream=stream)
+sim = Simulation(b, bd["hw"], bd["hh"], theta=args.theta, parity_mode=not args.fast, stream=stream, strict_centres=bool(args.strict))
 sim.config.coulomb_constant = float(KE)
 hw, hh = bd["hw"], bd["hh"]
 
