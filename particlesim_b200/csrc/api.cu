@@ -547,19 +547,22 @@ int32_t ensure_strict(psim_ctx* ctx) {
   if (ctx->strict_ready) return PSIM_OK;
   StrictArrays& S = ctx->strict;
   const size_t nb = ctx->cap_bodies ? ctx->cap_bodies : 1;
-  S.long_cap = (uint32_t)(nb / 256 + 1024);
-  S.item_cap = (uint32_t)(nb / 16 + nb / 256 + 1024);
+  S.long_cap = (uint32_t)(nb / 64 + 1024);
+  S.item_cap = (uint32_t)(nb / 16 + nb / 64 + 1024);
   S.blk_cap = (uint32_t)(nb / kStrictBlock + 2);
   bool ok = true;
   auto A = [&](auto** p, size_t cnt) {
     if (ok && dalloc(p, cnt) != cudaSuccess) ok = false;
   };
-  A(&S.cidx, nb + 1), A(&S.cw, nb), A(&S.chains, nb), A(&S.hist, 96), A(&S.longs, S.long_cap), A(&S.counters, 4);
+  S.cand_cap = (uint32_t)(nb / 16 + 4096);  // chains with a node of more than kStrictDirect bodies: <= 32 levels * nb / 64
+  A(&S.cidx, nb + 1), A(&S.cw, nb), A(&S.chains, S.cand_cap), A(&S.cand, S.cand_cap), A(&S.hist, 96), A(&S.longs, S.long_cap), A(&S.counters, 8);
   A(&S.item_first, (size_t)S.long_cap + 1), A(&S.pblk, 3 * ((size_t)S.blk_cap + 1)), A(&S.fns, 3 * (size_t)S.item_cap);
   if (!ok) {
     cudaGetLastError();
     return fail(ctx, PSIM_E_OOM, "strict_centres scratch");
   }
+  CK(cudaFuncSetAttribute(strict_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStreamSmem));
+  CK(cudaFuncSetAttribute(strict_blockfn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStreamSmem));
   ctx->strict_ready = true;
   return PSIM_OK;
 }
@@ -575,15 +578,14 @@ int32_t strict_stage(psim_ctx* ctx) {
   StrictArrays& S = ctx->strict;
   CK(exclusive_scan(ChargedBodyFn{b.pqr}, n, S.cidx, ctx->scan_partials, S.cidx + n, st));
   strict_addends_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(b.pqr, n, S.cidx, S.cw, S.hist, S.counters);
-  strict_chain_count_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(n, ctx->le, ctx->nodebase, ctx->meta, ctx->t,
-                                                                       S.cidx, S.hist);
-  const uint32_t per_block = 2048;
-  strict_chain_scatter_kernel<<<(n + per_block - 1) / per_block, 256, 0, st>>>(n, per_block, ctx->le, ctx->nodebase,
-                                                                               ctx->meta, ctx->t, S.cidx, S.hist, S.chains);
-  strict_chain_kernel<<<grid_for(ctx, n, 128, 16), 128, 0, st>>>(ctx->le, ctx->nodebase, ctx->meta, ctx->t, S);
+  strict_chain_count_kernel<<<grid_for(ctx, n / 16 + 1, 256, 8), 256, 0, st>>>(S.cand, S.counters + 4, S.cand_cap, S.cidx,
+                                                                               S.hist, S.counters);
+  strict_chain_scatter_kernel<<<grid_for(ctx, n / 16 + 1, 1024, 8), 256, 0, st>>>(S.cand, S.counters + 4, S.cand_cap, 1024,
+                                                                                  S.cidx, S.hist, S.chains);
+  strict_chain_kernel<<<grid_for(ctx, n / 16 + 1, kStreamThreads, 3), kStreamThreads, kStreamSmem, st>>>(ctx->meta, ctx->t, S);
   strict_blocksum_kernel<<<grid_for(ctx, (uint64_t)n / 16 + 1, 256, 8), 256, 0, st>>>(S.cw, S.cidx + n, S.blk_cap, S.pblk);
   strict_long_setup_kernel<<<1, 1024, 0, st>>>(S.cidx + n, S);
-  strict_blockfn_kernel<<<grid_for(ctx, (uint64_t)n / 16 + 1, 128, 16), 128, 0, st>>>(S);
+  strict_blockfn_kernel<<<grid_for(ctx, (uint64_t)n / 16 + 1, kStreamThreads, 3), kStreamThreads, kStreamSmem, st>>>(S);
   strict_compose_kernel<<<ctx->sm_count * 4, 96, 0, st>>>(ctx->meta, ctx->t, S);
   strict_slow_kernel<<<grid_for(ctx, (uint64_t)n * 2, 128, 16), 128, 0, st>>>(ctx->meta, b.pqr, b.accm, ctx->t, S.counters);
   ctx->launches += 12;
@@ -646,15 +648,22 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
   ctx->launches += 3;
   level_scan_kernel<<<1, 32, 0, st>>>(ctx->meta, ctx->node_cap);
   LAUNCHED(ctx);
+  StrictEmit se = {0, nullptr, nullptr, 0};
+  if (ctx->cfg.strict_centres) {
+    const int32_t rc = ensure_strict(ctx);
+    if (rc) return rc;
+    se = StrictEmit{kStrictDirect, ctx->strict.cand, ctx->strict.counters + 4, ctx->strict.cand_cap};
+    CK(cudaMemsetAsync(ctx->strict.counters + 4, 0, sizeof(uint32_t), st));
+  }
   tree_emit_kernel<<<emit_grid, 128, 0, st>>>(
       ctx->keys[1], ctx->keys[1], ctx->tree_plan, kTreePasses, n, per_block, ctx->le, ctx->nodebase, b.pqr,
       b.accm, ctx->cfg.leaf_capacity, ctx->cfg.thread_capacity,
-      ctx->meta, ctx->t);
+      ctx->meta, ctx->t, se);
   LAUNCHED(ctx);
   // bottom-up sweeps over the cells that straddle the emit slabs (a few thousand per level at most),
   // deepest level first; a level's node count is only known on the device
   for (int level = kMaxLevels - 1; level >= 0; --level) {
-    aggregate_level_kernel<<<ctx->sm_count, 128, 0, st>>>(level, ctx->meta, b.pqr, b.accm, ctx->t);
+    aggregate_level_kernel<<<ctx->sm_count, 128, 0, st>>>(level, ctx->meta, b.pqr, b.accm, ctx->t, se.direct);
     LAUNCHED(ctx);
   }
   if (ctx->cfg.strict_centres) {
@@ -1108,7 +1117,7 @@ void free_all(psim_ctx* c) {
   F(c->cell_start), F(c->cell_end), F(c->order), F(c->body_cell), F(c->cpos), F(c->polarB), F(c->polar_cutoff), F(c->cell_off);
   F(c->table_d), F(c->stage), F(c->qstage), F(c->step_counter);
   F(c->strict.cidx), F(c->strict.cw), F(c->strict.chains), F(c->strict.hist), F(c->strict.longs), F(c->strict.counters);
-  F(c->strict.item_first), F(c->strict.pblk), F(c->strict.fns);
+  F(c->strict.item_first), F(c->strict.pblk), F(c->strict.fns), F(c->strict.cand);
 }
 
 }  // namespace

@@ -257,6 +257,9 @@ __global__ void __launch_bounds__(256)
 
 struct ShardSink {
   static constexpr bool kTop = true;
+  static constexpr bool kStrict = false;
+  __device__ __forceinline__ uint32_t strict_direct() const { return 0xffffffffu; }
+  __device__ __forceinline__ void strict_chain(uint32_t, uint32_t, uint32_t, uint32_t) {}
   TreeMeta* meta;
   uint32_t* s_cursor;
   TopRec* heap;

@@ -22,6 +22,7 @@
 // Nodes without any charged body never enter a field sum; their centres are only needed by the export
 // (psim_download_nodes), which runs strict_chargeless_kernel first.
 #pragma once
+#include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -31,9 +32,11 @@
 
 namespace psim {
 
-constexpr uint32_t kStrictT1 = 8192;      // addends a single thread may walk
-constexpr int kStrictClasses = 15;        // length classes 1..14 (class c: 2^(c-1) <= len < 2^c, capped)
+constexpr uint32_t kStrictDirect = 64;    // nodes up to this many bodies are summed in the emit kernel (tree_logic.cuh)
+constexpr uint32_t kStrictT1 = 2048;      // addends a single thread may walk
+constexpr int kStrictClasses = 13;        // length classes 1..12 (class c: 2^(c-1) <= len < 2^c, capped)
 constexpr uint32_t kSlowSentinel = 0x7fc0deadu;
+constexpr uint32_t kChainLenCap = (1u << 27) - 1;  // chain lengths saturate here in the packed record
 
 struct StrictLong {  // a chain handed over to the block machinery
   uint32_t body;     // chain head (sorted body index)
@@ -47,10 +50,13 @@ struct StrictLong {  // a chain handed over to the block machinery
 struct StrictArrays {
   uint32_t* cidx;        // n + 1
   float4* cw;            // charged bodies: {|q|, x|q|, y|q|, 0}
-  uint32_t* chains;      // chain heads by length class, longest first
+  uint4* chains;         // per chain {head body, shallowest node, first addend, length | (nodes - 1) << 27},
+                         // by length class, longest first
   uint32_t* hist;        // [0, 32): class counts, [32]: chains, [64, 96): scatter cursors
   StrictLong* longs;
-  uint32_t* counters;    // [0] long chains, [1] items, [2] slow nodes, [3] error bits
+  uint32_t* counters;    // [0] long chains, [1] items, [2] slow nodes, [3] error bits, [4] candidates
+  uint4* cand;           // chains reported by the emit kernel
+  uint32_t cand_cap;
   uint32_t* item_first;  // long_cap + 1
   double* pblk;          // 3 arrays of (blocks + 1): exclusive f64 prefix of the block sums
   BlockFn* fns;          // 3 per item
@@ -78,68 +84,75 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// length (in charged bodies) of the chain that starts at body i, 0 if none
-__device__ __forceinline__ uint32_t chain_length(uint32_t i, const uint16_t* __restrict__ le,
-                                                 const uint32_t* __restrict__ nodebase,
-                                                 const uint4* __restrict__ nodeB,
-                                                 const uint32_t* __restrict__ cidx) {
-  const uint16_t lev = le[i];
-  if (le_ell(lev) - le_lambda(lev) < 2) return 0;  // the body starts no internal node
-  const uint32_t cnt = nodeB[nodebase[i]].z;       // the shallowest node of the chain is the largest
-  return cidx[i + cnt] - cidx[i];
-}
 __device__ __forceinline__ int chain_class(uint32_t len) {
   const int c = 32 - __clz(len);
   return c < kStrictClasses - 1 ? c : kStrictClasses - 1;
 }
 
+// The emit kernel reports every chain that has a node of more than kStrictDirect bodies (tree.cuh
+// StrictEmit); chains without a charged body drop out here.
 __global__ void __launch_bounds__(256)
-    strict_chain_count_kernel(uint32_t n, const uint16_t* __restrict__ le, const uint32_t* __restrict__ nodebase,
-                              const TreeMeta* __restrict__ meta, TreeArrays t, const uint32_t* __restrict__ cidx,
-                              uint32_t* __restrict__ hist) {
-  if (meta->num_nodes > t.node_cap) return;
+    strict_chain_count_kernel(const uint4* __restrict__ cand, const uint32_t* __restrict__ cand_count, uint32_t cand_cap,
+                              const uint32_t* __restrict__ cidx, uint32_t* __restrict__ hist,
+                              uint32_t* __restrict__ counters) {
   __shared__ uint32_t s_cnt[kStrictClasses];
   if (threadIdx.x < kStrictClasses) s_cnt[threadIdx.x] = 0;
   __syncthreads();
+  uint32_t nc = *cand_count;
+  if (nc > cand_cap) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&counters[3], 4u);
+    nc = cand_cap;
+  }
   const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const uint32_t len = chain_length(i, le, nodebase, t.nodeB, cidx);
+  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < nc; g += stride) {
+    const uint4 c = cand[g];
+    const uint32_t len = cidx[c.x + c.w] - cidx[c.x];
     if (len) atomicAdd(&s_cnt[chain_class(len)], 1u);
   }
   __syncthreads();
   if (threadIdx.x < kStrictClasses && s_cnt[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_cnt[threadIdx.x]);
 }
 
-// counting sort by class, longest class first.  Every CTA owns a contiguous slab of bodies, reserves one
+// counting sort by class, longest class first.  Every CTA owns a contiguous slab of candidates, reserves one
 // range per class with a single global atomic and scatters into it.
 __global__ void __launch_bounds__(256)
-    strict_chain_scatter_kernel(uint32_t n, uint32_t per_block, const uint16_t* __restrict__ le,
-                                const uint32_t* __restrict__ nodebase, const TreeMeta* __restrict__ meta,
-                                TreeArrays t, const uint32_t* __restrict__ cidx, uint32_t* __restrict__ hist,
-                                uint32_t* __restrict__ chains) {
-  if (meta->num_nodes > t.node_cap) return;
+    strict_chain_scatter_kernel(const uint4* __restrict__ cand, const uint32_t* __restrict__ cand_count,
+                                uint32_t cand_cap, uint32_t per_block, const uint32_t* __restrict__ cidx,
+                                uint32_t* __restrict__ hist, uint4* __restrict__ chains) {
   __shared__ uint32_t s_cnt[kStrictClasses], s_base[kStrictClasses];
   if (threadIdx.x < kStrictClasses) s_cnt[threadIdx.x] = 0;
   __syncthreads();
-  const uint32_t lo = blockIdx.x * per_block;
-  const uint32_t hi = lo + per_block < n ? lo + per_block : n;
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const uint32_t len = chain_length(i, le, nodebase, t.nodeB, cidx);
-    if (len) atomicAdd(&s_cnt[chain_class(len)], 1u);
+  uint32_t nc = *cand_count;
+  if (nc > cand_cap) nc = cand_cap;
+  for (uint32_t slab = blockIdx.x; (uint64_t)slab * per_block < nc; slab += gridDim.x) {
+    const uint32_t lo = slab * per_block;
+    const uint32_t hi = lo + per_block < nc ? lo + per_block : nc;
+    for (uint32_t g = lo + threadIdx.x; g < hi; g += blockDim.x) {
+      const uint4 c = cand[g];
+      const uint32_t len = cidx[c.x + c.w] - cidx[c.x];
+      if (len) atomicAdd(&s_cnt[chain_class(len)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < kStrictClasses) {
+      uint32_t start = 0;
+      for (int k = kStrictClasses - 1; k > (int)threadIdx.x; --k) start += hist[k];
+      const uint32_t mine = s_cnt[threadIdx.x];
+      s_base[threadIdx.x] = start + (mine ? atomicAdd(&hist[64 + threadIdx.x], mine) : 0u);
+      if (slab == 0 && threadIdx.x == 0) hist[32] = start + hist[0];  // class 0 is empty: total chains
+    }
+    __syncthreads();
+    for (uint32_t g = lo + threadIdx.x; g < hi; g += blockDim.x) {
+      const uint4 c = cand[g];
+      const uint32_t c0 = cidx[c.x], len = cidx[c.x + c.w] - c0;
+      if (len)
+        chains[atomicAdd(&s_base[chain_class(len)], 1u)] =
+            make_uint4(c.x, c.y, c0, (len < kChainLenCap ? len : kChainLenCap) | (c.z << 27));
+    }
+    __syncthreads();
+    if (threadIdx.x < kStrictClasses) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
   }
-  __syncthreads();
-  if (threadIdx.x < kStrictClasses) {
-    uint32_t start = 0;
-    for (int c = kStrictClasses - 1; c > (int)threadIdx.x; --c) start += hist[c];
-    const uint32_t mine = s_cnt[threadIdx.x];
-    s_base[threadIdx.x] = start + (mine ? atomicAdd(&hist[64 + threadIdx.x], mine) : 0u);
-    if (blockIdx.x == 0 && threadIdx.x == 0) hist[32] = start + hist[0];  // class 0 is empty: total chains
-  }
-  __syncthreads();
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const uint32_t len = chain_length(i, le, nodebase, t.nodeB, cidx);
-    if (len) chains[atomicAdd(&s_base[chain_class(len)], 1u)] = i;
-  }
+  if (nc == 0 && blockIdx.x == 0 && threadIdx.x == 0) hist[32] = 0;
 }
 
 __device__ __forceinline__ void strict_write_centre(float sa, float sx, float sy, uint32_t node, const TreeArrays& t,
@@ -158,52 +171,104 @@ __device__ __forceinline__ void strict_acc(const float4 v, float& sa, float& sx,
   sa = f_add(sa, v.x), sx = f_add(sx, v.y), sy = f_add(sy, v.z);
 }
 
-// one chain per thread
-__global__ void __launch_bounds__(128)
-    strict_chain_kernel(const uint16_t* __restrict__ le, const uint32_t* __restrict__ nodebase,
-                        const TreeMeta* __restrict__ meta, TreeArrays t, StrictArrays S) {
+// A thread's private sequential read of cw[first, last) through shared memory: cp.async copies of kStreamChunk
+// addends each, kStreamDepth chunks in the ring, so that kStreamDepth - 1 chunks are in flight while one is
+// consumed (a thread that walks a long run of addends one after the other would otherwise wait a full
+// memory latency every few additions).  Element j of ring slot b lives at ring[(b * chunk + j) * blockDim.x].
+constexpr int kStreamChunk = 8, kStreamDepth = 4;
+constexpr int kStreamThreads = 128;
+constexpr size_t kStreamSmem = (size_t)kStreamThreads * kStreamChunk * kStreamDepth * sizeof(float4);
+
+struct AddendStream {
+  float4* ring;  // this thread's column of the ring
+  const float4* src;
+  uint32_t next, last;  // next addend to request, end of the run
+  int issue_slot, read_slot;
+  __device__ __forceinline__ void issue() {
+    float4* dst = ring + (size_t)issue_slot * kStreamChunk * kStreamThreads;
+#pragma unroll
+    for (int j = 0; j < kStreamChunk; ++j)
+      if (next + j < last) __pipeline_memcpy_async(dst + j * kStreamThreads, src + next + j, sizeof(float4));
+    __pipeline_commit();
+    next = next + kStreamChunk < last ? next + kStreamChunk : last;
+    issue_slot = issue_slot + 1 == kStreamDepth ? 0 : issue_slot + 1;
+  }
+  __device__ __forceinline__ void start(float4* smem, const float4* cw, uint32_t first, uint32_t end) {
+    ring = smem + threadIdx.x, src = cw, next = first, last = end, issue_slot = 0, read_slot = 0;
+#pragma unroll
+    for (int k = 0; k < kStreamDepth - 1; ++k) issue();
+  }
+  // wait for the oldest chunk; at(j) reads its addends; release() recycles its slot
+  __device__ __forceinline__ void acquire() { __pipeline_wait_prior(kStreamDepth - 2); }
+  __device__ __forceinline__ float4 at(int j) const {
+    return ring[((size_t)read_slot * kStreamChunk + j) * kStreamThreads];
+  }
+  __device__ __forceinline__ void release() {
+    read_slot = read_slot + 1 == kStreamDepth ? 0 : read_slot + 1;
+    issue();
+  }
+};
+
+// one chain per thread.  The walk is ONE flat loop over chunks of the chain's addends (node boundaries are
+// handled inside a chunk), so that the lanes of a warp (chains of the same length class) stay converged
+// although their nodes end at different places.
+__global__ void __launch_bounds__(kStreamThreads)
+    strict_chain_kernel(const TreeMeta* __restrict__ meta, TreeArrays t, StrictArrays S) {
+  extern __shared__ float4 s_ring[];
   if (meta->num_nodes > t.node_cap) return;
   const uint32_t nchains = S.hist[32];
   const uint32_t stride = gridDim.x * blockDim.x;
-  const float4* __restrict__ cw = S.cw;
   for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < nchains; g += stride) {
-    const uint32_t i = S.chains[g];
-    const uint16_t lev = le[i];
-    const int K = le_ell(lev) - le_lambda(lev) - 1;  // internal nodes base .. base + K - 1, shallowest first
-    const uint32_t base = nodebase[i];
-    const uint32_t c0 = S.cidx[i];
+    const uint4 rec = S.chains[g];
+    const uint32_t i = rec.x, base = rec.y, c0 = rec.z;
+    int k = (int)(rec.w >> 27);  // nodes base .. base + k are open, shallowest first
+    const uint32_t len = rec.w & kChainLenCap;
     const uint32_t limit = ((c0 + kStrictT1) / kStrictBlock + 1) * kStrictBlock;
+    const uint32_t all_end = (len < kChainLenCap && c0 + len < limit) ? c0 + len : limit;
+    AddendStream st;
+    st.start(s_ring, S.cw, c0, all_end);
     uint32_t pos = c0;
+    // a single-node chain ends where the record says; otherwise the deepest open node's end is looked up
+    uint32_t cend = (k == 0 && len < kChainLenCap) ? c0 + len : S.cidx[i + t.nodeB[base + (uint32_t)k].z];
+    uint32_t stop = cend < limit ? cend : limit;
     float sa = 0.0f, sx = 0.0f, sy = 0.0f;
-    for (int k = K - 1; k >= 0; --k) {
-      const uint32_t node = base + (uint32_t)k;
-      const uint32_t cend = S.cidx[i + t.nodeB[node].z];
-      const uint32_t stop = cend < limit ? cend : limit;
-      while (pos < stop && (pos & 7u)) strict_acc(cw[pos++], sa, sx, sy);
-      while (pos + 8 <= stop) {
-        float4 v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = cw[pos + j];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) strict_acc(v[j], sa, sx, sy);
-        pos += 8;
-      }
-      while (pos < stop) strict_acc(cw[pos++], sa, sx, sy);
-      if (stop < cend) {  // hand the rest over
-        const uint32_t slot = atomicAdd(&S.counters[0], 1u);
-        if (slot < S.long_cap) {
-          StrictLong L;
-          L.body = i, L.base = base, L.k_next = k, L.blk0 = limit / kStrictBlock;
-          L.cend = S.cidx[i + t.nodeB[base].z];
-          L.s[0] = sa, L.s[1] = sx, L.s[2] = sy;
-          S.longs[slot] = L;
-        } else {
-          atomicOr(&S.counters[3], 1u);
+    bool open = true;
+    while (open) {
+      st.acquire();
+      int j = 0;
+      while (true) {
+        if (pos == stop) {
+          if (stop < cend) {  // hand the rest over
+            const uint32_t slot = atomicAdd(&S.counters[0], 1u);
+            if (slot < S.long_cap) {
+              StrictLong L;
+              L.body = i, L.base = base, L.k_next = k, L.blk0 = limit / kStrictBlock;
+              L.cend = S.cidx[i + t.nodeB[base].z];
+              L.s[0] = sa, L.s[1] = sx, L.s[2] = sy;
+              S.longs[slot] = L;
+            } else {
+              atomicOr(&S.counters[3], 1u);
+            }
+            open = false;
+            break;
+          }
+          if (cend > c0) strict_write_centre(sa, sx, sy, base + (uint32_t)k, t, S.counters);
+          if (--k < 0) {
+            open = false;
+            break;
+          }
+          cend = S.cidx[i + t.nodeB[base + (uint32_t)k].z];
+          stop = cend < limit ? cend : limit;
+          continue;
         }
-        break;
+        if (j == kStreamChunk) break;
+        int run = (int)(stop - pos < (uint32_t)(kStreamChunk - j) ? stop - pos : (uint32_t)(kStreamChunk - j));
+        pos += (uint32_t)run;
+        for (; run > 0; --run, ++j) strict_acc(st.at(j), sa, sx, sy);
       }
-      if (cend > c0) strict_write_centre(sa, sx, sy, node, t, S.counters);
+      st.release();
     }
+    __pipeline_wait_prior(0);  // nothing of this chain may land in the ring after the next one has started
   }
 }
 
@@ -303,7 +368,8 @@ __global__ void __launch_bounds__(1024)
 }
 
 // one (chain, block) item per thread: the block's effect on each of the three accumulators
-__global__ void __launch_bounds__(128) strict_blockfn_kernel(StrictArrays S) {
+__global__ void __launch_bounds__(kStreamThreads) strict_blockfn_kernel(StrictArrays S) {
+  extern __shared__ float4 s_ring[];
   if (S.counters[3]) return;
   const uint32_t nitems = S.counters[1];
   uint32_t nlong = S.counters[0];
@@ -319,6 +385,8 @@ __global__ void __launch_bounds__(128) strict_blockfn_kernel(StrictArrays S) {
     const uint32_t gb = L.blk0 + (it - S.item_first[a]);
     const uint32_t first = gb * kStrictBlock;
     const uint32_t last = first + kStrictBlock < L.cend ? first + kStrictBlock : L.cend;
+    AddendStream st;
+    st.start(s_ring, S.cw, first, last);
     BlockFn f[3];
     float iu[3];
 #pragma unroll
@@ -329,26 +397,48 @@ __global__ void __launch_bounds__(128) strict_blockfn_kernel(StrictArrays S) {
       blockfn_init(f[k], e);
       iu[k] = e == kBadExp ? 0.0f : inv_ulp(e);
     }
-    for (uint32_t i = first; i < last; ++i) {
-      const float4 v = S.cw[i];
-      if (f[0].e != kBadExp) blockfn_step(f[0], v.x, iu[0]);
-      if (f[1].e != kBadExp) blockfn_step(f[1], v.y, iu[1]);
-      if (f[2].e != kBadExp) blockfn_step(f[2], v.z, iu[2]);
+    for (uint32_t pos = first; pos < last; pos += kStreamChunk) {
+      st.acquire();
+      const int cnt = last - pos < (uint32_t)kStreamChunk ? (int)(last - pos) : kStreamChunk;
+      for (int j = 0; j < cnt; ++j) {
+        const float4 v = st.at(j);
+        if (f[0].e != kBadExp) blockfn_step(f[0], v.x, iu[0]);
+        if (f[1].e != kBadExp) blockfn_step(f[1], v.y, iu[1]);
+        if (f[2].e != kBadExp) blockfn_step(f[2], v.z, iu[2]);
+      }
+      st.release();
     }
+    __pipeline_wait_prior(0);
 #pragma unroll
     for (int k = 0; k < 3; ++k) S.fns[3 * (size_t)it + k] = f[k];
   }
 }
 
-// s + cw[first .. last).comp in order, by one warp (every lane returns the result)
+// s + cw[first .. last).comp in order, by one warp (every lane returns the result).  The addends of up to
+// 512 positions are fetched first (independent loads), then the additions run as one shuffle + add chain.
 __device__ __forceinline__ float strict_serial_run(float s, const float4* __restrict__ cw, int comp, uint32_t first,
                                                    uint32_t last, int lane) {
   const float* __restrict__ w = reinterpret_cast<const float*>(cw) + comp;
-  for (uint32_t base = first; base < last; base += 32) {
-    const uint32_t idx = base + lane;
-    const float v = idx < last ? w[4 * (size_t)idx] : 0.0f;
-    const int cnt = last - base < 32u ? (int)(last - base) : 32;
-    for (int j = 0; j < cnt; ++j) s = f_add(s, __shfl_sync(0xffffffffu, v, j));
+  for (uint32_t base = first; base < last; base += 512) {
+    float v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const uint32_t idx = base + 32u * r + lane;
+      v[r] = idx < last ? w[4 * (size_t)idx] : 0.0f;
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const uint32_t b0 = base + 32u * r;
+      if (b0 < last) {
+        const int cnt = last - b0 < 32u ? (int)(last - b0) : 32;
+        if (cnt == 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s = f_add(s, __shfl_sync(0xffffffffu, v[r], j));
+        } else {
+          for (int j = 0; j < cnt; ++j) s = f_add(s, __shfl_sync(0xffffffffu, v[r], j));
+        }
+      }
+    }
   }
   return s;
 }
@@ -370,11 +460,17 @@ __global__ void __launch_bounds__(96) strict_compose_kernel(const TreeMeta* __re
     uint32_t blk = 0;
     int kk = L.k_next;
     float s = L.s[w];
+    BlockFn pre;  // the window that follows if all 32 blocks of the current one apply (the common case)
+    uint32_t pre_blk = 0xffffffffu;
     while (blk < nblk) {
       BlockFn f;
       const bool have = blk + lane < nblk;
-      if (have) f = S.fns[3 * (size_t)(item0 + blk + lane) + w];
+      if (blk == pre_blk) f = pre;
+      else if (have) f = S.fns[3 * (size_t)(item0 + blk + lane) + w];
       else blockfn_init(f, kBadExp);
+      pre_blk = blk + 32;
+      if (pre_blk + lane < nblk) pre = S.fns[3 * (size_t)(item0 + pre_blk + lane) + w];
+      else blockfn_init(pre, kBadExp);
       int e = 0;
       int32_t M = 0;
       const bool ok = f32_split(s, e, M);

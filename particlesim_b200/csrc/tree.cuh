@@ -151,8 +151,22 @@ __global__ void level_scan_kernel(TreeMeta* __restrict__ meta, uint32_t node_cap
 // level-bucket slots.  A CTA first counts, from the packed (λ, ℓ) bytes alone, how many internal nodes
 // of each depth its bodies start, reserves one contiguous range per depth with a single global atomic,
 // and then hands slots out of shared-memory counters while it emits.
+struct StrictEmit {        // psim_config.strict_centres (strict.cuh); direct == 0: off
+  uint32_t direct;         // nodes of at most this many bodies are summed by finalize_node
+  uint4* cand;             // chains with larger nodes: {head body, shallowest node, big nodes - 1, bodies of the largest}
+  uint32_t* cand_count;
+  uint32_t cand_cap;
+};
+
 struct DeviceSink {
   static constexpr bool kTop = false;
+  static constexpr bool kStrict = true;
+  StrictEmit strict;
+  __device__ __forceinline__ uint32_t strict_direct() const { return strict.direct ? strict.direct : 0xffffffffu; }
+  __device__ __forceinline__ void strict_chain(uint32_t i, uint32_t base, uint32_t big, uint32_t cnt_top) {
+    const uint32_t slot = atomicAdd(strict.cand_count, 1u);
+    if (slot < strict.cand_cap) strict.cand[slot] = make_uint4(i, base, big - 1u, cnt_top);
+  }
   __device__ __forceinline__ void top_leaf(int, uint64_t, uint32_t, const NodeRec&) {}
   __device__ __forceinline__ void top_internal(int, uint64_t, uint32_t) {}
   TreeMeta* meta;
@@ -177,7 +191,7 @@ __global__ void __launch_bounds__(128)
                      const uint16_t* __restrict__ le, const uint32_t* __restrict__ nodebase,
                      const float4* __restrict__ pqr, const float4* __restrict__ accm,
                      uint32_t leaf_capacity, uint32_t thread_capacity, TreeMeta* __restrict__ meta,
-                     TreeArrays t) {
+                     TreeArrays t, StrictEmit strict) {
   const uint64_t* __restrict__ keys = plan->src[npass] ? keys1 : keys0;
   const uint32_t M = meta->num_nodes;
   if (M > t.node_cap) return;  // arena overflow, flagged by level_scan_kernel
@@ -213,7 +227,7 @@ __global__ void __launch_bounds__(128)
   __syncthreads();
   const float root_size = meta->root.size;
   const int dcap = (int)meta->dcap;
-  DeviceSink sink{meta, s_cursor, s_local, t.local_nodes};
+  DeviceSink sink{strict, meta, s_cursor, s_local, t.local_nodes};
   for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const int straddle = has_next ? lcp_levels(keys[i], key_hi) : -1;
     emit_nodes_for_body(keys, n, i, le[i], nodebase, M, pqr, accm, leaf_capacity, thread_capacity,
@@ -228,7 +242,7 @@ __global__ void __launch_bounds__(128)
     for (uint32_t k = begin + threadIdx.x; k < end; k += blockDim.x) {
       const uint32_t node = t.local_nodes[k];
       aggregate_node_ranged(node, level, t);
-      finalize_node(node, root_size, pqr, accm, t, SubtreeEndCount{});
+      finalize_node(node, root_size, pqr, accm, t, SubtreeEndCount{}, strict.direct);
     }
   }
 }
@@ -237,7 +251,7 @@ __global__ void __launch_bounds__(128)
 // boundaries; their centres are finished in the same visit
 __global__ void __launch_bounds__(128)
     aggregate_level_kernel(int level, const TreeMeta* __restrict__ meta, const float4* __restrict__ pqr,
-                           const float4* __restrict__ accm, TreeArrays t) {
+                           const float4* __restrict__ accm, TreeArrays t, uint32_t strict_direct) {
   const uint32_t M = meta->num_nodes;
   if (M > t.node_cap) return;
   const uint32_t begin = meta->level_start[level], end = meta->level_start[level + 1];
@@ -246,7 +260,7 @@ __global__ void __launch_bounds__(128)
   for (uint32_t k = begin + blockIdx.x * blockDim.x + threadIdx.x; k < end; k += stride) {
     const uint32_t node = t.level_nodes[k];
     aggregate_node_ranged(node, level, t);
-    finalize_node(node, root_size, pqr, accm, t, SubtreeEndCount{});
+    finalize_node(node, root_size, pqr, accm, t, SubtreeEndCount{}, strict_direct);
   }
 }
 
@@ -313,46 +327,6 @@ __global__ void export_root_leaf_kernel(const TreeMeta* __restrict__ meta, const
     for (uint32_t b = nb.y; b < nb.y + nb.z; ++b) lm = f_add(lm, accm[b].w);
   t.node_mass[0] = lm;
   t.parent[0] = 0xffffffffu;
-}
-
-// psim_config.strict_centres: the reference's own arithmetic for internal centres - three serial f32
-// running sums over the node's body range in sorted order (quadtree.rs:114-139).  One thread per node.
-__global__ void __launch_bounds__(128)
-    strict_centres_kernel(const TreeMeta* __restrict__ meta, const float4* __restrict__ pqr,
-                          const float4* __restrict__ accm, TreeArrays t) {
-  const uint32_t M = meta->num_nodes;
-  if (M > t.node_cap) return;
-  const uint32_t n_bodies = meta->n;
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t node = blockIdx.x * blockDim.x + threadIdx.x; node < M; node += stride) {
-    const uint4 nb = t.nodeB[node];
-    if (nb.w & kNodeLeaf) continue;
-    const uint32_t b0 = nb.y, b1 = nb.x < M ? t.nodeB[nb.x].y : n_bodies;
-    float total_mass = 0.0f, total_abs = 0.0f;
-    for (uint32_t b = b0; b < b1; ++b) total_mass = f_add(total_mass, accm[b].w);
-    for (uint32_t b = b0; b < b1; ++b) total_abs = f_add(total_abs, fabsf(pqr[b].z));
-    float wx = 0.0f, wy = 0.0f;
-    if (total_abs > 1e-6f) {
-      for (uint32_t b = b0; b < b1; ++b) {
-        const float4 p = pqr[b];
-        wx = f_add(wx, f_mul(p.x, fabsf(p.z))), wy = f_add(wy, f_mul(p.y, fabsf(p.z)));
-      }
-      wx = f_div(wx, total_abs), wy = f_div(wy, total_abs);
-    } else if (total_mass > 1e-6f) {
-      for (uint32_t b = b0; b < b1; ++b) {
-        const float4 p = pqr[b];
-        const float m = accm[b].w;
-        wx = f_add(wx, f_mul(p.x, m)), wy = f_add(wy, f_mul(p.y, m));
-      }
-      wx = f_div(wx, total_mass), wy = f_div(wy, total_mass);
-    } else if (b1 > b0) {
-      for (uint32_t b = b0; b < b1; ++b) wx = f_add(wx, pqr[b].x), wy = f_add(wy, pqr[b].y);
-      wx = f_div(wx, (float)(b1 - b0)), wy = f_div(wy, (float)(b1 - b0));
-    }
-    float4 a = t.nodeA[node];
-    a.x = wx, a.y = wy;
-    t.nodeA[node] = a;
-  }
 }
 
 // Traversal arrays: the nodes that can contribute to a field sum, i.e. those with a charged body

@@ -212,6 +212,7 @@ PSIM_HD void emit_nodes_for_body(const uint64_t* keys, uint32_t n, uint32_t i, u
   // boundary go to the level sweeps.
   uint32_t jprev = i + 1;
   if (internal_ranges) jprev = run_end(keys, n, i, i + 1, ell);
+  uint32_t big = 0;  // internal nodes of this chain that strict.cuh has to sum (the shallowest `big` ones)
   for (int d = ell - 1; d > lam; --d) {
     const uint32_t node = base + (uint32_t)(d - lam - 1);
     uint32_t nx = 0u, cnt = 0u;
@@ -219,6 +220,7 @@ PSIM_HD void emit_nodes_for_body(const uint64_t* keys, uint32_t n, uint32_t i, u
       jprev = run_end(keys, n, i, jprev, d);
       nx = (jprev < n) ? nodebase[jprev] : M;
       cnt = jprev - i;
+      if (Sink::kStrict && cnt > sink.strict_direct()) ++big;
     }
     t.nodeB[node] = make_uint4(nx, i + body_base, cnt, (uint32_t)d);
     t.ndepth[node] = (uint8_t)d;
@@ -228,6 +230,7 @@ PSIM_HD void emit_nodes_for_body(const uint64_t* keys, uint32_t n, uint32_t i, u
     }
     if (Sink::kTop && d <= min_bucket_depth) sink.top_internal(d, keys[i], node);
   }
+  if (Sink::kStrict && big) sink.strict_chain(i, base, big, jprev - i);
 }
 
 // One internal node of the build's bottom-up sweep (quadtree.rs:103-151): charge in the reference's
@@ -288,9 +291,45 @@ struct SubtreeEndLocal {  // first body after the subtree that ends where node c
   PSIM_HD uint32_t operator()(uint32_t c, const uint4&) const { return c < M ? nodeB[c].y : n_bodies; }
 };
 
+// The reference's own loop for one internal node's centre (quadtree.rs:114-139): serial f32 running sums over
+// the node's bodies, |q|-weighted, else mass-weighted, else the centroid.
+PSIM_HD void strict_centre_direct(uint32_t b0, uint32_t b1, const float4* pqr, const float4* accm, float& px,
+                                  float& py) {
+  float total_abs = 0.0f, wx = 0.0f, wy = 0.0f;
+  for (uint32_t b = b0; b < b1; ++b) {
+    const float4 p = pqr[b];
+    const float a = fabsf(p.z);
+    total_abs = f_add(total_abs, a);
+    wx = f_add(wx, f_mul(p.x, a)), wy = f_add(wy, f_mul(p.y, a));
+  }
+  if (total_abs > 1e-6f) {
+    px = f_div(wx, total_abs), py = f_div(wy, total_abs);
+    return;
+  }
+  float total_mass = 0.0f;
+  for (uint32_t b = b0; b < b1; ++b) total_mass = f_add(total_mass, accm[b].w);
+  wx = 0.0f, wy = 0.0f;
+  if (total_mass > 1e-6f) {
+    for (uint32_t b = b0; b < b1; ++b) {
+      const float4 p = pqr[b];
+      const float m = accm[b].w;
+      wx = f_add(wx, f_mul(p.x, m)), wy = f_add(wy, f_mul(p.y, m));
+    }
+    px = f_div(wx, total_mass), py = f_div(wy, total_mass);
+  } else if (b1 > b0) {
+    for (uint32_t b = b0; b < b1; ++b) wx = f_add(wx, pqr[b].x), wy = f_add(wy, pqr[b].y);
+    px = f_div(wx, (float)(b1 - b0)), py = f_div(wy, (float)(b1 - b0));
+  } else {
+    px = 0.0f, py = 0.0f;
+  }
+}
+
+// strict_direct > 0 (psim_config.strict_centres, single-GPU build): nodes of at most that many bodies get
+// the reference's serial sums right here, where their bodies are still in cache; larger ones are left to
+// strict.cuh.
 template <class SubtreeEnd>
 PSIM_HD void finalize_node(uint32_t node, float root_size, const float4* pqr, const float4* accm,
-                           const TreeArrays& t, const SubtreeEnd& subtree_end) {
+                           const TreeArrays& t, const SubtreeEnd& subtree_end, uint32_t strict_direct = 0) {
   uint4 nb = t.nodeB[node];
   if (nb.w & kNodeLeaf) return;
   const NodeRec r = t.rec[node];
@@ -299,7 +338,9 @@ PSIM_HD void finalize_node(uint32_t node, float root_size, const float4* pqr, co
   if (r.aq > 0.0) nb.w |= kNodeCharged;
   t.nodeB[node] = nb;
   float px = 0.0f, py = 0.0f;
-  if (r.aq > (double)1e-6f) {
+  if (strict_direct && nb.z <= strict_direct) {
+    strict_centre_direct(nb.y, nb.y + nb.z, pqr, accm, px, py);
+  } else if (r.aq > (double)1e-6f) {
     px = (float)(r.aqx / r.aq), py = (float)(r.aqy / r.aq);
   } else if (r.aq > 0.0) {
     const uint32_t b0 = nb.y, b1 = subtree_end(c, nb);

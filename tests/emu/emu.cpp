@@ -20,6 +20,9 @@ using namespace psim;
 namespace {
 struct HostSink {
   static constexpr bool kTop = false;
+  static constexpr bool kStrict = false;
+  uint32_t strict_direct() const { return 0xffffffffu; }
+  void strict_chain(uint32_t, uint32_t, uint32_t, uint32_t) {}
   void top_leaf(int, uint64_t, uint32_t, const NodeRec&) {}
   void top_internal(int, uint64_t, uint32_t) {}
   std::vector<std::vector<uint32_t>>* local = nullptr;  // per depth: the current slab's own cells
@@ -285,6 +288,9 @@ void emu_walk(void* h, uint32_t m, const float* pts_xy, const float* q, const fl
 // node), sentinel depths, heap slots with more than one writer, travA, travB.  Returns the node total.
 struct HostShardSink {
   static constexpr bool kTop = true;
+  static constexpr bool kStrict = false;
+  uint32_t strict_direct() const { return 0xffffffffu; }
+  void strict_chain(uint32_t, uint32_t, uint32_t, uint32_t) {}
   TopRec* heap;
   uint32_t* multi_writer;
   uint32_t level_slot(int) { return 0; }  // the level buckets are collected from the (lambda, ell) levels

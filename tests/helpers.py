@@ -224,7 +224,7 @@ class Emu:
         here = os.path.join(ROOT, "tests", "emu")
         so = os.path.join(here, "_build", "libemu.so")
         src = os.path.join(here, "emu.cpp")
-        deps = [src] + [os.path.join(ROOT, "particlesim_b200", "csrc", f) for f in ("psim_core.cuh", "tree_logic.cuh")]
+        deps = [src] + [os.path.join(ROOT, "particlesim_b200", "csrc", f) for f in ("psim_core.cuh", "tree_logic.cuh", "shard_logic.cuh", "strict_logic.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             os.makedirs(os.path.dirname(so), exist_ok=True)
             cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
@@ -249,6 +249,7 @@ class Emu:
         L.emu_walk_signatures.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_group_walk.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
+        L.emu_strict_sum.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p]
         L.emu_shard_check.restype = C.c_uint32
         L.emu_shard_check.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         self.h = L.emu_create()
@@ -257,6 +258,13 @@ class Emu:
         if getattr(self, "h", None):
             self.lib.emu_destroy(self.h)
             self.h = None
+
+    def strict_sum(self, a, block=512, s0=0.0):
+        """serial f32 sum of a from s0 three ways (plain loop, block functions, composed block functions)"""
+        a = np.ascontiguousarray(a, np.float32)
+        out, st = np.zeros(3, np.float32), np.zeros(2, np.uint64)
+        self.lib.emu_strict_sum(a.ctypes.data, len(a), block, np.float32(s0), out.ctypes.data, st.ctypes.data)
+        return out, int(st[0]), int(st[1])
 
     def walk_signatures(self, pts, radius=None, theta=1.0, epsilon=2.0):
         """per-target interaction signatures of the reference-order walk (see emu.cpp)"""

@@ -135,3 +135,39 @@ def test_group_walk_sums_exactly_the_reference_interaction_sets(gen, n, mode, th
     rng = np.random.default_rng(1)
     pts2 = (pts + rng.normal(0, 0.4, pts.shape)).astype(np.float32)
     assert np.array_equal(emu.group_walk(pts2, theta=theta)[1], emu.walk_signatures(pts2, theta=theta))
+
+
+def _strict_cases():
+    rng = np.random.default_rng(1)
+    m = 300_000
+    return {
+        "ones": np.ones(m),
+        "signed_x": rng.uniform(-8000, 8000, m),
+        "positive_x": rng.uniform(0, 8000, m),
+        "masses": rng.choice([6.94, 145.0, 88.06, 90.08], m),
+        "lognormal": rng.lognormal(0, 4, m) * rng.choice([-1, 1], m),
+        "morton_like": np.concatenate([rng.uniform(-8000, 0, m // 4), rng.uniform(0, 8000, m // 4),
+                                       rng.uniform(-8000, 0, m // 4), rng.uniform(0, 8000, m // 4)]),
+        "tiny": rng.uniform(-1e-30, 1e-30, 50_000),
+        "halves": rng.choice([0.5, 1.5, -0.5, 2.5, 0.25], m),
+        "with_inf": np.concatenate([rng.uniform(0, 1, 5000), [np.inf], rng.uniform(0, 1, 5000)]),
+        "zeros": np.zeros(10_000),
+        "cancelling": np.tile([1e6, -1e6, 3.0, -3.0], 20_000),
+    }
+
+
+@pytest.mark.parametrize("name", list(_strict_cases()))
+def test_strict_block_functions_equal_the_serial_f32_sum(name):
+    """strict_logic.cuh (what strict_blockfn_kernel / strict_compose_kernel run per block): the running f32 sum
+    of quadtree.rs:114-139 evaluated block-wise under a speculated binade, with the serial fall-back, gives
+    the bits of the plain loop for every input, block size and starting value."""
+    emu = Emu()
+    a = _strict_cases()[name]
+    for block in (512, 64, 7):
+        for s0 in (0.0, 12345.678, -1e9):
+            out, blocks, fallbacks = emu.strict_sum(a, block, s0)
+            bits = out.view(np.uint32)
+            assert bits[0] == bits[1] == bits[2], (name, block, s0, out)
+    if name in ("positive_x", "masses", "ones"):  # a monotone sum leaves its binade ~24 times, whatever its length
+        _, blocks, fallbacks = emu.strict_sum(a, 512, 0.0)
+        assert fallbacks <= 40 and blocks > 500

@@ -17,7 +17,7 @@ for gen, n in ((electrolyte, 30_011), (clustered, 20_003)):
     b = Bodies(bd["pos"], vel=bd.get("vel"), mass=bd["mass"], radius=bd["radius"], charge=bd["charge"],
                species=bd["species"], ebody=bd.get("ebody"), erel=bd.get("erel"))
     for mode in (1, 2, 0):
-        sim = Simulation(b, bd["hw"], bd["hh"], parity_mode=mode)
+        sim = Simulation(b, bd["hw"], bd["hh"], parity_mode=mode, strict_centres=(mode != 0))
         sim.config.coulomb_constant = float(KE)
         for _ in range(2):
             sim.step_device()
