@@ -6,11 +6,15 @@ A "step" = one pass of the hot path over the whole body set, in Simulation::step
 attract, LJ / repulsion / stack pressure, integrator, domain-bounded quadtree build, electron field
 sampling + drift.  Metric: Mparticles/s = bodies / step time (BASELINE.json).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--bodies BODIES] [--theta T]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config {2,3,4,5}] [--bodies BODIES] [--theta T]
   python bench.py --impl reference ...    # the C++ restatement of the reference's rayon path on the host cores
 
-Workload at N=1: BASELINE.json configs[3], "N=16M uniform electrolyte with electron polarization
+Default workload (--config 4): BASELINE.json configs[3], "N=16M uniform electrolyte with electron polarization
 field sampling" (the configuration the 100x target is quoted on); theta is the reference default 1.0.
+--config 2 / 3 / 5 run BASELINE.json configs[1] / [2] / [4] (1 M uniform +-1 charges at theta 0.5, Coulomb only;
+4 M clustered with LJ; 64 M mixed-species slab with the out-of-plane integrator) through the same code.
+Node centres are the reference's serial f32 sums (psim_config.strict_centres = 1), so the timed mode is the one
+whose fields meet the 1e-5 bar against the strict oracle; the line carries that parity figure ("parity").
 Timing: CUDA events on the stream the kernels are launched on, W warm-up steps, K timed steps between
 barrier + synchronize, max over ranks.  The body set (16 M x ~140 B of device state plus ~28 M tree nodes)
 is far larger than the 126 MB L2, so no explicit L2 flush is needed between steps.
@@ -104,13 +108,38 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def make_workload(n, seed=0xC0FFEE):
-    from helpers import electrolyte
-    return electrolyte(n, seed=seed)
+# BASELINE.json configs[1..4] (SURVEY.md 8d "Config 2..5"); configs[0] is the reference's CPU-only scenario
+CONFIGS = {
+    2: dict(gen="uniform_pm1", n=1_000_000, theta=0.5, short=False, electrons=False, iterate=False,
+            name="configs[1]: uniform random +-1 charges, Coulomb-only Barnes-Hut step (build + field)"),
+    3: dict(gen="clustered", n=4_000_000, theta=1.0, short=True, electrons=False, iterate=False,
+            name="configs[2]: clustered / dendrite-like LithiumMetal + electrolyte (deep unbalanced tree): build + field "
+                 "+ cell list + polar + LJ"),
+    4: dict(gen="electrolyte", n=16_000_000, theta=1.0, short=True, electrons=True, iterate=True,
+            name="configs[3]: uniform electrolyte (Li+/PF6-/EC/DMC 342:342:2393:2394), electron polarization "
+                 "field sampling, full hot-path step"),
+    5: dict(gen="slab", n=64_000_000, theta=1.0, short=True, electrons=True, iterate=True,
+            name="configs[4]: mixed-species slab (20 % LLZO/LLZT/S40B scaffold, 5 % LithiumMetal, 75 % electrolyte), "
+                 "2.5-D out-of-plane integrator, full hot-path step"),
+}
+
+
+def make_workload(n, seed=0xC0FFEE, gen="electrolyte"):
+    import helpers
+    return getattr(helpers, gen)(n, seed=seed)
+
+
+def host_threads():
+    """every core this process may run on (torchrun exports OMP_NUM_THREADS=1; the reference's rayon pool would
+    still use all of them)"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step(bodies, theta, threads, steps=1, warmup=0, variant="native", all_parallel=False):
+def cpu_reference_step(bodies, theta, threads, steps=1, warmup=0, variant="native", all_parallel=False, cfg=None):
     """One hot-path step with the oracle, structured like the reference: rayon-parallel field / iterate
     / tree build workers, SERIAL propagate, LJ, repulsion and electron loop (as in the reference).
     all_parallel also runs the electron loop on every thread (reported beside the reference-shaped
@@ -123,20 +152,29 @@ def cpu_reference_step(bodies, theta, threads, steps=1, warmup=0, variant="nativ
     except Exception:
         variant = ""
     from helpers import oracle_for
+    cfg = cfg or CONFIGS[4]
     o = oracle_for(bodies, theta=theta, variant=variant)
     hw, hh = bodies["hw"], bodies["hh"]
+    oop = bool(bodies.get("enable_out_of_plane", False))
     T = threads
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         o.reset_acc()
-        o.prepare_spatial_structures(hw, hh, threads=T)
+        if cfg["short"]:
+            o.prepare_spatial_structures(hw, hh, threads=T)
+        else:
+            o.build(threads=T)
         o.attract(KE, threads=T)
-        o.apply_lj_forces(True)
-        o.apply_repulsive_forces(True)
-        o.iterate(5.0, 1.0, hw, hh, 1.0, False, threads=T)
-        o.build_with_domain(hw, hh, threads=T)
-        o.update_electrons((0.0, 0.0), 5.0, KE, threads=T if all_parallel else 1)
+        if cfg["short"]:
+            o.apply_polar_forces(KE, True, 1)   # serial in the reference (forces.rs:52-175)
+            o.apply_lj_forces(True)
+            o.apply_repulsive_forces(True)
+        if cfg["iterate"]:
+            o.iterate(5.0, 1.0, hw, hh, float(bodies.get("hd", 1.0)), oop, threads=T)
+        if cfg["electrons"]:
+            o.build_with_domain(hw, hh, threads=T)
+            o.update_electrons((0.0, 0.0), 5.0, KE, threads=T if all_parallel else 1)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
@@ -146,7 +184,10 @@ def cpu_reference_step(bodies, theta, threads, steps=1, warmup=0, variant="nativ
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  The Rust crate cannot be
     built in this image (no cargo, un-vendored quarkstrom), so this is the C++ restatement (oracle/),
-    kind "port", with every host thread the reference's rayon pool would use."""
+    kind "port", with every host thread the reference's rayon pool would use, on the SAME body set as the
+    GPU arm (same generator, same n, same seed).  A 16 M-body step is ~30 s of CPU work, so the number of
+    timed steps is capped by a wall-clock budget (reported as "steps"); the first step is never a warm-up
+    casualty: if the budget allows a warm-up step it is taken, otherwise the timed steps include first touch."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -156,40 +197,83 @@ def run_reference(args):
         variant = "native"
     except Exception:
         variant = ""
-    threads = pyoracle.load(variant).orc_max_threads()
-    # bounded sample: a smaller instance of the same generator, sized so K + W steps take ~2 minutes
-    n_probe = min(args.n, 100_000)
-    t_probe, _ = cpu_reference_step(make_workload(n_probe), args.theta, threads, 1, 0, variant)
-    per_body = t_probe / n_probe
-    budget = 120.0 / max(1, args.steps + args.warmup)
-    n_s = int(min(args.n, max(100_000, min(2_000_000, budget / (per_body * 1.3)))))
-    bodies = make_workload(n_s)
-    t_step, _ = cpu_reference_step(bodies, args.theta, threads, args.steps, args.warmup, variant)
-    value = n_s / t_step / 1e6
+    cfg = CONFIGS[args.config]
+    threads = host_threads()
+    n_probe = min(args.n, 200_000)
+    t_probe, _ = cpu_reference_step(make_workload(n_probe, gen=cfg["gen"]), args.theta, threads, 1, 0, variant, cfg=cfg)
+    est = t_probe / n_probe * args.n * 1.25  # N log N growth + cache effects
+    budget = float(args.ref_budget_s)
+    steps = int(max(1, min(args.steps, budget // max(est, 1e-3))))
+    warmup = int(min(args.warmup, 1)) if est * (steps + 1) <= budget * 1.25 else 0
+    bodies = make_workload(args.n, gen=cfg["gen"])
+    t_step, _ = cpu_reference_step(bodies, args.theta, threads, steps, warmup, variant, cfg=cfg)
+    value = args.n / t_step / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
+        "steps": steps, "warmup": warmup, "requested": {"steps": args.steps, "warmup": args.warmup},
+        "ms_per_step": t_step * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, n_s),
+        "config": workload_config(args, args.n),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{n_s}-body instance of the same generator (full {args.n} would take minutes per step); "
-                                   "C++ restatement of the reference's rayon path: parallel field/iterate/build workers, "
-                                   "serial propagate, LJ and electron loop as in the reference"},
+                         "sample": f"the full {args.n}-body set of the GPU arm (same generator and seed), {steps} timed "
+                                   f"step(s) of ~{t_step:.0f} s inside a {budget:.0f} s budget; C++ restatement of the "
+                                   "reference's rayon path: parallel field / iterate / build workers on all host cores, "
+                                   "serial propagate, polar, LJ and electron loop as in the reference"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
 def workload_config(args, n):
-    return {"workload": "configs[3]: uniform electrolyte (Li+/PF6-/EC/DMC 342:342:2393:2394), electron polarization "
-                        "field sampling, full hot-path step", "n_bodies": int(n), "theta": args.theta, "epsilon": 2.0,
+    cfg = CONFIGS[args.config]
+    return {"workload": cfg["name"], "n_bodies": int(n), "theta": args.theta, "epsilon": 2.0,
             "leaf_capacity": 1, "density_per_A2": 0.0625, "seed": "0xC0FFEE", "parity_mode": int(args.ieee),
-            "l2": "working set >> 126 MB L2, no flush needed", "parallelism": f"morton-sharded x{args.gpus}",
+            "strict_centres": int(args.strict), "do_polar": int(cfg["short"]),
+            "l2": "device working set (bodies 2 x 61 B + 4 n node slots x ~185 B) >> 126 MB L2, no flush needed",
+            "parallelism": f"morton-sharded x{args.gpus}",
             "multi_gpu_build": "n/a" if args.gpus == 1 else ("replicated" if args.replicated_build else
                                                             "sharded by key range (65536 top-level cells), tree pieces all-gathered")}
 
 
 # ------------------------------------------------------------------------------------------------
+def parity_block(sim, bd, cfg, args, threads):
+    """Field of the timed configuration against the oracle on the SAME bodies (north star: rel-L2 <= 1e-5 at the
+    same theta, bit-exact permutation): the strict oracle (the reference restatement with its serial f32 node-centre
+    sums), the f64-centre variant, and an FP64 direct sum on a sample of targets."""
+    from helpers import KE, oracle_for, rel_l2
+    n = len(bd["pos"])
+    sim._call("psim_build", 0, 0.0, 0.0)
+    sim._call("psim_field", float(KE), 0.0, 0.0, 0, None, None)
+    e_dev = np.zeros((n, 2), np.float32)
+    orig = np.zeros(n, np.uint32)
+    pos = np.zeros((n, 2), np.float32)
+    radius = np.zeros(n, np.float32)
+    sim._call("psim_download_bodies", pos.ctypes.data, None, None, None, None, None, None, radius.ctypes.data, None,
+              None, e_dev.ctypes.data, orig.ctypes.data)
+    out = {"mode": f"strict_centres={int(args.strict)}, parity_mode={int(args.ieee)}", "n": int(n), "theta": args.theta,
+           "quantity": "e_field of Quadtree::field after Quadtree::build, all bodies"}
+    for key, variant in (("rel_l2_vs_strict", ""), ("rel_l2_vs_f64centre", "hp")):
+        t0 = time.perf_counter()
+        o = oracle_for(bd, theta=args.theta, variant=variant)
+        o.build(threads=threads)
+        e_ref, _ = o.field(KE, threads=threads)
+        same = bool(np.array_equal(o.permutation(), orig.astype(np.int64)))
+        out[key] = rel_l2(e_dev, e_ref) if same else None
+        if variant == "":
+            out["permutation_equal"] = same
+            rng = np.random.default_rng(7)
+            pick = rng.choice(n, min(n, 256), replace=False)
+            direct = o.direct_f64(pos[pick], target_radius=radius[pick], k_e=float(KE), epsilon=2.0, threads=threads)
+            out["rel_l2_vs_direct_f64"] = rel_l2(e_dev[pick], direct)
+            out["oracle_rel_l2_vs_direct_f64"] = rel_l2(e_ref[pick], direct)
+            out["direct_sample"] = int(len(pick))
+        out.setdefault("oracle_seconds", {})[variant or "strict"] = round(time.perf_counter() - t0, 1)
+        del o
+    out["note"] = ("rel_l2_vs_strict is the bar (<= 1e-5); rel_l2_vs_direct_f64 is the Barnes-Hut truncation error at this "
+                   "theta and must equal the oracle's")
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -202,20 +286,24 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cfg = CONFIGS[args.config]
     n = args.n
-    bd = make_workload(n)
+    bd = make_workload(n, gen=cfg["gen"])
     hw, hh = bd["hw"], bd["hh"]
     stream = torch.cuda.current_stream().cuda_stream
-    b = Bodies(bd["pos"], vel=bd["vel"], mass=bd["mass"], radius=bd["radius"], charge=bd["charge"],
-               species=bd["species"], ebody=bd["ebody"], erel=bd["erel"])
+    b = Bodies(bd["pos"], z=bd.get("z"), vel=bd.get("vel"), mass=bd["mass"], radius=bd["radius"], charge=bd["charge"],
+               species=bd["species"], ebody=bd.get("ebody"), erel=bd.get("erel"))
     if world > 1:
         from particlesim_b200.parallel import ShardedSimulation
         sim = ShardedSimulation(b, hw, hh, theta=args.theta, parity_mode=int(args.ieee), device=local_rank,
                                 stream=stream, rank=rank, world=world, local_build=not args.replicated_build)
     else:
-        sim = Simulation(b, hw, hh, theta=args.theta, parity_mode=int(args.ieee), device=local_rank, stream=stream)
+        sim = Simulation(b, hw, hh, domain_depth=float(bd.get("hd", 1.0)), theta=args.theta, parity_mode=int(args.ieee),
+                         device=local_rank, stream=stream, strict_centres=bool(args.strict))
     sim.config.coulomb_constant = float(KE)
-    params = sim.step_params()
+    sim.config.enable_out_of_plane = bool(bd.get("enable_out_of_plane", False))
+    params = sim.step_params(do_short_range=cfg["short"], do_electrons=cfg["electrons"], do_iterate=cfg["iterate"],
+                             do_polar=cfg["short"])
 
     def barrier():
         if world > 1:
@@ -229,7 +317,6 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    phase_ms = np.zeros((args.steps, 8), np.float64)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -282,55 +369,85 @@ def run_ours(args):
         t_field = phase["quadtree_field"] * 1e-3
         achieved = flops / t_field / 1e12
         st = sim.stats()
+        peaks = measured_peaks()
+        sm_max = float((clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0)
         line["roofline"] = {
             "kernel": "bh_group_bodies_kernel", "bound": "fp32",
             "achieved": achieved, "peak": float(tf.value), "unit": "TFLOP/s", "frac": achieved / float(tf.value),
             "traffic": ncu_traffic(n),
             "peak_source": "measured live: FP32 FMA microbenchmark on this GPU (MEASURED_PEAKS.json holds HBM and bf16 "
                            "tensor peaks only; the traversal is FP32-pipe bound and uses no tensor cores, SURVEY.md 8d)",
+            "peak_formula": {"value": 2 * 128 * int(sms.value) * sm_max * 1e6 / 1e12,
+                             "rule": f"2 flops x 128 FP32 lanes x {int(sms.value)} SMs x {sm_max:.0f} MHz"},
             "algorithmic": {"node_visits_per_body": visits / n, "monopoles_per_body": accepted / n,
                             "direct_terms_per_body": pairs / n, "flops_per_body": flops / n,
                             "rule": "12 flops per opening test + 14 per monopole or direct term (SURVEY.md 8d)",
                             "warp_steps_per_32_bodies": wsteps / ((n + 31) // 32)},
             "avg_launch_ms": phase["quadtree_field"],
-            "algorithmic_bytes": int(st["compact_nodes"] * 0 + n * (16 + 8 + 16)),
+            "algorithmic_bytes": int(n * (16 + 8 + 16)),
         }
-        # HBM roofline of the build pipeline (keys, sort, gather, nodes, aggregation), for the explanation
-        peaks = measured_peaks()
+        # HBM roofline of the build pipeline (keys, sort, gather, nodes, aggregation)
         hbm = float(peaks.get("hbm_gbs", 6650.0))
         M = st["compact_nodes"]
-        # keys 16 r + 16 w; radix passes on the upper key word 4 + 4 x 16; sorted keys + run fix-up 28; body
-        # gather 2 x 61; levels 2 + node scan 4 + emit 16 r; per node: records 32 + 4 + 4, sums 64, compaction 48
-        build_bytes = n * (16 + 16 + 4 + 4 * 16 + 28 + 2 * 61 + 2 + 4 + 16) + M * (32 + 4 + 4 + 64 + 48)
-        line["roofline_build"] = {"bound": "hbm", "achieved": build_bytes / (phase["quadtree_build"] * 1e-3) / 1e9,
-                                  "peak": hbm, "unit": "GB/s",
-                                  "frac": build_bytes / (phase["quadtree_build"] * 1e-3) / 1e9 / hbm,
+        d_sig = int(st["max_depth"])
+        passes = -(-2 * d_sig // 8)
+        # keygen 16, sort 8 + passes x 2 x 12 with passes = ceil(2 D_sig / 8), gather 32, nodes M x (32 + 16)
+        survey_bytes = n * (16 + 8 + 24 * passes + 32) + M * 48
+        # what this pipeline moves: keys 16 r + 16 w; radix passes on the upper key word 4 + 4 x 16; sorted keys + run
+        # fix-up 28; body gather 2 x 61; levels 2 + node scan 4 + emit 16 r; per node: records 32 + 4 + 4, sums 64, compaction 48
+        model_bytes = n * (16 + 16 + 4 + 4 * 16 + 28 + 2 * 61 + 2 + 4 + 16) + M * (32 + 4 + 4 + 64 + 48)
+        t_build = phase["quadtree_build"] * 1e-3
+        line["roofline_build"] = {"bound": "hbm", "achieved": survey_bytes / t_build / 1e9, "peak": hbm, "unit": "GB/s",
+                                  "frac": survey_bytes / t_build / 1e9 / hbm,
                                   "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                                  "bytes_per_body": build_bytes / n}
+                                  "bytes_per_body": survey_bytes / n,
+                                  "rule": f"SURVEY.md 8d algorithmic bytes with the measured M = {M} nodes and D_sig = {d_sig} "
+                                          f"({passes} 8-bit passes over 12-byte pairs)",
+                                  "own_traffic_model": {"bytes_per_body": model_bytes / n,
+                                                        "frac": model_bytes / t_build / 1e9 / hbm}}
+        if cfg["short"] and phase["forces_lj"] > 0.02:
+            # short_range_kernel (+ the polar pass): SURVEY.md 8d puts cell build + LJ at ~350 B per body
+            t_sr = (phase["forces_lj"] + phase["cell_list_rebuild"]) * 1e-3
+            line["roofline_short_range"] = {"bound": "hbm", "kernels": "cell_id / onesweep / cell_ranges / polar / short_range",
+                                            "achieved": 350.0 * n / t_sr / 1e9, "peak": hbm, "unit": "GB/s",
+                                            "frac": 350.0 * n / t_sr / 1e9 / hbm, "bytes_per_body": 350.0,
+                                            "ms": t_sr * 1e3}
         line["tree"] = {"compact_nodes": int(M), "reference_nodes": int(st["reference_nodes"]), "max_depth": int(st["max_depth"])}
 
-        # ---- the same step with the other traversal arithmetic, for the explanation ------------------
+        # ---- the same step in the other modes, for the explanation -----------------------------------
+        def timed_steps(k=5):
+            for _ in range(2):
+                sim.step_device(params)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(k):
+                sim.step_device(params)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / k
+
         other = 0 if args.ieee else 1
         sim._cfg.parity_mode = other
         sim._call("psim_set_config", C.byref(sim._cfg))
-        for _ in range(2):
-            sim.step_device(params)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(min(args.steps, 5)):
-            sim.step_device(params)
-        e1.record()
-        torch.cuda.synchronize()
-        ms_other = e0.elapsed_time(e1) / min(args.steps, 5)
+        ms_other = timed_steps(min(args.steps, 5))
         line["other_arithmetic"] = {"parity_mode": other, "ms_per_step": ms_other, "value": n / ms_other / 1e3, "unit": UNIT,
                                     "note": "parity_mode 1 = IEEE div/sqrt, no FMA contraction (the reference's per-term "
                                             "arithmetic); parity_mode 0 = MUFU rsqrt/rcp + FMA on the same interaction sets"}
         sim._cfg.parity_mode = int(args.ieee)
+        sim._cfg.strict_centres = 0 if args.strict else 1
+        sim._call("psim_set_config", C.byref(sim._cfg))
+        ms_centres = timed_steps(min(args.steps, 5))
+        line["other_centres"] = {"strict_centres": int(sim._cfg.strict_centres), "ms_per_step": ms_centres,
+                                 "value": n / ms_centres / 1e3, "unit": UNIT,
+                                 "note": "strict_centres 1 = node centres by the reference's serial f32 sums (bit-identical "
+                                         "nodes, fields within 1e-5 of the reference); 0 = f64 sums carried up the tree "
+                                         "(faster, ~1e-4 from the reference: its own summation noise)"}
+        sim._cfg.strict_centres = int(args.strict)
         sim._call("psim_set_config", C.byref(sim._cfg))
 
         # ---- e2e: host buffers in, host buffers out, every step -------------------------------------
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        h_pos, h_vel, h_q = pin(bd["pos"]), pin(bd["vel"]), pin(bd["charge"])
+        h_pos, h_vel, h_q = pin(bd["pos"]), pin(b.vel), pin(bd["charge"])
         o_pos, o_vel = torch.empty_like(h_pos).pin_memory(), torch.empty_like(h_vel).pin_memory()
         o_ef = torch.empty_like(h_pos).pin_memory()
         o_orig = torch.empty(n, dtype=torch.int32).pin_memory()
@@ -374,6 +491,10 @@ def run_ours(args):
                        "host_cache": "256 MB scratch write before each timed call (evicts the 60 MB CPU LLC)",
                        "unpipelined_ms_per_step": t_seq * 1e3,
                        "unpipelined_api": "psim_update_state + psim_step + psim_download_bodies"}
+        # ---- parity of the timed mode against the oracle, same bodies ---------------------------------
+        if not args.no_parity:
+            sim.upload()  # back to the generator's state (the e2e steps moved the bodies)
+            line["parity"] = parity_block(sim, bd, cfg, args, host_threads())
         sim.close()
         # ---- CPU baseline on a bounded sample --------------------------------------------------------
         if not args.no_cpu:
@@ -383,11 +504,11 @@ def run_ours(args):
                 variant = "native"
             except Exception:
                 variant = ""
-            threads = pyoracle.load(variant).orc_max_threads()
+            threads = host_threads()
             n_s = min(n, args.cpu_n)
-            w_s = make_workload(n_s)
-            t_cpu, _ = cpu_reference_step(w_s, args.theta, threads, 1, 0, variant)
-            t_par, _ = cpu_reference_step(w_s, args.theta, threads, 1, 0, variant, all_parallel=True)
+            w_s = bd if n_s == n else make_workload(n_s, gen=cfg["gen"])
+            t_cpu, _ = cpu_reference_step(w_s, args.theta, threads, 1, 0, variant, cfg=cfg)
+            t_par, _ = cpu_reference_step(w_s, args.theta, threads, 1, 0, variant, all_parallel=True, cfg=cfg)
             line["cpu_baseline"] = {"value": n_s / t_cpu / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
                                     "all_parallel_value": n_s / t_par / 1e6,
                                     "all_parallel_note": "same step with the electron loop on every thread too (the "
@@ -455,8 +576,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--bodies", dest="n", type=int, default=16_000_000)
-    ap.add_argument("--theta", type=float, default=1.0)
+    ap.add_argument("--config", type=int, default=4, choices=sorted(CONFIGS),
+                    help="SURVEY.md 8d config number: 2 = BASELINE configs[1] ... 5 = configs[4]; default 4 (16 M electrolyte)")
+    ap.add_argument("--bodies", dest="n", type=int, default=None)
+    ap.add_argument("--theta", type=float, default=None)
+    ap.add_argument("--strict", type=int, default=1,
+                    help="1 (default): node centres by the reference's serial f32 sums (psim_config.strict_centres); "
+                         "0: f64 sums carried up the tree")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed mode")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0,
+                    help="--impl reference: wall-clock budget for the timed CPU steps on the full body set")
     ap.add_argument("--ieee", type=int, default=0,
                     help="1: traversal with IEEE div/sqrt and no FMA contraction (parity_mode 1) instead of the default "
                          "MUFU rsqrt/rcp arithmetic (parity_mode 0); both sum the reference's interaction sets and "
@@ -467,6 +596,10 @@ def main():
     ap.add_argument("--replicated-build", action="store_true",
                     help="multi-GPU: every rank builds the whole tree (the v1 scheme) instead of its key range")
     args = ap.parse_args()
+    if args.n is None:
+        args.n = CONFIGS[args.config]["n"]
+    if args.theta is None:
+        args.theta = CONFIGS[args.config]["theta"]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -57,10 +57,12 @@ typedef struct {
   float stack_pressure_decay;
   uint32_t parity_mode;     /* 1: IEEE sqrt/div, reference operation order (default); 0: fast math */
   float node_factor;        /* node arena = node_factor * max_bodies + 1024 compact nodes (default 4) */
-  uint32_t strict_centres;  /* 1: recompute every internal node's centre with the reference's serial f32
-                               running sums over its body range (quadtree.rs:114-139) - bit-identical to the
-                               reference for leaf_capacity 1, O(N depth) with one thread per node, so slow
-                               for large N; 0 (default): f64 sums carried up the tree */
+  uint32_t strict_centres;  /* 1 (default): every internal node's centre is the reference's serial f32 running
+                               sum over its body range (quadtree.rs:114-139), evaluated in parallel but bit for
+                               bit (csrc/strict.cuh) - node centres equal the reference's for leaf_capacity 1
+                               and fields meet the 1e-5 bar against it; 0: f64 sums carried up the tree
+                               (~10 % faster builds, fields ~1e-4 from the reference: its own summation noise).
+                               Sharded builds (psim_shard_phase) support 0 only. */
   uint32_t reserved[4];
 } psim_config;
 
@@ -170,6 +172,15 @@ int32_t psim_field(psim_ctx *ctx, float k_e, float bg_x, float bg_y, int32_t wri
  * Quadtree::field_at_point (quadtree.rs:504-507) */
 int32_t psim_acc_points(psim_ctx *ctx, uint64_t m, const float *pts_xy, const float *q_opt,
                         const float *radius_opt, float k_e, float *out_xy);
+/* Electron hopping, the field part of the candidate predicate (simulation/electron_hopping.rs:283-329), batched:
+ * m_src donors (indices in the current body order), their candidate acceptors in CSR form (pair_offsets[m_src + 1]
+ * into dst_idx).  For every donor: local_field = (bg_x, bg_y) + Quadtree::field_at_point(bodies[src].pos)
+ * (:290-295, one Barnes-Hut walk per donor instead of one per candidate); for every pair:
+ * alignment = max(0, -hop_dir . field_dir) (1 if the field vanishes) * max(alignment_bias, 0), raised to 0.5 on a
+ * metal / electrode conduction path (:301-328).  out_local_field_xy may be NULL.  Needs a tree (psim_build). */
+int32_t psim_hop_alignment(psim_ctx *ctx, uint64_t m_src, const uint32_t *src_idx, const uint32_t *pair_offsets,
+                           const uint32_t *dst_idx, float k_e, float bg_x, float bg_y, float alignment_bias,
+                           float *out_local_field_xy, float *out_alignment);
 /* the loop at simulation.rs:1186-1196 over Body::update_electrons (body/electron.rs:19-46) */
 int32_t psim_update_electrons(psim_ctx *ctx, float bg_x, float bg_y, float dt, float k_e);
 

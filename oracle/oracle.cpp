@@ -1358,6 +1358,36 @@ void orc_direct_f64(const OrcSim *s, uint64_t m, const float *pts_xy, const floa
   }
 }
 
+// simulation/electron_hopping.rs:283-329: what the hopping loop computes per candidate before the rate tests
+void orc_hop_alignment(const OrcSim *s, uint64_t m_src, const uint32_t *src_idx, const uint32_t *pair_offsets,
+                       const uint32_t *dst_idx, float k_e, float bg_x, float bg_y, float alignment_bias,
+                       float *local_field_xy, float *alignment) {
+  auto electrode = [](uint8_t sp) { return sp >= 13 && sp <= 20; };             // :312-315
+  auto metal_or_electrode = [&](uint8_t sp) { return sp == 1 || sp == 2 || electrode(sp); };  // :316-320
+  for (uint64_t i = 0; i < m_src; ++i) {
+    const auto &src = s->bodies[src_idx[i]];
+    for (uint32_t k = pair_offsets[i]; k < pair_offsets[i + 1]; ++k) {
+      const auto &dst = s->bodies[dst_idx[k]];
+      const V2 hop_vec = dst.pos - src.pos;                                                    // :284
+      const V2 hop_dir = mag(hop_vec) > 1e-6f ? normalized(hop_vec) : v2(0.0f, 0.0f);           // :285-289
+      const V2 local_field = v2(bg_x, bg_y) + s->qt.acc_pos(src.pos, 1.0f, 0.0f, s->bodies, k_e, nullptr);  // :290-295
+      const V2 field_dir = mag(local_field) > 1e-6f ? normalized(local_field) : v2(0.0f, 0.0f); // :296-300
+      float a = rmax(-(hop_dir.x * field_dir.x + hop_dir.y * field_dir.y), 0.0f);              // :301
+      if (field_dir.x == 0.0f && field_dir.y == 0.0f) a = 1.0f;                                 // :302-304
+      a = a * rmax(alignment_bias, 0.0f);                                                       // :305-307
+      const bool both = metal_or_electrode(src.species) && metal_or_electrode(dst.species);     // :323
+      const bool involves = electrode(src.species) || electrode(dst.species);                   // :324
+      if (both && involves) a = rmax(a, 0.5f);                                                  // :326-329
+      alignment[k] = a;
+      if (local_field_xy) local_field_xy[2 * i] = local_field.x, local_field_xy[2 * i + 1] = local_field.y;
+    }
+    if (local_field_xy && pair_offsets[i] == pair_offsets[i + 1]) {
+      const V2 lf = v2(bg_x, bg_y) + s->qt.acc_pos(src.pos, 1.0f, 0.0f, s->bodies, k_e, nullptr);
+      local_field_xy[2 * i] = lf.x, local_field_xy[2 * i + 1] = lf.y;
+    }
+  }
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -156,6 +156,11 @@ void orc_enforce_metal_z_boundaries(OrcSim *, float max_z, float hw, float hh, f
 void orc_direct_f64(const OrcSim *, uint64_t m, const float *pts_xy, const float *target_radius,
                     double k_e, double epsilon, double *out_xy, int threads);
 
+/* simulation/electron_hopping.rs:283-329, the field part of the candidate predicate for a batch of (donor, acceptor)
+ * pairs in CSR form; local_field_xy may be NULL */
+void orc_hop_alignment(const OrcSim *, uint64_t m_src, const uint32_t *src_idx, const uint32_t *pair_offsets,
+                       const uint32_t *dst_idx, float k_e, float bg_x, float bg_y, float alignment_bias,
+                       float *local_field_xy, float *alignment);
 int orc_max_threads(void);
 /* 1 if Vec2::mag_sq/dot were compiled as mul_add (ORC_UV_FMA), else 0 */
 int orc_uv_fma(void);

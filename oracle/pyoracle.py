@@ -123,6 +123,7 @@ def load(variant: str = "") -> C.CDLL:
         "orc_get_surrounded": (None, [vp, vp, vp, vp]),
         "orc_enforce_metal_z_boundaries": (None, [vp, f, f, f, f]),
         "orc_direct_f64": (None, [vp, u64, pf, pf, C.c_double, C.c_double, pd, i]),
+        "orc_hop_alignment": (None, [vp, u64, vp, vp, vp, f, f, f, f, vp, vp]),
         "orc_max_threads": (i, []),
         "orc_uv_fma": (i, []),
     }
@@ -322,6 +323,19 @@ class OracleSim:
 
     def iterate(self, dt, damping_base, hw, hh, hd=1.0, enable_out_of_plane=False, threads=0):
         self.lib.orc_iterate(self.h, dt, damping_base, hw, hh, hd, int(enable_out_of_plane), threads)
+
+    def hop_alignment(self, src_idx, candidates, k_e, bg=(0.0, 0.0), alignment_bias=1.0):
+        """simulation/electron_hopping.rs:283-329 per candidate: (local_field per donor, alignment per candidate)"""
+        src = np.ascontiguousarray(src_idx, np.uint32)
+        off = np.zeros(len(src) + 1, np.uint32)
+        off[1:] = np.cumsum([len(c) for c in candidates])
+        dst = (np.ascontiguousarray(np.concatenate([np.asarray(c, np.uint32) for c in candidates]), np.uint32)
+               if len(src) and off[-1] else np.zeros(0, np.uint32))
+        field = np.zeros((len(src), 2), np.float32)
+        al = np.zeros(int(off[-1]), np.float32)
+        self.lib.orc_hop_alignment(self.h, len(src), src.ctypes.data, off.ctypes.data, dst.ctypes.data, k_e, bg[0], bg[1],
+                                   alignment_bias, field.ctypes.data, al.ctypes.data)
+        return field, [al[off[i]:off[i + 1]] for i in range(len(src))]
 
     def update_electrons(self, bg, dt, k_e, threads=1):
         self.lib.orc_update_electrons(self.h, bg[0], bg[1], dt, k_e, threads)

@@ -13,6 +13,7 @@
 
 #include "../../include/psim_b200.h"
 #include "cells.cuh"
+#include "hopping.cuh"
 #include "polar.cuh"
 #include "sort.cuh"
 #include "traverse.cuh"
@@ -189,6 +190,19 @@ int32_t fail(psim_ctx* c, int32_t code, const char* what, cudaError_t e = cudaSu
   } while (0)
 
 #define LAUNCHED(ctx) ((ctx)->launches++)
+
+// Every entry point runs on its context's device, whatever device the calling thread had current (a host
+// thread may own one context per GPU), and leaves the caller's current device as it found it.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) cudaSetDevice(device); else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
 
 template <typename T>
 cudaError_t dalloc(T** p, size_t count) {
@@ -1138,6 +1152,7 @@ void psim_default_config(psim_config* cfg) {
   cfg->stack_pressure_decay = 1.0f;
   cfg->parity_mode = 1;
   cfg->node_factor = 4.0f;
+  cfg->strict_centres = 1;      // node centres by the reference's own serial f32 sums (quadtree.rs:114-139)
 }
 
 void psim_default_species_table(psim_species* rows21) {
@@ -1247,18 +1262,21 @@ int32_t psim_set_config(psim_ctx* ctx, const psim_config* cfg) {
 
 int32_t psim_set_stream(psim_ctx* ctx, uint64_t cuda_stream) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
   return PSIM_OK;
 }
 
 int32_t psim_sync(psim_ctx* ctx) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   CK(cudaStreamSynchronize(ctx->stream));
   return PSIM_OK;
 }
 
 int32_t psim_reset_counters(psim_ctx* ctx) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   ctx->launches = 0;
   CK(cudaMemsetAsync(ctx->step_counter, 0, sizeof(unsigned long long), ctx->stream));
   return PSIM_OK;
@@ -1266,6 +1284,7 @@ int32_t psim_reset_counters(psim_ctx* ctx) {
 
 int32_t psim_field_counters(psim_ctx* ctx, uint64_t* out4) {
   if (!ctx || !out4) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   if (!ctx->tree_valid) return fail(ctx, PSIM_E_STATE, "psim_field_counters: no tree");
   out4[0] = out4[1] = out4[2] = out4[3] = 0;
   if (ctx->n == 0) return PSIM_OK;
@@ -1287,6 +1306,7 @@ int32_t psim_field_counters(psim_ctx* ctx, uint64_t* out4) {
 
 int32_t psim_fp32_peak(psim_ctx* ctx, float* tflops, int32_t* sm_count) {
   if (!ctx || !tflops) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   float* d = nullptr;
   CK(cudaMalloc(&d, sizeof(float)));
   cudaEvent_t e0, e1;
@@ -1314,6 +1334,7 @@ int32_t psim_fp32_peak(psim_ctx* ctx, float* tflops, int32_t* sm_count) {
 
 int32_t psim_stats_get(psim_ctx* ctx, psim_stats* out) {
   if (!ctx || !out) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   memset(out, 0, sizeof(*out));
   int32_t rc = fetch_meta(ctx);
   if (rc) return rc;
@@ -1339,6 +1360,7 @@ int32_t psim_stats_get(psim_ctx* ctx, psim_stats* out) {
 
 int32_t psim_upload_species_table(psim_ctx* ctx, const psim_species* rows, uint32_t nrows) {
   if (!ctx || !rows || nrows == 0 || nrows > kMaxSpecies) return fail(ctx, PSIM_E_ARG, "species table: 1..32 rows");
+  DeviceGuard guard(ctx->device);
   memset(ctx->table_h, 0, sizeof(ctx->table_h));
   memcpy(ctx->table_h, rows, nrows * sizeof(SpeciesRow));
   ctx->nspecies = nrows;
@@ -1351,6 +1373,7 @@ int32_t psim_upload_bodies(psim_ctx* ctx, uint64_t n, const float* pos_xy, const
                            const float* vz, const float* mass, const float* radius, const float* charge,
                            const uint8_t* species) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   if (n > ctx->cap_bodies) return fail(ctx, PSIM_E_ARG, "psim_upload_bodies: n exceeds max_bodies");
   if (n && !pos_xy) return fail(ctx, PSIM_E_ARG, "psim_upload_bodies: pos_xy is null");
   cudaStream_t st = ctx->stream;
@@ -1358,6 +1381,7 @@ int32_t psim_upload_bodies(psim_ctx* ctx, uint64_t n, const float* pos_xy, const
   ctx->m = 0;
   ctx->tgt_set = ctx->etgt_set = false;
   ctx->tree_valid = ctx->grid_valid = ctx->perm_valid = false;
+  ctx->host_map_valid = false;  // the hosted-step row map (psim_step_host) belongs to the previous body set
   if (n == 0) return PSIM_OK;
   // layout of the staging buffer: pos | vel | z | vz | mass | radius | charge | species
   const size_t o_pos = 0, o_vel = o_pos + align256(8 * n), o_z = o_vel + align256(8 * n),
@@ -1401,6 +1425,8 @@ int32_t psim_upload_bodies(psim_ctx* ctx, uint64_t n, const float* pos_xy, const
 
 int32_t psim_update_positions(psim_ctx* ctx, uint64_t n, const float* pos_xy) {
   if (!ctx || n != ctx->n || (n && !pos_xy)) return fail(ctx, PSIM_E_ARG, "psim_update_positions: size mismatch");
+  DeviceGuard guard(ctx->device);
+  ctx->host_map_valid = false;
   if (n == 0) return PSIM_OK;
   int32_t rc = ensure_stage(ctx, 8 * n);
   if (rc) return rc;
@@ -1414,6 +1440,8 @@ int32_t psim_update_positions(psim_ctx* ctx, uint64_t n, const float* pos_xy) {
 
 int32_t psim_update_charges(psim_ctx* ctx, uint64_t n, const float* charge) {
   if (!ctx || n != ctx->n || (n && !charge)) return fail(ctx, PSIM_E_ARG, "psim_update_charges: size mismatch");
+  DeviceGuard guard(ctx->device);
+  ctx->host_map_valid = false;
   if (n == 0) return PSIM_OK;
   int32_t rc = ensure_stage(ctx, 4 * n);
   if (rc) return rc;
@@ -1427,6 +1455,7 @@ int32_t psim_update_charges(psim_ctx* ctx, uint64_t n, const float* charge) {
 
 int32_t psim_upload_electrons(psim_ctx* ctx, uint64_t m, const uint32_t* body, const float* rel_xy, const float* vel_xy) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   CK(cudaStreamSynchronize(ctx->stream));  // the copies below are synchronous and must not overtake queued work
   if (m > ctx->cap_elec) return fail(ctx, PSIM_E_ARG, "psim_upload_electrons: m exceeds max_electrons");
   if (m && (!body || !rel_xy)) return fail(ctx, PSIM_E_ARG, "psim_upload_electrons: null array");
@@ -1466,8 +1495,10 @@ int32_t psim_download_bodies(psim_ctx* ctx, float* pos_xy, float* z, float* vel_
                              float* az, float* mass, float* radius, float* charge, uint8_t* species,
                              float* e_field_xy, uint32_t* orig_index) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   const uint64_t n = ctx->n;
   if (n == 0) return PSIM_OK;
+  ctx->host_map_valid = false;  // the caller now holds the device's row order
   cudaStream_t st = ctx->stream;
   const size_t o_pos = 0, o_vel = o_pos + align256(8 * n), o_acc = o_vel + align256(8 * n),
                o_z = o_acc + align256(8 * n), o_vz = o_z + align256(4 * n), o_az = o_vz + align256(4 * n),
@@ -1503,6 +1534,7 @@ int32_t psim_download_bodies(psim_ctx* ctx, float* pos_xy, float* z, float* vel_
 
 int32_t psim_download_electrons(psim_ctx* ctx, uint32_t* body, float* rel_xy, float* vel_xy) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   const uint64_t m = ctx->m;
   if (m == 0) return PSIM_OK;
   const int e = ctx->ecur;
@@ -1515,6 +1547,7 @@ int32_t psim_download_electrons(psim_ctx* ctx, uint32_t* body, float* rel_xy, fl
 
 int32_t psim_build(psim_ctx* ctx, int32_t mode, float hw, float hh) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   if (mode != PSIM_BUILD_CONTAINING && mode != PSIM_BUILD_DOMAIN) return fail(ctx, PSIM_E_ARG, "psim_build: mode");
   int32_t rc = build_async(ctx, mode, hw, hh);
   if (rc) return rc;
@@ -1524,6 +1557,7 @@ int32_t psim_build(psim_ctx* ctx, int32_t mode, float hw, float hh) {
 
 int32_t psim_build_async(psim_ctx* ctx, int32_t mode, float hw, float hh) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   if (mode != PSIM_BUILD_CONTAINING && mode != PSIM_BUILD_DOMAIN) return fail(ctx, PSIM_E_ARG, "psim_build: mode");
   int32_t rc = build_async(ctx, mode, hw, hh);
   if (rc) return rc;
@@ -1533,11 +1567,13 @@ int32_t psim_build_async(psim_ctx* ctx, int32_t mode, float hw, float hh) {
 
 int32_t psim_build_status(psim_ctx* ctx) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   return check_build(ctx);
 }
 
 int32_t psim_get_permutation(psim_ctx* ctx, uint32_t* out) {
   if (!ctx || !out) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   if (!ctx->perm_valid && ctx->n) return fail(ctx, PSIM_E_STATE, "psim_get_permutation: no build since the last upload");
   CK(cudaStreamSynchronize(ctx->stream));
   if (ctx->n) CK(cudaMemcpy(out, ctx->perm, (size_t)ctx->n * 4, cudaMemcpyDeviceToHost));
@@ -1546,6 +1582,7 @@ int32_t psim_get_permutation(psim_ctx* ctx, uint32_t* out) {
 
 int32_t psim_get_keys(psim_ctx* ctx, uint64_t* out) {
   if (!ctx || !out) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   if (!ctx->perm_valid && ctx->n) return fail(ctx, PSIM_E_STATE, "psim_get_keys: no build since the last upload");
   if (ctx->sh.tree_is_sharded) return fail(ctx, PSIM_E_STATE, "psim_get_keys: the last build was sharded (each rank holds its own keys only)");
   if (!ctx->n) return PSIM_OK;
@@ -1556,6 +1593,7 @@ int32_t psim_get_keys(psim_ctx* ctx, uint64_t* out) {
 
 int32_t psim_download_nodes(psim_ctx* ctx, psim_node* out, uint64_t cap, uint64_t* count) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   if (!ctx->perm_valid && ctx->n) return fail(ctx, PSIM_E_STATE, "psim_download_nodes: no tree");
   if (ctx->sh.tree_is_sharded)
     return fail(ctx, PSIM_E_STATE, "psim_download_nodes: the last build was sharded (each rank holds its piece of the node array only)");
@@ -1604,6 +1642,7 @@ int32_t psim_download_nodes(psim_ctx* ctx, psim_node* out, uint64_t cap, uint64_
 
 int32_t psim_field(psim_ctx* ctx, float k_e, float bg_x, float bg_y, int32_t write_acc, float* out_e, float* out_acc) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   int32_t rc = field_async(ctx, k_e, bg_x, bg_y, write_acc);
   if (rc) return rc;
   CK(cudaGetLastError());
@@ -1616,6 +1655,7 @@ int32_t psim_field(psim_ctx* ctx, float k_e, float bg_x, float bg_y, int32_t wri
 int32_t psim_acc_points(psim_ctx* ctx, uint64_t m, const float* pts_xy, const float* q, const float* radius,
                         float k_e, float* out_xy) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   if (m == 0) return PSIM_OK;
   if (!pts_xy || !out_xy || m >= (1ull << 30)) return fail(ctx, PSIM_E_ARG, "psim_acc_points: null array or m too large");
   const size_t o_p = 0, o_q = o_p + align256(8 * m), o_r = o_q + align256(4 * m), o_o = o_r + align256(4 * m),
@@ -1637,8 +1677,49 @@ int32_t psim_acc_points(psim_ctx* ctx, uint64_t m, const float* pts_xy, const fl
   return PSIM_OK;
 }
 
+int32_t psim_hop_alignment(psim_ctx* ctx, uint64_t m_src, const uint32_t* src_idx, const uint32_t* pair_offsets,
+                           const uint32_t* dst_idx, float k_e, float bg_x, float bg_y, float alignment_bias,
+                           float* out_local_field_xy, float* out_alignment) {
+  if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
+  if (m_src == 0) return PSIM_OK;
+  if (!src_idx || !pair_offsets || m_src >= (1ull << 30)) return fail(ctx, PSIM_E_ARG, "psim_hop_alignment: null array or too many donors");
+  const uint64_t np = pair_offsets[m_src];
+  if (np >= (1ull << 31) || (np && (!dst_idx || !out_alignment))) return fail(ctx, PSIM_E_ARG, "psim_hop_alignment: pair arrays");
+  if (!ctx->tree_valid) return fail(ctx, PSIM_E_STATE, "psim_hop_alignment: no tree (call psim_build first)");
+  const uint32_t m = (uint32_t)m_src;
+  const size_t o_src = 0, o_off = o_src + align256(4 * m_src), o_dst = o_off + align256(4 * (m_src + 1)),
+               o_pts = o_dst + align256(4 * np), o_fld = o_pts + align256(8 * m_src), o_loc = o_fld + align256(8 * m_src),
+               o_al = o_loc + align256(8 * m_src), total = o_al + align256(4 * np);
+  int32_t rc = ensure_qstage(ctx, total);
+  if (rc) return rc;
+  char* sb = static_cast<char*>(ctx->qstage);
+  cudaStream_t st = ctx->stream;
+  BodyArrays& b = ctx->b[ctx->cur];
+  CK(cudaMemcpyAsync(sb + o_src, src_idx, 4 * m_src, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(sb + o_off, pair_offsets, 4 * (m_src + 1), cudaMemcpyHostToDevice, st));
+  if (np) CK(cudaMemcpyAsync(sb + o_dst, dst_idx, 4 * np, cudaMemcpyHostToDevice, st));
+  hop_points_kernel<<<grid_for(ctx, m, 256, 8), 256, 0, st>>>(b.pqr, reinterpret_cast<const uint32_t*>(sb + o_src), m, ctx->n,
+                                                              reinterpret_cast<float2*>(sb + o_pts));
+  LAUNCHED(ctx);
+  rc = points_async(ctx, reinterpret_cast<const float2*>(sb + o_pts), nullptr, nullptr, m, k_e,
+                    reinterpret_cast<float2*>(sb + o_fld));
+  if (rc) return rc;
+  hop_alignment_kernel<<<grid_for(ctx, m, 128, 8), 128, 0, st>>>(
+      b.pqr, b.species, reinterpret_cast<const uint32_t*>(sb + o_src), reinterpret_cast<const uint32_t*>(sb + o_off),
+      reinterpret_cast<const uint32_t*>(sb + o_dst), m, ctx->n, reinterpret_cast<const float2*>(sb + o_fld), bg_x, bg_y,
+      alignment_bias, reinterpret_cast<float2*>(sb + o_loc), reinterpret_cast<float*>(sb + o_al));
+  LAUNCHED(ctx);
+  CK(cudaGetLastError());
+  if (out_local_field_xy) CK(cudaMemcpyAsync(out_local_field_xy, sb + o_loc, 8 * m_src, cudaMemcpyDeviceToHost, st));
+  if (np) CK(cudaMemcpyAsync(out_alignment, sb + o_al, 4 * np, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return PSIM_OK;
+}
+
 int32_t psim_update_electrons(psim_ctx* ctx, float bg_x, float bg_y, float dt, float k_e) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   int32_t rc = electrons_async(ctx, bg_x, bg_y, dt, k_e);
   if (rc) return rc;
   CK(cudaGetLastError());
@@ -1647,6 +1728,7 @@ int32_t psim_update_electrons(psim_ctx* ctx, float bg_x, float bg_y, float dt, f
 
 int32_t psim_cell_build(psim_ctx* ctx, float hw, float hh, float cell_size) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   int32_t rc = cell_build_async(ctx, hw, hh, cell_size);
   if (rc) return rc;
   CK(cudaGetLastError());
@@ -1655,6 +1737,7 @@ int32_t psim_cell_build(psim_ctx* ctx, float hw, float hh, float cell_size) {
 
 int32_t psim_cell_download(psim_ctx* ctx, uint64_t* gx, uint64_t* gy, uint32_t* offsets, uint32_t* indices) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   if (!ctx->grid_valid) return fail(ctx, PSIM_E_STATE, "psim_cell_download: no cell grid");
   if (gx) *gx = ctx->grid.gx;
   if (gy) *gy = ctx->grid.gy;
@@ -1679,6 +1762,7 @@ int32_t psim_cell_download(psim_ctx* ctx, uint64_t* gx, uint64_t* gy, uint32_t* 
 int32_t psim_neighbors_within(psim_ctx* ctx, uint64_t m, const uint32_t* body_idx, float cutoff, int32_t metals_only,
                               uint32_t* offsets, uint32_t* indices, uint64_t indices_cap, uint64_t* total) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   if (!ctx->grid_valid) return fail(ctx, PSIM_E_STATE, "psim_neighbors_within: no cell grid");
   if (total) *total = 0;
   if (m == 0) {
@@ -1725,6 +1809,7 @@ int32_t psim_neighbors_within(psim_ctx* ctx, uint64_t m, const uint32_t* body_id
 
 int32_t psim_reset_acc(psim_ctx* ctx) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   if (ctx->n == 0) return PSIM_OK;
   reset_acc_kernel<<<grid_for(ctx, ctx->n, 256, 16), 256, 0, ctx->stream>>>(ctx->b[ctx->cur].accm, ctx->n);
   LAUNCHED(ctx);
@@ -1734,6 +1819,7 @@ int32_t psim_reset_acc(psim_ctx* ctx) {
 
 int32_t psim_use_cell_list(const psim_ctx* ctx, float hw, float hh, float density_threshold) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   const float area = (2.0f * hw) * (2.0f * hh);  // simulation.rs:1798-1802
   const float density = (float)ctx->n / area;
   return density > density_threshold ? 1 : 0;
@@ -1741,6 +1827,7 @@ int32_t psim_use_cell_list(const psim_ctx* ctx, float hw, float hh, float densit
 
 int32_t psim_prepare_spatial_structures(psim_ctx* ctx, float hw, float hh, float density_threshold) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   int32_t rc = build_async(ctx, PSIM_BUILD_CONTAINING, 0.f, 0.f);
   if (rc) return rc;
   // forces.rs:17-24.  Below the density threshold the reference answers neighbour queries from the
@@ -1759,6 +1846,7 @@ int32_t psim_prepare_spatial_structures(psim_ctx* ctx, float hw, float hh, float
 
 int32_t psim_short_range(psim_ctx* ctx, uint32_t flags) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   int32_t rc = short_range_async(ctx, flags);
   if (rc) return rc;
   CK(cudaGetLastError());
@@ -1767,6 +1855,7 @@ int32_t psim_short_range(psim_ctx* ctx, uint32_t flags) {
 
 int32_t psim_apply_polar_forces(psim_ctx* ctx, float k_e, int32_t dipole_model) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   if (dipole_model != 0 && dipole_model != 1) return fail(ctx, PSIM_E_ARG, "psim_apply_polar_forces: dipole_model");
   int32_t rc = polar_async(ctx, k_e, dipole_model);
   if (rc) return rc;
@@ -1776,6 +1865,7 @@ int32_t psim_apply_polar_forces(psim_ctx* ctx, float k_e, int32_t dipole_model) 
 
 int32_t psim_iterate(psim_ctx* ctx, float dt, float damping_base, float hw, float hh, float hd, int32_t enable_z) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   int32_t rc = iterate_async(ctx, dt, damping_base, hw, hh, hd, enable_z);
   if (rc) return rc;
   CK(cudaGetLastError());
@@ -1855,6 +1945,7 @@ static int32_t step_async(psim_ctx* ctx, const psim_step_params* p) {
 
 int32_t psim_step(psim_ctx* ctx, const psim_step_params* p) {
   if (!ctx || !p) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   return step_async(ctx, p);
 }
 
@@ -1873,6 +1964,7 @@ int32_t psim_step_host(psim_ctx* ctx, const psim_step_params* p, uint64_t n, con
                        const float* vel_xy, const float* charge, float* out_pos_xy, float* out_vel_xy,
                        float* out_e_field_xy, uint32_t* out_orig_index) {
   if (!ctx || !p) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   if (n != ctx->n || (n && !pos_xy)) return fail(ctx, PSIM_E_ARG, "psim_step_host: size mismatch");
   if (ctx->tgt_set || ctx->etgt_set) return fail(ctx, PSIM_E_STATE, "psim_step_host: not available on a sharded context");
   if (n == 0) return step_async(ctx, p);
@@ -1940,6 +2032,7 @@ int32_t psim_step_host(psim_ctx* ctx, const psim_step_params* p, uint64_t n, con
 
 int32_t psim_set_target_range(psim_ctx* ctx, uint64_t first, uint64_t count) {
   if (!ctx || first > ctx->n || count > ctx->n - first) return fail(ctx, PSIM_E_ARG, "psim_set_target_range: out of range");
+  DeviceGuard guard(ctx->device);
   ctx->tgt_set = true, ctx->tgt_first = (uint32_t)first, ctx->tgt_count = (uint32_t)count;
   return PSIM_OK;
 }
@@ -1961,6 +2054,7 @@ int32_t psim_device_ptrs(psim_ctx* ctx, uint64_t* out8) {
 int32_t psim_update_surrounded_flags(psim_ctx* ctx, float hw, float hh, uint64_t frame, float radius_factor,
                                      uint64_t neighbor_threshold) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   if (ctx->n == 0) return PSIM_OK;  // simulation.rs:1894-1896
   const float neighbor_radius = max_lj_cutoff(ctx);
   if (!(neighbor_radius > 0.0f)) return fail(ctx, PSIM_E_ARG, "psim_update_surrounded_flags: no LJ species (cell size 0)");
@@ -1981,6 +2075,7 @@ int32_t psim_update_surrounded_flags(psim_ctx* ctx, float hw, float hh, uint64_t
 
 int32_t psim_get_surrounded(psim_ctx* ctx, uint8_t* flags, float* last_pos_xy, uint64_t* last_frame) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   const uint64_t n = ctx->n;
   if (n == 0) return PSIM_OK;
   const size_t o_f = 0, o_p = o_f + align256(n), o_l = o_p + align256(8 * n), total = o_l + align256(8 * n);
@@ -2001,6 +2096,7 @@ int32_t psim_get_surrounded(psim_ctx* ctx, uint8_t* flags, float* last_pos_xy, u
 
 int32_t psim_enforce_metal_z_boundaries(psim_ctx* ctx, float max_z, float hw, float hh) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   if (!isfinite(max_z) || max_z <= 0.0f) return PSIM_OK;            // out_of_plane.rs:142-145
   if (ctx->n == 0 || !(ctx->species_present & 0x6u)) return PSIM_OK;  // no metals: :147-154
   const float metal_max_r = fmaxf(ctx->table_h[1].radius, ctx->table_h[2].radius);
@@ -2017,6 +2113,7 @@ int32_t psim_enforce_metal_z_boundaries(psim_ctx* ctx, float max_z, float hw, fl
 int32_t psim_shard_init(psim_ctx* ctx, uint32_t rank, uint32_t world) {
   if (!ctx || world < 1 || world > (uint32_t)kMaxRanks || rank >= world)
     return fail(ctx, PSIM_E_ARG, "psim_shard_init: rank / world (at most 64 ranks)");
+  DeviceGuard guard(ctx->device);
   auto& S = ctx->sh;
   if (!S.binhist) {
     bool ok = true;
@@ -2036,6 +2133,7 @@ int32_t psim_shard_init(psim_ctx* ctx, uint32_t rank, uint32_t world) {
 }
 int32_t psim_shard_phase(psim_ctx* ctx, int32_t phase, int32_t mode, float hw, float hh, uint32_t* out) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   if (mode != PSIM_BUILD_CONTAINING && mode != PSIM_BUILD_DOMAIN) return fail(ctx, PSIM_E_ARG, "psim_shard_phase: mode");
   return shard_phase(ctx, phase, mode, hw, hh, out);
 }
@@ -2050,12 +2148,14 @@ int32_t psim_shard_ptrs(psim_ctx* ctx, uint64_t* out8) {
 }
 int32_t psim_mark_positions_changed(psim_ctx* ctx) {
   if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   ctx->tree_valid = ctx->grid_valid = false;
   return PSIM_OK;
 }
 
 int32_t psim_phase_times(psim_ctx* ctx, float* ms8) {
   if (!ctx || !ms8) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
   for (int k = 0; k < PSIM_NUM_PHASES; ++k) ms8[k] = 0.0f;
   if (!ctx->ev_recorded) return fail(ctx, PSIM_E_STATE, "psim_phase_times: no psim_step recorded");
   CK(cudaEventSynchronize(ctx->ev[7]));
@@ -2066,6 +2166,8 @@ int32_t psim_phase_times(psim_ctx* ctx, float* ms8) {
 
 int32_t psim_update_state(psim_ctx* ctx, uint64_t n, const float* pos_xy, const float* vel_xy, const float* charge) {
   if (!ctx || n != ctx->n || (n && !pos_xy)) return fail(ctx, PSIM_E_ARG, "psim_update_state: size mismatch");
+  DeviceGuard guard(ctx->device);
+  ctx->host_map_valid = false;  // rows are in the device's order from here on
   if (n == 0) return PSIM_OK;
   const size_t o_pos = 0, o_vel = align256(8 * n), o_q = o_vel + align256(8 * n), total = o_q + align256(4 * n);
   int32_t rc = ensure_stage(ctx, total);

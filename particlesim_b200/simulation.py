@@ -180,7 +180,7 @@ class Simulation:
     def __init__(self, bodies: Bodies, domain_width, domain_height, domain_depth=1.0, dt=5.0,
                  theta=1.0, epsilon=2.0, leaf_capacity=1, thread_capacity=1024, config: SimConfig | None = None,
                  device=0, parity_mode=True, node_factor=4.0, species_table=None, max_bodies=None,
-                 max_electrons=None, stream=0, strict_centres=False):
+                 max_electrons=None, stream=0, strict_centres=True):
         self.lib = _lib.load()
         self.bodies = bodies
         self.domain_width, self.domain_height, self.domain_depth = float(domain_width), float(domain_height), float(domain_depth)
@@ -351,13 +351,28 @@ class Simulation:
         self._call("psim_enforce_metal_z_boundaries", np.float32(max_z), self.domain_width, self.domain_height)
         self.download(("z", "vz"))
 
+    def hop_alignment(self, src_idx, candidates, alignment_bias=1.0):
+        """simulation/electron_hopping.rs:283-329 for a batch: `candidates[i]` lists the acceptor indices of donor
+        src_idx[i] (current body order).  Returns (local_field per donor, list of alignment arrays)."""
+        src = np.ascontiguousarray(src_idx, np.uint32)
+        off = np.zeros(len(src) + 1, np.uint32)
+        off[1:] = np.cumsum([len(c) for c in candidates])
+        dst = np.ascontiguousarray(np.concatenate([np.asarray(c, np.uint32) for c in candidates]) if len(src) and off[-1]
+                                   else np.zeros(0, np.uint32), np.uint32)
+        field = np.zeros((len(src), 2), np.float32)
+        al = np.zeros(int(off[-1]), np.float32)
+        bg = self.background_e_field
+        self._call("psim_hop_alignment", len(src), _p(src), _p(off), _p(dst), self.config.coulomb_constant,
+                   bg[0], bg[1], np.float32(alignment_bias), _p(field), _p(al))
+        return field, [al[off[i]:off[i + 1]] for i in range(len(src))]
+
     def update_electrons(self):
         """the loop at simulation.rs:1186-1196 over Body::update_electrons (body/electron.rs:19-46)"""
         self._call("psim_update_electrons", self.background_e_field[0], self.background_e_field[1], self.dt,
                    self.config.coulomb_constant)
         self.download_electrons()
 
-    def step_params(self, do_short_range=True, do_electrons=True, do_iterate=True, do_polar=False) -> "_lib.StepParams":
+    def step_params(self, do_short_range=True, do_electrons=True, do_iterate=True, do_polar=True) -> "_lib.StepParams":
         p = _lib.StepParams()
         p.hw, p.hh, p.hd = self.domain_width, self.domain_height, self.domain_depth
         p.dt, p.damping_base = self.dt, self.config.damping_base

@@ -210,8 +210,8 @@ def _dedupe(pos, rng, L):
 
 def oracle_for(bodies, theta=1.0, epsilon=2.0, leaf=1, thread=1024, variant=""):
     s = OracleSim(theta, epsilon, leaf, thread, variant=variant)
-    s.set_bodies(bodies["pos"], vel=bodies.get("vel"), mass=bodies.get("mass"), radius=bodies.get("radius"),
-                 charge=bodies.get("charge"), species=bodies.get("species"))
+    s.set_bodies(bodies["pos"], z=bodies.get("z"), vel=bodies.get("vel"), mass=bodies.get("mass"),
+                 radius=bodies.get("radius"), charge=bodies.get("charge"), species=bodies.get("species"))
     if "ebody" in bodies:
         s.set_electrons(bodies["ebody"], bodies["erel"])
     return s
@@ -345,3 +345,56 @@ class Emu:
         self.lib.emu_set_params(self.h, theta, epsilon)
         self.lib.emu_walk(self.h, m, p(pts), p(q), p(radius), k_e, p(out), C.byref(steps), C.byref(pairs))
         return out, steps.value, pairs.value
+
+
+def slab(n, seed=SEED, rho=RHO):
+    """config 5: mixed-species slab.  20 % solid-electrolyte scaffold (LLZO / LLZT / S40B, LJ-enabled, neutral) on a
+    jittered 5 A lattice in a central band, 5 % LithiumMetal in two lattice slabs (3.04 A) at the +-x edges, 75 %
+    electrolyte mix (Li+ / PF6- / EC / DMC 342:342:2393:2394) everywhere; z ~ U(-1, 1) for the 2.5-D path."""
+    rng = np.random.default_rng(seed)
+    L = float(np.sqrt(n / rho))
+    n_sc, n_li = n // 5, n // 20
+    n_el = n - n_sc - n_li
+
+    def lattice(count, a, x0, width):
+        """`count` jittered sites of spacing a filling x in [x0, x0 + width), y over the whole height"""
+        nx = max(1, int(width / a))
+        ny = (count + nx - 1) // nx
+        a_y = min(a, L / max(ny, 1))
+        k = np.arange(count)
+        p = np.stack([x0 + (k % nx + 0.5) * a, -L / 2 + (k // nx + 0.5) * a_y], 1)
+        return p + rng.normal(0, 0.05, p.shape)
+
+    w_sc = n_sc * 25.0 / L
+    p_sc = lattice(n_sc, 5.0, -w_sc / 2, w_sc)
+    w_li = (n_li // 2) * 3.04 ** 2 / L
+    p_li = np.concatenate([lattice(n_li // 2, 3.04, -L / 2, w_li), lattice(n_li - n_li // 2, 3.04, L / 2 - w_li, w_li)])
+    p_el = rng.uniform(-L / 2, L / 2, (n_el, 2))
+    pos = np.clip(np.concatenate([p_sc, p_li, p_el]), -L / 2, np.nextafter(np.float32(L / 2), np.float32(0))).astype(np.float32)
+    pos = _dedupe(pos, rng, L)
+    kind = rng.choice(4, size=n_el, p=np.array([342, 342, 2393, 2394]) / 5471.0)
+    sc_species = rng.choice(np.array([9, 10, 11], np.uint8), n_sc)
+    species = np.concatenate([sc_species, np.full(n_li, 1, np.uint8), np.array([0, 3, 4, 5], np.uint8)[kind]])
+    table = {0: (6.94, 0.76), 1: (6.94, 1.52), 3: (145.0, 2.0), 4: (88.06, 2.5), 5: (90.08, 2.5), 9: (840.0, 4.5),
+             10: (865.0, 4.7), 11: (340.0, 4.2)}
+    mass = np.zeros(n, np.float32)
+    radius = np.zeros(n, np.float32)
+    for s, (m, r) in table.items():
+        sel = species == s
+        mass[sel], radius[sel] = m, r
+    charge = np.zeros(n, np.float32)
+    charge[species == 0], charge[species == 3] = 1.0, -1.0
+    polar = np.zeros(n, np.float32)
+    polar[species == 3], polar[species == 4], polar[species == 5] = 0.3, 0.85, 0.60
+    ebody = np.nonzero(polar > 0)[0].astype(np.uint32)
+    ang = rng.uniform(0, 2 * np.pi, len(ebody))
+    rr = np.sqrt(rng.uniform(0, 1, len(ebody))) * polar[ebody] * radius[ebody]
+    erel = np.stack([rr * np.cos(ang), rr * np.sin(ang)], 1).astype(np.float32)
+    sh = rng.permutation(n)
+    inv = np.empty(n, np.int64)
+    inv[sh] = np.arange(n)
+    ebody = np.sort(inv[ebody]).astype(np.uint32)  # electrons keep their body; rel_pos is i.i.d., so re-pairing by rank is fine
+    vel = rng.normal(0, 0.01, (n, 2)).astype(np.float32)
+    z = rng.uniform(-1, 1, n).astype(np.float32)
+    return dict(pos=pos[sh], charge=charge[sh], radius=radius[sh], species=species[sh], mass=mass[sh], vel=vel, z=z,
+                ebody=ebody, erel=erel, hw=L / 2, hh=L / 2, hd=1.0, enable_out_of_plane=True)

@@ -67,3 +67,26 @@ def test_product_does_not_reference_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 # comments may mention the test harness; code must not import or load the oracle
                 assert "pyoracle" not in text and "liboracle" not in text and "oracle/" not in text, f
+
+
+def build_c_smoke():
+    """tests/c/smoke.c -> tests/c/_build/smoke with plain gcc in C99 mode against include/psim_b200.h"""
+    import subprocess
+    from particlesim_b200 import _lib
+    _lib.load()
+    out_dir = os.path.join(ROOT, "tests", "c", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    exe = os.path.join(out_dir, "smoke")
+    libdir = os.path.join(ROOT, "particlesim_b200")
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.run([cc, "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "smoke.c"), "-o", exe, "-L", libdir, "-lpsim_b200",
+                    "-Wl,-rpath," + libdir, "-Wl,-rpath,/usr/local/cuda/lib64"], check=True)
+    return exe
+
+
+def test_header_is_plain_c_and_a_c_client_links():
+    """the boundary is a C ABI: a C99 translation unit includes the header, compiles warning-free and links
+    against libpsim_b200.so (running it needs a GPU: tests/test_gpu_tree.py::test_c_client)"""
+    exe = build_c_smoke()
+    assert os.path.exists(exe)

@@ -31,10 +31,36 @@ def per_target_rel(a, b):
     ("electrolyte_50k", lambda: electrolyte(50_000), 1),
     ("clustered_60k", lambda: clustered(60_000), 0),
 ])
-def test_field_parity(cuda_device, name, gen, mode, theta):
+def test_field_parity_default_mode(cuda_device, name, gen, mode, theta):
+    """the default configuration (strict_centres = 1): <= 1e-5 against the STRICT oracle, the bar of the north star"""
     bodies = gen()
     hw, hh = bodies["hw"], bodies["hh"]
     sim = make_sim(bodies, theta=theta)
+    if mode == 0:
+        sim.quadtree.build(sim.bodies)
+    else:
+        sim.quadtree.build_with_domain(sim.bodies, hw, hh)
+    sim.quadtree.field(sim.bodies, KE)
+    o = oracle_for(bodies, theta=theta)
+    o.build() if mode == 0 else o.build_with_domain(hw, hh)
+    assert np.array_equal(o.permutation(), sim.bodies.id.astype(np.int64))
+    e, _ = o.field(KE)
+    err = rel_l2(sim.bodies.e_field, e)
+    assert err <= TOL, f"rel-L2 vs strict oracle {err:.3e}"
+    sim.close()
+
+
+@pytest.mark.parametrize("theta", [0.5, 1.0])
+@pytest.mark.parametrize("name,gen,mode", [
+    ("uniform_50k", lambda: uniform_pm1(50_000), 0),
+    ("electrolyte_50k", lambda: electrolyte(50_000), 1),
+    ("clustered_60k", lambda: clustered(60_000), 0),
+])
+def test_field_parity(cuda_device, name, gen, mode, theta):
+    """strict_centres = 0 (f64 centre sums), the three comparisons of the module docstring"""
+    bodies = gen()
+    hw, hh = bodies["hw"], bodies["hh"]
+    sim = make_sim(bodies, theta=theta, strict_centres=False)
     if mode == 0:
         sim.quadtree.build(sim.bodies)
     else:
@@ -125,7 +151,7 @@ def test_acc_points_with_charge_and_radius(cuda_device):
     q = rng.uniform(-2, 2, m).astype(np.float32)
     rad = rng.uniform(0, 3, m).astype(np.float32)
     f = sim.quadtree.acc_pos(pts, q, rad, sim.bodies, KE)
-    o = oracle_for(bodies, variant="hp")
+    o = oracle_for(bodies)
     o.build()
     fo, _ = o.acc_points(pts, q=q, radius=rad, k_e=KE)
     assert rel_l2(f, fo) <= TOL
@@ -140,7 +166,8 @@ def test_multi_body_leaves_and_refused_leaves(cuda_device):
     b = uniform_pm1(4000)
     b["pos"][100:104] = b["pos"][100]
     for leaf, thread in [(8, 32), (1, 1024), (4, 3)]:
-        sim = make_sim(b, leaf_capacity=leaf, thread_capacity=thread)
+        # f64 centres on both sides: the running-sum order inside a multi-body leaf is the partition's, not ours
+        sim = make_sim(b, leaf_capacity=leaf, thread_capacity=thread, strict_centres=False)
         sim.quadtree.build(sim.bodies)
         sim.quadtree.field(sim.bodies, KE)
         o = oracle_for(b, leaf=leaf, thread=thread, variant="hp")
@@ -163,7 +190,7 @@ def test_attract_epilogue(cuda_device):
     sim.background_e_field = (0.01, -0.02)
     forces.prepare_spatial_structures(sim)
     forces.attract(sim)
-    o = oracle_for(bodies, variant="hp")
+    o = oracle_for(bodies)
     o.prepare_spatial_structures(bodies["hw"], bodies["hh"])
     o.attract(KE, bg=(0.01, -0.02))
     ob = o.get_bodies()
@@ -178,7 +205,7 @@ def test_reference_order_mode_is_bit_identical(cuda_device):
     the f64-centre oracle and to the reference-order oracle traversing the device's centres"""
     for gen, mode, theta in [(lambda: uniform_pm1(30_000), 0, 0.5), (lambda: electrolyte(30_000), 1, 1.0)]:
         bodies = gen()
-        sim = make_sim(bodies, theta=theta, parity_mode=2)
+        sim = make_sim(bodies, theta=theta, parity_mode=2, strict_centres=False)
         if mode == 0:
             sim.quadtree.build(sim.bodies)
         else:
@@ -201,7 +228,7 @@ def test_fast_math_mode_within_tolerance(cuda_device):
     sim = make_sim(bodies, parity_mode=0)
     sim.quadtree.build(sim.bodies)
     sim.quadtree.field(sim.bodies, KE)
-    o = oracle_for(bodies, variant="hp")
+    o = oracle_for(bodies)
     o.build()
     e, _ = o.field(KE)
     assert rel_l2(sim.bodies.e_field, e) <= TOL
@@ -214,7 +241,7 @@ def test_nonfinite_target_does_not_hang(cuda_device):
     sim.quadtree.build(sim.bodies)
     pts = np.array([[np.nan, 0.0], [np.inf, 1.0], [0.0, 0.0]], np.float32)
     f = sim.quadtree.field_at_point(sim.bodies, pts, KE)
-    o = oracle_for(bodies, variant="hp")
+    o = oracle_for(bodies)
     o.build()
     fo, _ = o.acc_points(pts, k_e=KE)
     assert np.allclose(f[2], fo[2], rtol=1e-5, atol=1e-9)
@@ -252,3 +279,42 @@ def test_strict_centres_reproduce_the_reference_bit_for_bit(cuda_device, name, g
     assert rel_l2(sim2.bodies.e_field, e) <= TOL
     sim.close()
     sim2.close()
+
+
+def test_hop_alignment_batch(cuda_device):
+    """the field part of the hopping candidate predicate (simulation/electron_hopping.rs:283-329)
+    for a batch of (donor, acceptor) pairs - donors' own positions are the sample points (the positional self skip
+    of acc_pos drops the donor itself), metals / electrode materials exercise the conduction-path floor"""
+    bodies = electrolyte(30_000)
+    n = len(bodies["pos"])
+    rng = np.random.default_rng(11)
+    metal = rng.choice(n, 3000, replace=False)
+    bodies["species"][metal[:1500]] = 1           # LithiumMetal
+    bodies["species"][metal[1500:2500]] = 13      # Graphite
+    bodies["species"][metal[2500:]] = 2           # FoilMetal
+    sim = make_sim(bodies)
+    sim.background_e_field = (0.002, -0.001)
+    sim.quadtree.build(sim.bodies)
+    o = oracle_for(bodies)
+    o.build()
+    assert np.array_equal(o.permutation(), sim.bodies.id.astype(np.int64))
+    sp = sim.bodies.species
+    donors = np.nonzero((sp == 1) | (sp == 2) | (sp == 13))[0][:800].astype(np.uint32)
+    # candidates: the cell-list neighbours within the hop radius (hop_radius_factor * radius, electron_hopping.rs:163)
+    sim._call("psim_cell_build", bodies["hw"], bodies["hh"], 11.88)
+    cands = sim._neighbors(donors, 6.0, False)
+    cands = [np.asarray(c, np.uint32) for c in cands]
+    assert sum(len(c) for c in cands) > 1000
+    cands[0] = np.zeros(0, np.uint32)  # a donor without candidates still reports its field
+    f_dev, a_dev = sim.hop_alignment(donors, cands, alignment_bias=1.3)
+    f_ref, a_ref = o.hop_alignment(donors, cands, KE, bg=(0.002, -0.001), alignment_bias=1.3)
+    assert rel_l2(f_dev, f_ref) <= TOL
+    ad, ar = np.concatenate(a_dev), np.concatenate(a_ref)
+    assert np.all(np.isfinite(ad)) and (ar == 0.5).any() and (ar > 0.5).any()
+    assert np.abs(ad - ar).max() <= 2e-5 * 1.3
+    # off-body sample points through the same walk (field_at_point semantics): psim_acc_points with q = 1, radius = 0
+    pts = (sim.bodies.pos[donors] + rng.normal(0, 0.3, (len(donors), 2))).astype(np.float32)
+    f_pts = sim.quadtree.field_at_point(sim.bodies, pts, KE)
+    fo, _ = o.acc_points(pts, k_e=KE)
+    assert rel_l2(f_pts, fo) <= TOL
+    sim.close()

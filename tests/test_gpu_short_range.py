@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
-def both_after_build(bodies, variant="hp", **kw):
+def both_after_build(bodies, variant="", **kw):
     sim = make_sim(bodies, **kw)
     o = oracle_for(bodies, variant=variant)
     sim.quadtree.build(sim.bodies)
@@ -69,7 +69,7 @@ def test_lj_forces(cuda_device):
     from particlesim_b200 import forces
     bodies = clustered(40_000)
     sim = make_sim(bodies)
-    o = oracle_for(bodies, variant="hp")
+    o = oracle_for(bodies)
     hw, hh = bodies["hw"], bodies["hh"]
     sim.reset_acc()
     forces.prepare_spatial_structures(sim)
@@ -97,7 +97,7 @@ def test_repulsion_and_stack_pressure(cuda_device):
     cfg = SimConfig(stack_pressure_enabled=True, stack_pressure=0.5, stack_pressure_decay=30.0)
     sim = make_sim(bodies, config=cfg, species_table=table)
     sim.config.coulomb_constant = float(KE)
-    o = oracle_for(bodies, variant="hp")
+    o = oracle_for(bodies)
     o.set_species_table(table)
     hw, hh = bodies["hw"], bodies["hh"]
     sim.reset_acc()
@@ -133,7 +133,7 @@ def test_iterate(cuda_device, enable_z):
                charge=bodies["charge"], species=bodies["species"])
     sim = Simulation(b, bodies["hw"], bodies["hh"], domain_depth=1.0, dt=5.0, config=cfg)
     sim.config.coulomb_constant = float(KE)
-    o = oracle_for(bodies, variant="hp")
+    o = oracle_for(bodies)
     o.set_bodies(bodies["pos"], z=z, vel=bodies["vel"], vz=vz, mass=bodies["mass"], radius=bodies["radius"],
                  charge=bodies["charge"], species=bodies["species"])
     hw, hh = bodies["hw"], bodies["hh"]
@@ -164,7 +164,7 @@ def test_update_electrons(cuda_device):
     sim.background_e_field = (0.003, 0.001)
     sim.quadtree.build_with_domain(sim.bodies, hw, hh)
     sim.update_electrons()
-    o = oracle_for(bodies, variant="hp")
+    o = oracle_for(bodies)
     o.build_with_domain(hw, hh)
     o.update_electrons((0.003, 0.001), 5.0, KE, threads=0)
     ebody, erel, evel = o.get_electrons()
@@ -175,7 +175,7 @@ def test_update_electrons(cuda_device):
 
 
 def test_fused_step_matches_the_call_sequence(cuda_device):
-    """psim_step == reset_acc, prepare_spatial_structures, attract, LJ, repulsion, stack pressure,
+    """psim_step == reset_acc, prepare_spatial_structures, attract, polar, LJ, repulsion, stack pressure,
     iterate, build_with_domain, update_electrons (simulation.rs:1000-1196) on the oracle"""
     bodies = electrolyte(40_000)
     # make some bodies LJ species so the short-range pass has work
@@ -193,10 +193,11 @@ def test_fused_step_matches_the_call_sequence(cuda_device):
     sim.download_electrons()
     orig = np.zeros(len(sim.bodies), np.uint32)
     sim._call("psim_download_bodies", *([None] * 11), orig.ctypes.data)
-    o = oracle_for(bodies, variant="hp")
+    o = oracle_for(bodies)
     o.reset_acc()
     o.prepare_spatial_structures(hw, hh)
     o.attract(KE)
+    o.apply_polar_forces(KE, True, 1)  # Simulation::step runs it every step (simulation.rs:1007); do_polar defaults to 1
     o.apply_lj_forces(True)
     o.apply_repulsive_forces(True)
     o.iterate(5.0, 1.0, hw, hh, 1.0, False)
@@ -224,7 +225,7 @@ def test_polar_forces(cuda_device, dipole_model):
     bodies = electrolyte(30_000)
     hw, hh = bodies["hw"], bodies["hh"]
     sim = make_sim(bodies)
-    o = oracle_for(bodies, variant="hp")
+    o = oracle_for(bodies)
     sim.reset_acc()
     forces.prepare_spatial_structures(sim)
     forces.attract(sim)
@@ -252,7 +253,7 @@ def test_fused_step_with_polar_forces(cuda_device):
     sim.download(("pos", "vel", "acc"))
     orig = np.zeros(len(sim.bodies), np.uint32)
     sim._call("psim_download_bodies", *([None] * 11), orig.ctypes.data)
-    o = oracle_for(bodies, variant="hp")
+    o = oracle_for(bodies)
     o.reset_acc()
     o.prepare_spatial_structures(hw, hh)
     o.attract(KE)

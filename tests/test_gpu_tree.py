@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from helpers import (KE, Emu, assert_same_topology, canonical_from_nodes, check_next_pointers, clustered,
-                     electrolyte, oracle_for, uniform_pm1)
+                     electrolyte, oracle_for, rel_l2, uniform_pm1)
 
 pytestmark = pytest.mark.gpu
 
@@ -21,7 +21,7 @@ def make_sim(bodies, **kw):
 
 
 def build_both(bodies, mode, leaf=1, thread=1024, variant=""):
-    sim = make_sim(bodies, leaf_capacity=leaf, thread_capacity=thread)
+    sim = make_sim(bodies, leaf_capacity=leaf, thread_capacity=thread, strict_centres=(variant != "hp"))
     o = oracle_for(bodies, leaf=leaf, thread=thread, variant=variant)
     if mode == 0:
         sim.quadtree.build(sim.bodies)
@@ -208,3 +208,36 @@ def test_dense_subcell_clumps_sort_by_the_full_key(cuda_device, clump):
         assert np.array_equal(sim.bodies.id.astype(np.int64), o.permutation())
         assert_same_topology(canonical_from_nodes(sim.quadtree.nodes), o.canonical())
         sim.close()
+
+
+def test_c_client(cuda_device):
+    """the plain-C client (tests/c/smoke.c, gcc -std=c99) gives the numbers of the Python path: same permutation,
+    same sorted positions, same field bits"""
+    import subprocess
+    from test_abi import build_c_smoke
+    exe = build_c_smoke()
+    n = 300
+    res = subprocess.run([exe, str(n)], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr
+    lines = res.stdout.strip().splitlines()
+    assert lines[-1] == "ok"
+    rows = np.array([[float(v) for v in ln.split()] for ln in lines[1:1 + n]])
+    perm = rows[:, 0].astype(np.int64)
+    assert np.array_equal(np.sort(perm), np.arange(n))
+    # the same bodies through the Python mirror: positions regenerated from the C client's output
+    pos = np.zeros((n, 2), np.float32)
+    pos[perm] = rows[:, 1:3].astype(np.float32)
+    idx = np.arange(n)
+    q = np.where(idx % 2 == 1, -1.0, 1.0).astype(np.float32)
+    bodies = dict(pos=pos, charge=q, radius=np.where(idx % 2 == 1, 2.0, 0.76).astype(np.float32),
+                  mass=np.where(idx % 2 == 1, 145.0, 6.94).astype(np.float32), hw=50.0, hh=50.0)
+    sim = make_sim(bodies, theta=0.5)
+    sim.quadtree.build(sim.bodies)
+    sim.quadtree.field(sim.bodies, KE)
+    assert np.array_equal(sim.bodies.id.astype(np.int64), perm)
+    assert np.array_equal(sim.bodies.e_field, rows[:, 3:5].astype(np.float32))
+    o = oracle_for(bodies, theta=0.5)
+    o.build()
+    e, _ = o.field(KE)
+    assert rel_l2(sim.bodies.e_field, e) <= 1e-5
+    sim.close()

@@ -60,8 +60,12 @@ C("psim_reset_counters")
 tf = timed("field+attract", lambda: C("psim_field", float(KE), 0.0, 0.0, 1, None, None))
 st = sim.stats()
 print("warp steps per group:", st["traversal_warp_steps"] / args.reps / ((args.n + 31) // 32))
+C("psim_cell_build", hw, hh, 11.88)
+timed("polar (ConjugatePair)", lambda: C("psim_apply_polar_forces", float(KE), 1))
 if len(b.ebody):
     timed("update_electrons", lambda: C("psim_update_electrons", 0.0, 0.0, 5.0, float(KE)))
+p = sim.step_params(do_polar=False)
+timed("psim_step (no polar)", lambda: sim.step_device(p))
 p = sim.step_params()
 ts = timed("psim_step (full)", lambda: C("psim_step", p.__class__.from_buffer_copy(p)) if False else sim.step_device(p))
 print(f"N={args.n} step {ts:.3f} ms -> {args.n/ts/1e3:.1f} Mparticles/s", flush=True)
