@@ -308,6 +308,25 @@ int32_t psim_enforce_metal_z_boundaries(psim_ctx *ctx, float max_z, float hw, fl
 int32_t psim_shard_init(psim_ctx *ctx, uint32_t rank, uint32_t world);
 int32_t psim_shard_phase(psim_ctx *ctx, int32_t phase, int32_t mode, float hw, float hh, uint32_t *out);
 int32_t psim_shard_ptrs(psim_ctx *ctx, uint64_t *out8);
+/* ---- the same, orchestrated by the library over NCCL (NVLink / NVSwitch) ----------------------------------------
+ * One context per rank, created with max_bodies / max_electrons >= psim_shard_capacity(n, nranks) (slices are padded
+ * to a multiple of 64 bodies so that the 32-target groups of the walk are the single-GPU ones).  Every rank uploads
+ * the same bodies (psim_upload_bodies / psim_upload_electrons), rank 0 makes a 128-byte id with psim_comm_unique_id
+ * and the host distributes it (MPI, a file, torch.distributed ...).  libnccl.so.2 is loaded at run time (the copy
+ * already in the process, else $PSIM_NCCL_LIB, else the system's); failures return PSIM_E_NCCL.
+ *   psim_build_sharded = Quadtree::build / build_with_domain (quadtree.rs:153-195) with each rank building the part
+ *                        of the tree that starts in its key range (the seven phases above + their exchanges);
+ *   psim_step_sharded  = psim_step with both builds sharded, each rank computing field / polar / short-range /
+ *                        integrator for its slice of the Morton order and an equal slice of the electrons, the slices
+ *                        all-gathered in place (positions at once, velocities behind the next build's first phases).
+ * Results are bit-identical to psim_step on one GPU with strict_centres = 0 (the sharded build carries f64 centre
+ * sums).  psim_phase_times works after psim_step_sharded (the exchanges are inside the phases they follow). */
+uint64_t psim_shard_capacity(uint64_t n, uint32_t nranks);
+int32_t psim_comm_unique_id(uint8_t *out128);
+int32_t psim_comm_init(psim_ctx *ctx, const uint8_t *unique_id128, uint32_t rank, uint32_t nranks);
+int32_t psim_comm_destroy(psim_ctx *ctx);
+int32_t psim_build_sharded(psim_ctx *ctx, int32_t mode, float hw, float hh);
+int32_t psim_step_sharded(psim_ctx *ctx, const psim_step_params *p);
 /* the caller wrote positions into the device arrays (e.g. an all-gather): tree and grid are stale */
 int32_t psim_mark_positions_changed(psim_ctx *ctx);
 

@@ -116,6 +116,12 @@ SIGNATURES = {
     "psim_shard_phase": (_i32, [_vp, _i32, _i32, _f, _f, _vp]),
     "psim_shard_ptrs": (_i32, [_vp, _vp]),
     "psim_step": (_i32, [_vp, _vp]),
+    "psim_shard_capacity": (_u64, [_u64, _u32]),
+    "psim_comm_unique_id": (_i32, [_vp]),
+    "psim_comm_init": (_i32, [_vp, _vp, _u32, _u32]),
+    "psim_comm_destroy": (_i32, [_vp]),
+    "psim_build_sharded": (_i32, [_vp, _i32, _f, _f]),
+    "psim_step_sharded": (_i32, [_vp, _vp]),
     "psim_step_host": (_i32, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "psim_phase_times": (_i32, [_vp, _vp]),
     "psim_set_target_range": (_i32, [_vp, _u64, _u64]),

@@ -9,10 +9,12 @@
 
 #include <new>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/psim_b200.h"
 #include "cells.cuh"
+#include "comm.h"
 #include "hopping.cuh"
 #include "polar.cuh"
 #include "sort.cuh"
@@ -117,6 +119,18 @@ struct psim_ctx {
     ShardPlan plan_h = {};
     ShardMeta meta_h = {};
   } sh;
+
+  // multi-GPU communicator (psim_comm_init): NCCL on the context's stream, plus a side stream for the exchanges
+  // that run beside independent device work
+  struct Comm {
+    bool on = false;
+    ncclComm_t comm = nullptr;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_side = nullptr, ev_vel = nullptr;
+    void* stage = nullptr;  // padded all-gather staging
+    size_t stage_bytes = 0;
+    bool vel_pending = false;
+  } comm;
 
   // cells
   uint32_t *cell_start = nullptr, *cell_end = nullptr, *order = nullptr, *body_cell = nullptr;
@@ -1238,6 +1252,7 @@ int32_t psim_destroy(psim_ctx* ctx) {
   if (!ctx) return PSIM_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  psim_comm_destroy(ctx);
   if (ctx->ev_ok)
     for (int k = 0; k < 9; ++k) cudaEventDestroy(ctx->ev[k]);
   if (ctx->copy_in) cudaStreamSynchronize(ctx->copy_in), cudaStreamDestroy(ctx->copy_in);
@@ -1872,6 +1887,173 @@ int32_t psim_iterate(psim_ctx* ctx, float dt, float damping_base, float hw, floa
   return PSIM_OK;
 }
 
+// ---- multi-GPU orchestration (one context per rank; replaces the Python loop of particlesim_b200/parallel.py) -----
+#define NCK(call)                                                                          \
+  do {                                                                                     \
+    ncclResult_t _r = (call);                                                              \
+    if (_r != ncclSuccess) {                                                               \
+      ctx->err = std::string(#call) + ": " + nccl_api().GetErrorString(_r);               \
+      return PSIM_E_NCCL;                                                                  \
+    }                                                                                      \
+  } while (0)
+
+static uint32_t shard_width(uint64_t n, uint32_t world) {  // bodies per rank, a multiple of 64 (two walk groups)
+  return n ? (uint32_t)(((n + world - 1) / world + 63) / 64 * 64) : 0u;
+}
+
+// In-place all-gather of UNEVEN row segments: rank r contributes rows [lo[r], lo[r+1]) of `full` (row_bytes each,
+// `rows_cap` rows allocated).  One ncclAllGather of max-segment blocks into a staging area, then the valid rows of
+// the other ranks are copied into place.
+static int32_t all_gatherv(psim_ctx* ctx, void* full, size_t row_bytes, size_t rows_cap, const uint32_t* lo,
+                           cudaStream_t st) {
+  auto& K = ctx->comm;
+  const uint32_t world = ctx->sh.world, rank = ctx->sh.rank;
+  size_t seg = 0;
+  for (uint32_t r = 0; r < world; ++r) seg = std::max<size_t>(seg, lo[r + 1] - lo[r]);
+  if (seg == 0) return PSIM_OK;
+  seg = (seg + 1023) / 1024 * 1024;
+  const size_t need = (size_t)(world + 1) * seg * row_bytes;
+  if (need > K.stage_bytes) {
+    if (K.stage) {
+      CK(cudaStreamSynchronize(ctx->stream));
+      CK(cudaStreamSynchronize(K.side));
+      cudaFree(K.stage);
+    }
+    K.stage = nullptr, K.stage_bytes = 0;
+    const size_t want = need + need / 4;
+    if (cudaMalloc(&K.stage, want) != cudaSuccess) return fail(ctx, PSIM_E_OOM, "all-gather staging");
+    K.stage_bytes = want;
+  }
+  char* stage = static_cast<char*>(K.stage);
+  char* base = static_cast<char*>(full);
+  const size_t a = lo[rank], cnt = lo[rank + 1] - lo[rank];
+  const char* mine = base + a * row_bytes;
+  if (a + seg > rows_cap) {  // the padded block would run past the array: go through the spare block
+    char* spare = stage + (size_t)world * seg * row_bytes;
+    if (cnt) CK(cudaMemcpyAsync(spare, mine, cnt * row_bytes, cudaMemcpyDeviceToDevice, st));
+    mine = spare;
+  }
+  NCK(nccl_api().AllGather(mine, stage, seg * row_bytes, ncclChar, K.comm, st));
+  for (uint32_t r = 0; r < world; ++r) {
+    const size_t c = lo[r + 1] - lo[r];
+    if (r != rank && c)
+      CK(cudaMemcpyAsync(base + (size_t)lo[r] * row_bytes, stage + (size_t)r * seg * row_bytes, c * row_bytes,
+                         cudaMemcpyDeviceToDevice, st));
+  }
+  return PSIM_OK;
+}
+
+// equal slices of `width` rows, in place (rank r owns rows [r * width, (r + 1) * width))
+static int32_t all_gather_slices(psim_ctx* ctx, void* full, size_t row_bytes, uint32_t width, cudaStream_t st) {
+  if (width == 0) return PSIM_OK;
+  char* base = static_cast<char*>(full);
+  NCK(nccl_api().AllGather(base + (size_t)ctx->sh.rank * width * row_bytes, base, (size_t)width * row_bytes, ncclChar,
+                           ctx->comm.comm, st));
+  return PSIM_OK;
+}
+
+// Quadtree::build / build_with_domain across the communicator: the seven phases of shard_phase with the exchanges
+// between them.  `cell_size` > 0: the cell list is rebuilt while the traversal pieces travel (it only needs the
+// sorted bodies).
+static int32_t build_sharded(psim_ctx* ctx, int mode, float hw, float hh, const psim_step_params* p, float cell_size) {
+  auto& K = ctx->comm;
+  auto& S = ctx->sh;
+  cudaStream_t st = ctx->stream;
+  int32_t rc;
+  uint32_t lo[kMaxRanks + 1], tl[kMaxRanks + 1];
+  if ((rc = shard_phase(ctx, 0, mode, hw, hh, lo))) return rc;
+  if ((rc = shard_phase(ctx, 1, mode, hw, hh, nullptr))) return rc;
+  if ((rc = all_gatherv(ctx, ctx->keys_idx_all, sizeof(uint32_t), ctx->cap_bodies, lo, st))) return rc;
+  if (K.vel_pending) {  // the velocities all-gathered behind the first two phases must be in place before the gather
+    CK(cudaStreamWaitEvent(st, K.ev_vel, 0));
+    K.vel_pending = false;
+  }
+  if ((rc = shard_phase(ctx, 2, mode, hw, hh, nullptr))) return rc;
+  NCK(nccl_api().AllReduce(S.xbuf, S.xbuf, kBins + kMaxRanks, ncclUint64, ncclSum, K.comm, st));
+  if ((rc = shard_phase(ctx, 3, mode, hw, hh, nullptr))) return rc;
+  NCK(nccl_api().AllReduce(S.heap, S.heap, (size_t)kTopSlots * (sizeof(TopRec) / 8), ncclUint64, ncclSum, K.comm, st));
+  if ((rc = shard_phase(ctx, 4, mode, hw, hh, nullptr))) return rc;
+  NCK(nccl_api().AllReduce(S.xbuf, S.xbuf, kBins + kMaxRanks, ncclUint64, ncclSum, K.comm, st));
+  if ((rc = shard_phase(ctx, 5, mode, hw, hh, tl))) return rc;
+  // traversal pieces on the side stream, the cell list on the main one
+  CK(cudaEventRecord(K.ev_main, st));
+  CK(cudaStreamWaitEvent(K.side, K.ev_main, 0));
+  if ((rc = all_gatherv(ctx, ctx->travA, sizeof(float4), ctx->node_cap, tl, K.side))) return rc;
+  if ((rc = all_gatherv(ctx, ctx->travB, sizeof(uint4), ctx->node_cap, tl, K.side))) return rc;
+  CK(cudaEventRecord(K.ev_side, K.side));
+  if (cell_size > 0.0f && p && (rc = cell_build_async(ctx, p->hw, p->hh, cell_size))) return rc;
+  CK(cudaStreamWaitEvent(st, K.ev_side, 0));
+  return shard_phase(ctx, 6, mode, hw, hh, nullptr);
+}
+
+static int32_t step_sharded(psim_ctx* ctx, const psim_step_params* p) {
+  auto& K = ctx->comm;
+  auto& S = ctx->sh;
+  cudaStream_t st = ctx->stream;
+  const uint32_t world = S.world, rank = S.rank, n = ctx->n, m = ctx->m;
+  const uint32_t wb = shard_width(n, world), we = shard_width(m, world);
+  if ((uint64_t)wb * world > ctx->cap_bodies || (m && (uint64_t)we * world > ctx->cap_elec))
+    return fail(ctx, PSIM_E_ARG, "psim_step_sharded: create the context with psim_shard_capacity() bodies / electrons");
+  {  // this rank's targets: a contiguous slice of the Morton order, and an equal slice of the electrons
+    const uint32_t f = std::min(rank * wb, n), c = std::min(wb, n - f);
+    ctx->tgt_set = true, ctx->tgt_first = f, ctx->tgt_count = c;
+    const uint32_t ef = std::min(rank * we, m), ec = std::min(we, m - ef);
+    ctx->etgt_set = true, ctx->e_first = ef, ctx->e_count = ec;
+  }
+  int32_t rc;
+  auto mark = [&](int k) {
+    if (ctx->ev_ok) cudaEventRecord(ctx->ev[k], st);
+  };
+  mark(0);
+  if ((rc = psim_reset_acc(ctx))) return rc;
+  float cell = 0.0f;
+  if (p->do_short_range) {
+    const float lj_cutoff = max_lj_cutoff(ctx), repulsion_cutoff = max_repulsion_cutoff(ctx);
+    cell = p->do_polar ? fmaxf(fmaxf(3.0f * lj_cutoff, repulsion_cutoff), lj_cutoff) : fmaxf(repulsion_cutoff, lj_cutoff);
+  }
+  if ((rc = build_sharded(ctx, PSIM_BUILD_CONTAINING, 0.f, 0.f, p, cell))) return rc;
+  mark(1);
+  mark(2);
+  if ((rc = field_async(ctx, p->k_e, p->bg_x, p->bg_y, 1))) return rc;
+  if (p->do_polar && p->do_short_range && cell > 0.0f && (rc = polar_async(ctx, p->k_e, 1))) return rc;
+  mark(3);
+  if (p->do_short_range && (rc = short_range_async(ctx, PSIM_SR_LJ | PSIM_SR_REPULSION | PSIM_SR_STACK_PRESSURE))) return rc;
+  mark(4);
+  if (p->do_iterate) {
+    if ((rc = iterate_async(ctx, p->dt, p->damping_base, p->hw, p->hh, p->hd, (int)p->enable_out_of_plane))) return rc;
+    BodyArrays& b = ctx->b[ctx->cur];
+    if ((rc = all_gather_slices(ctx, b.pqr, sizeof(float4), wb, st))) return rc;
+    // the velocities are not needed before the next build permutes the bodies: their all-gather runs on the side
+    // stream behind that build's first two phases, which only read positions
+    CK(cudaEventRecord(K.ev_main, st));
+    CK(cudaStreamWaitEvent(K.side, K.ev_main, 0));
+    if ((rc = all_gather_slices(ctx, b.velz, sizeof(float4), wb, K.side))) return rc;
+    CK(cudaEventRecord(K.ev_vel, K.side));
+    K.vel_pending = true;
+    ctx->tree_valid = ctx->grid_valid = false;
+  }
+  mark(5);
+  if (p->do_electrons) {
+    if ((rc = build_sharded(ctx, PSIM_BUILD_DOMAIN, p->hw, p->hh, p, 0.0f))) return rc;
+    mark(6);
+    if ((rc = electrons_async(ctx, p->bg_x, p->bg_y, p->dt, p->k_e))) return rc;
+    if (we) {
+      if ((rc = all_gather_slices(ctx, ctx->erel[ctx->ecur], sizeof(float2), we, st))) return rc;
+      if ((rc = all_gather_slices(ctx, ctx->evel[ctx->ecur], sizeof(float2), we, st))) return rc;
+    }
+  } else {
+    mark(6);
+  }
+  if (K.vel_pending) {
+    CK(cudaStreamWaitEvent(st, K.ev_vel, 0));
+    K.vel_pending = false;
+  }
+  mark(7);
+  ctx->ev_recorded = ctx->ev_ok;
+  CK(cudaGetLastError());
+  return PSIM_OK;
+}
+
 static int32_t step_async(psim_ctx* ctx, const psim_step_params* p) {
   int32_t rc;
   auto mark = [&](int k) {
@@ -2146,6 +2328,69 @@ int32_t psim_shard_ptrs(psim_ctx* ctx, uint64_t* out8) {
   out8[5] = kBins + kMaxRanks, out8[6] = (uint64_t)kTopSlots * (sizeof(TopRec) / 8), out8[7] = ctx->node_cap;
   return PSIM_OK;
 }
+uint64_t psim_shard_capacity(uint64_t n, uint32_t world) { return world ? (uint64_t)shard_width(n, world) * world : n; }
+
+int32_t psim_comm_unique_id(uint8_t* out128) {
+  if (!out128) return PSIM_E_ARG;
+  NcclApi& api = nccl_api();
+  if (!api.ok) return PSIM_E_NCCL;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  if (api.GetUniqueId(&id) != ncclSuccess) return PSIM_E_NCCL;
+  memcpy(out128, &id, 128);
+  return PSIM_OK;
+}
+
+int32_t psim_comm_init(psim_ctx* ctx, const uint8_t* unique_id128, uint32_t rank, uint32_t nranks) {
+  if (!ctx || !unique_id128) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
+  NcclApi& api = nccl_api();
+  if (!api.ok) return fail(ctx, PSIM_E_NCCL, "psim_comm_init: libnccl.so.2 not found (set PSIM_NCCL_LIB)");
+  auto& K = ctx->comm;
+  if (K.on) return fail(ctx, PSIM_E_STATE, "psim_comm_init: the context already has a communicator");
+  int32_t rc = psim_shard_init(ctx, rank, nranks);
+  if (rc) return rc;
+  ncclUniqueId id;
+  memcpy(&id, unique_id128, 128);
+  NCK(api.CommInitRank(&K.comm, (int)nranks, id, (int)rank));
+  CK(cudaStreamCreateWithFlags(&K.side, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&K.ev_main, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&K.ev_side, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&K.ev_vel, cudaEventDisableTiming));
+  K.on = true;
+  return PSIM_OK;
+}
+
+int32_t psim_comm_destroy(psim_ctx* ctx) {
+  if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
+  auto& K = ctx->comm;
+  if (!K.on) return PSIM_OK;
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(K.side);
+  nccl_api().CommDestroy(K.comm);
+  cudaStreamDestroy(K.side);
+  cudaEventDestroy(K.ev_main), cudaEventDestroy(K.ev_side), cudaEventDestroy(K.ev_vel);
+  if (K.stage) cudaFree(K.stage);
+  K = psim_ctx::Comm();
+  return PSIM_OK;
+}
+
+int32_t psim_build_sharded(psim_ctx* ctx, int32_t mode, float hw, float hh) {
+  if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
+  if (!ctx->comm.on) return fail(ctx, PSIM_E_STATE, "psim_build_sharded: call psim_comm_init first");
+  if (mode != PSIM_BUILD_CONTAINING && mode != PSIM_BUILD_DOMAIN) return fail(ctx, PSIM_E_ARG, "psim_build_sharded: mode");
+  return build_sharded(ctx, mode, hw, hh, nullptr, 0.0f);
+}
+
+int32_t psim_step_sharded(psim_ctx* ctx, const psim_step_params* p) {
+  if (!ctx || !p) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
+  if (!ctx->comm.on) return fail(ctx, PSIM_E_STATE, "psim_step_sharded: call psim_comm_init first");
+  return step_sharded(ctx, p);
+}
+
 int32_t psim_mark_positions_changed(psim_ctx* ctx) {
   if (!ctx) return PSIM_E_ARG;
   DeviceGuard guard(ctx->device);

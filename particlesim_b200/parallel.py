@@ -229,7 +229,13 @@ class _DevArray:
 
 
 class ShardedSimulation(Simulation):
-    def __init__(self, bodies, domain_width, domain_height, *, rank: int, world: int, local_build: bool = True, **kw):
+    """One rank of the multi-GPU hot path.  orchestration = "library" (default): psim_comm_init + psim_step_sharded,
+    the library runs the phases and the NCCL exchanges itself (the unique id travels over torch.distributed);
+    "python": the same sequence driven from here through psim_shard_phase and torch.distributed collectives (kept as
+    the readable reference of the protocol and for the comparison in tools/)."""
+
+    def __init__(self, bodies, domain_width, domain_height, *, rank: int, world: int, local_build: bool = True,
+                 orchestration: str = "library", **kw):
         n, m = len(bodies), len(bodies.ebody)
         self.rank, self.world = rank, world
         self.wb, self.we = shard_width(n, world), shard_width(m, world)
@@ -245,7 +251,20 @@ class ShardedSimulation(Simulation):
         self._scratch_e = torch.empty((self.we, 2), dtype=torch.float32, device="cuda")
         self._shard_nb = kw["max_bodies"]
         self.local_build = local_build and world > 1
-        if self.local_build:
+        self.library = orchestration == "library" and self.local_build
+        if self.library:
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                buf = np.zeros(128, np.uint8)
+                rc = self.lib.psim_comm_unique_id(buf.ctypes.data)
+                if rc != 0:
+                    raise _lib.PsimError(rc, "psim_comm_unique_id: NCCL not available")
+                uid = torch.from_numpy(buf)
+            uid = uid.cuda()
+            dist.broadcast(uid, src=0)
+            self._uid = uid.cpu().numpy().copy()
+            self._call("psim_comm_init", self._uid.ctypes.data, rank, world)
+        elif self.local_build:
             self._call("psim_shard_init", rank, world)
             self._comm = DistComm(dist, rank)
         f, c = shard_range(n, world, rank)
@@ -280,6 +299,11 @@ class ShardedSimulation(Simulation):
         at the phase boundaries (see phase_ms)."""
         p = params or self.step_params()
         C = self._call
+        if self.library:
+            import ctypes
+            C("psim_step_sharded", ctypes.byref(p))
+            self._events = None
+            return
         ev = []
 
         def mark():
@@ -299,6 +323,8 @@ class ShardedSimulation(Simulation):
         mark()
         mark()
         C("psim_field", p.k_e, p.bg_x, p.bg_y, 1, None, None)
+        if p.do_polar and do_cells:  # forces::apply_polar_forces (simulation.rs:1007), between attract and the LJ pass
+            C("psim_apply_polar_forces", p.k_e, 1)
         mark()
         if p.do_short_range:
             C("psim_short_range", _lib.SR_LJ | _lib.SR_REPULSION | _lib.SR_STACK_PRESSURE)
@@ -334,6 +360,10 @@ class ShardedSimulation(Simulation):
         """device ms of the phases of the last recorded step (same order as psim_phase_times; the two
         exchanges are inside `iterate` and `electron_updates`)"""
         ev = self._events
+        if ev is None:  # library orchestration: the context's own phase events
+            ph = np.zeros(8, np.float32)
+            self._call("psim_phase_times", ph.ctypes.data)
+            return [float(v) for v in ph]
         self.torch.cuda.synchronize()
         out = [ev[k].elapsed_time(ev[k + 1]) for k in range(7)]
         out.append(ev[0].elapsed_time(ev[7]))

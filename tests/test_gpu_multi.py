@@ -1,0 +1,31 @@
+"""GPU, more than one device: the sharded hot path over REAL NCCL (psim_comm_init + psim_step_sharded, one process per
+GPU under torch.distributed.run) must leave the single-GPU state, bit for bit.  Skipped on a one-GPU box (NCCL refuses
+two ranks on one device); the one-GPU protocol tests are tests/test_gpu_shard.py."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from helpers import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("how", ["library", "python"])
+def test_sharded_steps_over_nccl_equal_single_gpu(cuda_device, how):
+    g = _gpus()
+    if g < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 8 if g >= 8 else (4 if g >= 4 else 2)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.join(ROOT, "tools", "check_sharded.py"),
+           "200001", how]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    print(res.stdout[-3000:], res.stderr[-2000:])
+    assert res.returncode == 0 and "== SINGLE: True" in res.stdout

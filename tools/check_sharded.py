@@ -1,4 +1,6 @@
-"""torchrun --nproc-per-node G tools/check_sharded.py: the sharded step must give the single-GPU result."""
+"""torchrun --nproc-per-node G tools/check_sharded.py [n] [library|python|repl]: three sharded hot-path steps (both
+builds, field, polar, LJ, integrator, electrons) over real NCCL must leave exactly the single-GPU state (same centre
+mode: the sharded build carries f64 centre sums).  Exits non-zero on a mismatch; tests/test_gpu_multi.py runs it."""
 import os
 import sys
 
@@ -41,13 +43,16 @@ def state(sim):
     return pos, vel, orig, eb, er, ev
 
 
-sh = mk(ShardedSimulation, rank=rank, world=world, local_build=not (len(sys.argv) > 2 and sys.argv[2] == "repl"))
+how = sys.argv[2] if len(sys.argv) > 2 else "library"
+sh = mk(ShardedSimulation, rank=rank, world=world, local_build=how != "repl",
+        orchestration="python" if how == "python" else "library")
 for _ in range(3):
     sh.step_device()
 torch.cuda.synchronize()
 a = state(sh)
+ok = True
 if rank == 0:
-    one = mk(Simulation)
+    one = mk(Simulation, strict_centres=False)
     for _ in range(3):
         one.step_device()
     b = state(one)
@@ -62,6 +67,9 @@ if rank == 0:
             rows = np.unique(np.argwhere(d > 0)[:, 0])
             extra = f"  differing rows {len(rows)} of {len(x)} (first {rows[:4].tolist()}, last {rows[-1]}), max |diff| {d.max():.3e}"
         print(f"{nm}: identical={same}{extra}")
-    print("SHARDED == SINGLE:", ok, flush=True)
+    print(f"SHARDED ({how}, {world} ranks, n = {n}) == SINGLE:", ok, flush=True)
+flag = torch.tensor([1 if (rank != 0 or ok) else 0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.barrier()
 dist.destroy_process_group()
+sys.exit(0 if int(flag.item()) == 1 else 1)
