@@ -90,3 +90,31 @@ def test_header_is_plain_c_and_a_c_client_links():
     against libpsim_b200.so (running it needs a GPU: tests/test_gpu_tree.py::test_c_client)"""
     exe = build_c_smoke()
     assert os.path.exists(exe)
+
+
+def test_rust_binding_covers_the_header():
+    """rust/psim-b200-sys: ffi.rs is generated from the header (every declared symbol bound, argument for argument),
+    the #[repr(C)] structs list the header's fields in order, and the safe wrappers only call declared symbols"""
+    import subprocess
+    import sys
+    assert subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_rust_ffi.py"), "--check"]).returncode == 0, \
+        "rust/psim-b200-sys/src/ffi.rs is stale: run tools/gen_rust_ffi.py"
+    ffi = open(os.path.join(ROOT, "rust", "psim-b200-sys", "src", "ffi.rs")).read()
+    bound = set(re.findall(r"pub fn (psim_\w+)\(", ffi))
+    assert bound == set(declared_symbols())
+    lib = open(os.path.join(ROOT, "rust", "psim-b200-sys", "src", "lib.rs")).read()
+    used = set(re.findall(r"\b(psim_[a-z0-9_]+)\(", lib))
+    assert used <= bound, used - bound
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "psim_b200.h")).read(), flags=re.S)
+    for name in ("psim_config", "psim_species", "psim_node", "psim_stats", "psim_step_params"):
+        body = re.search(r"typedef struct \{([^}]*)\} " + name + ";", header).group(1)
+        c_fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            names = decl.split(None, 1)[1]
+            c_fields += [re.sub(r"\[.*", "", f.strip()) for f in names.split(",")]
+        rust = re.search(r"pub struct " + name + r" \{(.*?)\n\}", lib, flags=re.S).group(1)
+        r_fields = re.findall(r"pub (\w+):", rust)
+        assert c_fields == r_fields, (name, c_fields, r_fields)
