@@ -255,7 +255,7 @@ int32_t psim_step_host(psim_ctx *ctx, const psim_step_params *p, uint64_t n, con
                        float *out_vel_xy_opt, float *out_e_field_xy_opt, uint32_t *out_orig_index_opt);
 /* Device time of each phase of the last psim_step, in ms (CUDA events on the context's stream;
  * synchronises).  Names follow the reference's profile scopes (src/profiler.rs users):
- * [0] quadtree_build  [1] cell_list_rebuild  [2] quadtree_field (+attract)  [3] forces_lj/repulsion
+ * [0] quadtree_build  [1] cell_list_rebuild  [2] quadtree_field (+attract)  [3] forces_polar + forces_lj/repulsion
  * [4] iterate  [5] quadtree_build_domain  [6] electron_updates  [7] whole step */
 #define PSIM_NUM_PHASES 8
 int32_t psim_phase_times(psim_ctx *ctx, float *ms8);

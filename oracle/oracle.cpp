@@ -1011,6 +1011,11 @@ void orc_apply_polar_forces(OrcSim *s, int use_cell, float k_e, int dipole_model
     float dist = mag(d);
     float min_sep = point_radius + src_radius;
     float r_eff = rmax(dist, min_sep);
+    // DOCUMENTED DIVERGENCE from forces.rs:91-96: two zero-radius sites at exactly the same place give
+    // d * (k q / 0) = 0 * inf = NaN in the reference, after which its next propagate() makes every node centre NaN.
+    // At 16 M bodies f32 positions sit on a ~1e-3 A grid and this happens a few times per step, so the bounded CPU
+    // arm of the benchmark could never finish a step.  The term is taken as the zero vector d already is.
+    if (r_eff == 0.0f) return v2(0, 0);
     float denom = (r_eff * r_eff + epsilon_sq) * r_eff;
     return d * (k_e * src_charge / denom);
   };

@@ -473,6 +473,20 @@ float max_repulsion_cutoff(const psim_ctx* ctx) {
   return m;
 }
 
+// Cell size the fused steps bin at.  The reference sizes its grid at max(3 x LJ cutoff, repulsion, LJ) = 11.88 A
+// (forces.rs:17-22); the PAIR SETS of the polar / LJ / repulsion passes do not depend on the cell size, only the
+// number of candidates scanned does, so the steps bin at the largest cutoff the passes actually use: the LJ and
+// repulsion cutoffs and, with the polar pass, 3 x the radius of the polar species (EC / DMC, forces.rs:74).
+float step_cell_size(const psim_ctx* ctx, bool do_polar) {
+  float cell = fmaxf(max_repulsion_cutoff(ctx), max_lj_cutoff(ctx));
+  if (do_polar) {
+    float polar = 0.0f;
+    for (uint32_t s = 4; s <= 5 && s < ctx->nspecies; ++s) polar = fmaxf(polar, 3.0f * ctx->table_h[s].radius);
+    cell = fmaxf(cell, polar);
+  }
+  return cell;
+}
+
 void default_species(SpeciesRow* t) {
   // species.rs:26-408 with config.rs:40-48,106-126 and units.rs
   const double EV_TO_SIM =
@@ -1077,10 +1091,14 @@ int32_t polar_async(psim_ctx* ctx, float k_e, int dipole_model) {
   uint32_t first, count;
   body_range(ctx, first, count);
   if (count == 0) return PSIM_OK;
-  polar_forces_kernel<<<(count + 127) / 128, 128, 0, st>>>(b.pqr, b.species, b.ecount, ctx->eoff[e], ctx->erel[e],
-                                                           ctx->table_d, first, first + count, ctx->cell_start,
-                                                           ctx->cell_end, recA, ctx->polarB, ctx->body_cell,
-                                                           ctx->polar_cutoff, P, b.accm);
+  if (ctx->cfg.parity_mode)
+    polar_forces_kernel<true><<<(count + kPolarThreads - 1) / kPolarThreads, kPolarThreads, 0, st>>>(
+        b.pqr, b.species, b.ecount, ctx->eoff[e], ctx->erel[e], ctx->table_d, first, first + count, ctx->cell_start,
+        ctx->cell_end, recA, ctx->polarB, ctx->body_cell, ctx->polar_cutoff, P, b.accm);
+  else
+    polar_forces_kernel<false><<<(count + kPolarThreads - 1) / kPolarThreads, kPolarThreads, 0, st>>>(
+        b.pqr, b.species, b.ecount, ctx->eoff[e], ctx->erel[e], ctx->table_d, first, first + count, ctx->cell_start,
+        ctx->cell_end, recA, ctx->polarB, ctx->body_cell, ctx->polar_cutoff, P, b.accm);
   LAUNCHED(ctx);
   return PSIM_OK;
 }
@@ -2008,15 +2026,14 @@ static int32_t step_sharded(psim_ctx* ctx, const psim_step_params* p) {
   if ((rc = psim_reset_acc(ctx))) return rc;
   float cell = 0.0f;
   if (p->do_short_range) {
-    const float lj_cutoff = max_lj_cutoff(ctx), repulsion_cutoff = max_repulsion_cutoff(ctx);
-    cell = p->do_polar ? fmaxf(fmaxf(3.0f * lj_cutoff, repulsion_cutoff), lj_cutoff) : fmaxf(repulsion_cutoff, lj_cutoff);
+    cell = step_cell_size(ctx, p->do_polar != 0);
   }
   if ((rc = build_sharded(ctx, PSIM_BUILD_CONTAINING, 0.f, 0.f, p, cell))) return rc;
   mark(1);
   mark(2);
   if ((rc = field_async(ctx, p->k_e, p->bg_x, p->bg_y, 1))) return rc;
-  if (p->do_polar && p->do_short_range && cell > 0.0f && (rc = polar_async(ctx, p->k_e, 1))) return rc;
   mark(3);
+  if (p->do_polar && p->do_short_range && cell > 0.0f && (rc = polar_async(ctx, p->k_e, 1))) return rc;
   if (p->do_short_range && (rc = short_range_async(ctx, PSIM_SR_LJ | PSIM_SR_REPULSION | PSIM_SR_STACK_PRESSURE))) return rc;
   mark(4);
   if (p->do_iterate) {
@@ -2078,9 +2095,7 @@ static int32_t step_async(psim_ctx* ctx, const psim_step_params* p) {
     // The reference sizes its grid for the polar pass too (3 x the LJ cutoff, forces.rs:17-22).  The
     // pair sets of the LJ / repulsion passes do not depend on the cell size, so the fused step bins at
     // the largest cutoff those passes use: 9x fewer candidates per body than at 3 x cutoff.
-    const float lj_cutoff = max_lj_cutoff(ctx), repulsion_cutoff = max_repulsion_cutoff(ctx);
-    const float cell = p->do_polar ? fmaxf(fmaxf(3.0f * lj_cutoff, repulsion_cutoff), lj_cutoff)
-                                   : fmaxf(repulsion_cutoff, lj_cutoff);
+    const float cell = step_cell_size(ctx, p->do_polar != 0);
     if (cell > 0.0f && (rc = cell_build_async(ctx, p->hw, p->hh, cell))) return rc;
   }
   mark(2);
@@ -2089,8 +2104,8 @@ static int32_t step_async(psim_ctx* ctx, const psim_step_params* p) {
     results_from_here();
     cudaMemcpyAsync(H.out_ef, ctx->b[ctx->cur].efield, 8 * n, cudaMemcpyDeviceToHost, ctx->copy_out);
   }
-  if (p->do_polar && p->do_short_range && (rc = polar_async(ctx, p->k_e, 1))) return rc;
   mark(3);
+  if (p->do_polar && p->do_short_range && (rc = polar_async(ctx, p->k_e, 1))) return rc;
   if (p->do_short_range && (rc = short_range_async(ctx, PSIM_SR_LJ | PSIM_SR_REPULSION | PSIM_SR_STACK_PRESSURE))) return rc;
   mark(4);
   if (H.active && H.late_vel) {  // the velocities have had the whole force phase to arrive

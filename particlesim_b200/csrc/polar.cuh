@@ -49,13 +49,29 @@ struct PolarParams {
   int dipole_model;  // 0 SingleOffset, 1 ConjugatePair (config.rs:270-281)
 };
 
-// field_from_source closure of forces.rs:84-97
+// field_from_source closure of forces.rs:84-97.  IEEE: the reference's operations one by one (IEEE sqrt and division,
+// no contraction); otherwise (psim_config.parity_mode 0, like the traversal) MUFU rsqrt / rcp and FMA on the same terms.
+template <bool IEEE>
 __device__ __forceinline__ float2 polar_field(float px, float py, float point_radius, float sx, float sy,
                                               float src_radius, float src_charge, float k_e, float eps_sq) {
   if (fabsf(src_charge) < 1.1920929e-07f) return make_float2(0.f, 0.f);
+  if (!IEEE) {
+    const float dx = px - sx, dy = py - sy;
+    const float d2 = fmaf(dx, dx, dy * dy);
+    const float dist = d2 > 0.0f ? d2 * rsqrtf(d2) : 0.0f;
+    const float r_eff = fmaxf(dist, point_radius + src_radius);
+    if (r_eff == 0.0f) return make_float2(0.f, 0.f);
+    const float s = __fdividef(k_e * src_charge, fmaf(r_eff, r_eff, eps_sq) * r_eff);
+    return make_float2(dx * s, dy * s);
+  }
   const float dx = __fsub_rn(px, sx), dy = __fsub_rn(py, sy);
   const float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
   const float r_eff = fmaxf(dist, __fadd_rn(point_radius, src_radius));
+  // Two zero-radius sites at exactly the same place (an electron of i on an electron of j): the reference evaluates
+  // d * (k q / 0) = 0 * inf = NaN there, which turns every node centre of its next build into NaN.  With f32
+  // positions on a ~1e-3 A grid (|x| ~ 8000 A) that happens a few times per step at 16 M bodies, so the term is
+  // taken as the zero vector d already is (documented divergence).
+  if (r_eff == 0.0f) return make_float2(0.f, 0.f);
   const float denom = __fmul_rn(__fadd_rn(__fmul_rn(r_eff, r_eff), eps_sq), r_eff);
   const float s = __fdiv_rn(__fmul_rn(k_e, src_charge), denom);
   return make_float2(__fmul_rn(dx, s), __fmul_rn(dy, s));
@@ -63,25 +79,26 @@ __device__ __forceinline__ float2 polar_field(float px, float py, float point_ra
 
 // force on polar body i (nucleus at ipos with radius irad, electron at ipos + irel) from neighbour j
 // (forces.rs:99-158); returns false if the reference skips the pair (both fields exactly zero)
+template <bool IEEE>
 __device__ __forceinline__ bool polar_pair_force(float ix, float iy, float irad, float irx, float iry, float i_qeff,
                                                  float jx, float jy, float jrad, float jq, bool j_dip,
                                                  float jrx, float jry, float j_qeff, const PolarParams& P,
                                                  float& fx, float& fy) {
   const float iex = __fadd_rn(ix, irx), iey = __fadd_rn(iy, iry);
-  float2 fn = polar_field(ix, iy, irad, jx, jy, jrad, jq, P.k_e, P.epsilon_sq);
-  float2 fe = polar_field(iex, iey, 0.0f, jx, jy, jrad, jq, P.k_e, P.epsilon_sq);
+  float2 fn = polar_field<IEEE>(ix, iy, irad, jx, jy, jrad, jq, P.k_e, P.epsilon_sq);
+  float2 fe = polar_field<IEEE>(iex, iey, 0.0f, jx, jy, jrad, jq, P.k_e, P.epsilon_sq);
   // the reference starts from Vec2::zero() and += each term
   fn.x = __fadd_rn(0.0f, fn.x), fn.y = __fadd_rn(0.0f, fn.y);
   fe.x = __fadd_rn(0.0f, fe.x), fe.y = __fadd_rn(0.0f, fe.y);
   if (P.dipole_model == 1 && j_dip) {
     const float jex = __fadd_rn(jx, jrx), jey = __fadd_rn(jy, jry);
-    float2 t = polar_field(ix, iy, irad, jx, jy, jrad, j_qeff, P.k_e, P.epsilon_sq);
+    float2 t = polar_field<IEEE>(ix, iy, irad, jx, jy, jrad, j_qeff, P.k_e, P.epsilon_sq);
     fn.x = __fadd_rn(fn.x, t.x), fn.y = __fadd_rn(fn.y, t.y);
-    t = polar_field(ix, iy, irad, jex, jey, 0.0f, j_qeff, P.k_e, P.epsilon_sq);
+    t = polar_field<IEEE>(ix, iy, irad, jex, jey, 0.0f, j_qeff, P.k_e, P.epsilon_sq);
     fn.x = __fsub_rn(fn.x, t.x), fn.y = __fsub_rn(fn.y, t.y);
-    t = polar_field(iex, iey, 0.0f, jx, jy, jrad, j_qeff, P.k_e, P.epsilon_sq);
+    t = polar_field<IEEE>(iex, iey, 0.0f, jx, jy, jrad, j_qeff, P.k_e, P.epsilon_sq);
     fe.x = __fadd_rn(fe.x, t.x), fe.y = __fadd_rn(fe.y, t.y);
-    t = polar_field(iex, iey, 0.0f, jex, jey, 0.0f, j_qeff, P.k_e, P.epsilon_sq);
+    t = polar_field<IEEE>(iex, iey, 0.0f, jex, jey, 0.0f, j_qeff, P.k_e, P.epsilon_sq);
     fe.x = __fsub_rn(fe.x, t.x), fe.y = __fsub_rn(fe.y, t.y);
   }
   if (fn.x == 0.0f && fn.y == 0.0f && fe.x == 0.0f && fe.y == 0.0f) return false;
@@ -90,7 +107,17 @@ __device__ __forceinline__ bool polar_pair_force(float ix, float iy, float irad,
   return true;
 }
 
-__global__ void __launch_bounds__(128)
+// Two passes per body so that the lanes of a warp stay together: (1) a cheap sweep over the candidates of the
+// 3 x 3 (or wider) cell block that only measures distances and notes the few that are inside either partner's
+// cutoff (~1 in 7 at the reference's densities), (2) the pair forces of the noted candidates - six softened
+// point-source fields with IEEE sqrt and divisions each - in cell order, as a dense loop of similar length in every
+// lane.  The candidate list lives in shared memory (kPolarList slots per thread) and is drained whenever it is full,
+// so the order of the additions is the cell order whatever its capacity.
+constexpr int kPolarThreads = 128;
+constexpr int kPolarList = 24;
+
+template <bool IEEE>
+__global__ void __launch_bounds__(kPolarThreads)
     polar_forces_kernel(const float4* __restrict__ pqr, const uint8_t* __restrict__ species,
                         const uint8_t* __restrict__ ecount, const uint32_t* __restrict__ eoff,
                         const float2* __restrict__ erel, const SpeciesRow* __restrict__ table_g,
@@ -100,69 +127,93 @@ __global__ void __launch_bounds__(128)
                         const uint32_t* __restrict__ max_cutoff_bits, PolarParams P,
                         float4* __restrict__ acc_mass) {
   __shared__ float s_polar_charge[kMaxSpecies];
+  __shared__ uint32_t s_list[kPolarList][kPolarThreads];
   if (threadIdx.x < kMaxSpecies) s_polar_charge[threadIdx.x] = table_g[threadIdx.x].polar_charge;
   __syncthreads();
   const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
   const float max_cutoff = __uint_as_float(*max_cutoff_bits);
   if (!(max_cutoff > 0.0f)) return;  // no polar body with an electron: the reference loop does nothing
-  const float4 me = pqr[i];
-  const uint32_t msp = species[i] < kMaxSpecies ? species[i] : 0;
-  const bool me_dip = (msp == 4u || msp == 5u) && ecount[i] != 0;
+  const bool live = i < n;
+  const float4 me = live ? pqr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const uint32_t msp = live && species[i] < kMaxSpecies ? species[i] : 0;
+  const bool me_dip = live && (msp == 4u || msp == 5u) && ecount[i] != 0;
   float2 mrel = make_float2(0.f, 0.f);
   if (me_dip) mrel = erel[eoff[i]];
   const float me_qeff = s_polar_charge[msp];
   const float my_cut = __fmul_rn(3.0f, me.w), my_cut_sq = __fmul_rn(my_cut, my_cut);
-  float4 am = acc_mass[i];
-  const uint32_t c = body_cell[i];
-  const int cx = (int)(c % P.g.gx), cy = (int)(c / P.g.gx);
-  const int range = (int)ceilf(max_cutoff / P.g.cell_size);
-  const int y0 = max(cy - range, 0), y1 = min(cy + range, (int)P.g.gy - 1);
-  const int x0 = max(cx - range, 0), x1 = min(cx + range, (int)P.g.gx - 1);
+  float4 am = live ? acc_mass[i] : make_float4(0.f, 0.f, 0.f, 1.f);
+  const float inv_mass = __frcp_rn(am.w);
   float ax = 0.0f, ay = 0.0f;
-  for (int y = y0; y <= y1; ++y) {
-    for (int x = x0; x <= x1; ++x) {
-      const uint32_t cc = (uint32_t)x + (uint32_t)y * P.g.gx;
-      const uint32_t e = cell_end[cc];
-      for (uint32_t k = cell_start[cc]; k < e; ++k) {
-        const float4 b4 = __ldg(&recB[k]);
-        const uint32_t j = __float_as_uint(b4.y);
-        if (j == i) continue;
-        const uint32_t jbits = __float_as_uint(b4.x);
-        const bool j_dip = (jbits & kPolarHasDipole) != 0;
-        if (!me_dip && !j_dip) continue;
-        const float4 a4 = __ldg(&recA[k]);
-        const float rx = __fsub_rn(a4.x, me.x), ry = __fsub_rn(a4.y, me.y);
-        const float r2 = __fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry));
-        uint32_t jsp = jbits & 0xffu;
-        if (jsp >= kMaxSpecies) jsp = 0;
-        const float j_qeff_tab = s_polar_charge[jsp];
-        float fx, fy;
-        // me as the polar body i, the candidate as its neighbour j
-        if (me_dip && r2 < my_cut_sq) {
-          if (polar_pair_force(me.x, me.y, me.w, mrel.x, mrel.y, me_qeff, a4.x, a4.y, a4.w, a4.z, j_dip, b4.z,
-                               b4.w, j_dip ? j_qeff_tab : 0.0f, P, fx, fy)) {
-            ax = __fadd_rn(ax, __fdiv_rn(fx, am.w));
-            ay = __fadd_rn(ay, __fdiv_rn(fy, am.w));
-          }
+  int filled = 0;
+
+  auto drain = [&]() {
+    for (int t = 0; t < filled; ++t) {
+      const uint32_t k = s_list[t][threadIdx.x];
+      const float4 b4 = __ldg(&recB[k]);
+      const float4 a4 = __ldg(&recA[k]);
+      const uint32_t jbits = __float_as_uint(b4.x);
+      const bool j_dip = (jbits & kPolarHasDipole) != 0;
+      const float rx = __fsub_rn(a4.x, me.x), ry = __fsub_rn(a4.y, me.y);
+      const float r2 = __fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry));
+      uint32_t jsp = jbits & 0xffu;
+      if (jsp >= kMaxSpecies) jsp = 0;
+      const float j_qeff_tab = s_polar_charge[jsp];
+      float fx, fy;
+      // me as the polar body i, the candidate as its neighbour j
+      if (me_dip && r2 < my_cut_sq) {
+        if (polar_pair_force<IEEE>(me.x, me.y, me.w, mrel.x, mrel.y, me_qeff, a4.x, a4.y, a4.w, a4.z, j_dip, b4.z, b4.w,
+                             j_dip ? j_qeff_tab : 0.0f, P, fx, fy)) {
+          ax = __fadd_rn(ax, IEEE ? __fdiv_rn(fx, am.w) : fx * inv_mass);
+          ay = __fadd_rn(ay, IEEE ? __fdiv_rn(fy, am.w) : fy * inv_mass);
         }
-        // the candidate as the polar body i, me as its neighbour j: reaction  -force / m_me
-        if (j_dip) {
-          const float jc = __fmul_rn(3.0f, a4.w);
-          if (r2 < __fmul_rn(jc, jc)) {
-            if (polar_pair_force(a4.x, a4.y, a4.w, b4.z, b4.w, j_qeff_tab, me.x, me.y, me.w, me.z, me_dip, mrel.x,
-                                 mrel.y, me_dip ? me_qeff : 0.0f, P, fx, fy)) {
-              ax = __fsub_rn(ax, __fdiv_rn(fx, am.w));
-              ay = __fsub_rn(ay, __fdiv_rn(fy, am.w));
-            }
+      }
+      // the candidate as the polar body i, me as its neighbour j: reaction  -force / m_me
+      if (j_dip) {
+        const float jc = __fmul_rn(3.0f, a4.w);
+        if (r2 < __fmul_rn(jc, jc)) {
+          if (polar_pair_force<IEEE>(a4.x, a4.y, a4.w, b4.z, b4.w, j_qeff_tab, me.x, me.y, me.w, me.z, me_dip, mrel.x, mrel.y,
+                               me_dip ? me_qeff : 0.0f, P, fx, fy)) {
+            ax = __fsub_rn(ax, IEEE ? __fdiv_rn(fx, am.w) : fx * inv_mass);
+            ay = __fsub_rn(ay, IEEE ? __fdiv_rn(fy, am.w) : fy * inv_mass);
           }
         }
       }
     }
+    filled = 0;
+  };
+
+  if (live) {
+    const uint32_t c = body_cell[i];
+    const int cx = (int)(c % P.g.gx), cy = (int)(c / P.g.gx);
+    const int range = (int)ceilf(max_cutoff / P.g.cell_size);
+    const int y0 = max(cy - range, 0), y1 = min(cy + range, (int)P.g.gy - 1);
+    const int x0 = max(cx - range, 0), x1 = min(cx + range, (int)P.g.gx - 1);
+    // any pair closer than this may interact (either partner's 3 * radius, bounded by the largest one present)
+    const float any_cut_sq = __fmul_rn(max_cutoff, max_cutoff);
+    for (int y = y0; y <= y1; ++y) {
+      for (int x = x0; x <= x1; ++x) {
+        const uint32_t cc = (uint32_t)x + (uint32_t)y * P.g.gx;
+        const uint32_t k1 = cell_end[cc];
+        for (uint32_t k = cell_start[cc]; k < k1; ++k) {
+          const float4 a4 = __ldg(&recA[k]);
+          const float rx = __fsub_rn(a4.x, me.x), ry = __fsub_rn(a4.y, me.y);
+          const float r2 = __fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry));
+          if (!(r2 < any_cut_sq)) continue;
+          const float4 b4 = __ldg(&recB[k]);
+          if (__float_as_uint(b4.y) == i) continue;
+          if (!me_dip && !(__float_as_uint(b4.x) & kPolarHasDipole)) continue;
+          s_list[filled][threadIdx.x] = k;
+          if (++filled == kPolarList) drain();
+        }
+      }
+    }
   }
-  am.x = __fadd_rn(am.x, ax);
-  am.y = __fadd_rn(am.y, ay);
-  acc_mass[i] = am;
+  drain();
+  if (live) {
+    am.x = __fadd_rn(am.x, ax);
+    am.y = __fadd_rn(am.y, ay);
+    acc_mass[i] = am;
+  }
 }
 
 }  // namespace psim

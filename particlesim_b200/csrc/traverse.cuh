@@ -286,10 +286,16 @@ __device__ __forceinline__ float2 bh_group_walk(const float4* __restrict__ nodeA
   const uint32_t lt = (1u << lane) - 1u;
   float ax = 0.0f, ay = 0.0f;
   nodes_out = 0;
-  const uint32_t live_mask = __ballot_sync(FULL, live);
-  if (live_mask == 0 || M == 0) return make_float2(0.f, 0.f);
-  // bounding box and radius range of the live targets
   const float INF = __int_as_float(0x7f800000);
+  // A target at a NaN / infinite position never passes an opening test, visits every body of the tree and comes
+  // back with NaN (quadtree.rs:361-394: d, d_sq and every term are NaN).  That result is returned at once; the
+  // lane sits out the shared walk instead of dragging its 31 neighbours through all N leaves.
+  const bool lost = live && !(fabsf(px) < INF && fabsf(py) < INF) && M != 0;
+  if (lost) live = false;
+  const float lost_value = __int_as_float(0x7fc00000);
+  const uint32_t live_mask = __ballot_sync(FULL, live);
+  if (live_mask == 0 || M == 0) return lost ? make_float2(lost_value, lost_value) : make_float2(0.f, 0.f);
+  // bounding box and radius range of the live targets
   float bx0 = live ? px : INF, bx1 = live ? px : -INF, by0 = live ? py : INF, by1 = live ? py : -INF;
   float rmin = live ? radius : INF, rmax = live ? radius : -INF;
 #pragma unroll
@@ -488,6 +494,7 @@ __device__ __forceinline__ float2 bh_group_walk(const float4* __restrict__ nodeA
     }
   }
   nodes_out = visited;
+  if (lost) return make_float2(lost_value, lost_value);
   return make_float2(ax, ay);
 }
 

@@ -292,8 +292,8 @@ class Simulation:
         return float(max(np.float32(3.0) * lj, rep, lj))
 
     def step_cell_size(self, do_polar: bool = False) -> float:
-        """the cell size psim_step bins at: the largest cutoff its short-range passes use (the pair sets of
-        the LJ / repulsion passes do not depend on the cell size; only a polar pass needs 3 x the LJ cutoff)"""
+        """the cell size psim_step bins at: the largest cutoff its short-range passes use (the pair sets of the polar /
+        LJ / repulsion passes do not depend on the cell size; the polar pass reaches 3 x the radius of EC / DMC)"""
         t = self.species_table
         lj = np.float32(0.0)
         rep = np.float32(0.0)
@@ -302,7 +302,10 @@ class Simulation:
                 lj = max(lj, np.float32(r["lj_cutoff"]) * np.float32(r["lj_sigma"]))
             if r["repulsion_enabled"]:
                 rep = max(rep, np.float32(r["repulsion_cutoff"]))
-        return float(max(np.float32(3.0) * lj, rep, lj)) if do_polar else float(max(rep, lj))
+        if not do_polar:
+            return float(max(rep, lj))
+        polar = max(np.float32(3.0) * np.float32(t[s]["radius"]) for s in (4, 5) if s < len(t))  # EC / DMC, forces.rs:74
+        return float(max(rep, lj, polar))
 
     def stats(self) -> dict:
         st = _lib.Stats()

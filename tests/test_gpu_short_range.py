@@ -218,13 +218,14 @@ def test_fused_step_matches_the_call_sequence(cuda_device):
     sim.close()
 
 
-@pytest.mark.parametrize("dipole_model", [1, 0])
-def test_polar_forces(cuda_device, dipole_model):
-    """forces.rs:52-175 (the pass between attract and LJ in Simulation::step), gather form vs the serial loop"""
+@pytest.mark.parametrize("dipole_model,parity_mode", [(1, 1), (0, 1), (1, 0)])
+def test_polar_forces(cuda_device, dipole_model, parity_mode):
+    """forces.rs:52-175 (the pass between attract and LJ in Simulation::step), gather form vs the serial loop;
+    parity_mode 0 = the MUFU rsqrt / rcp arithmetic of the benchmarked mode on the same pair terms"""
     from particlesim_b200 import forces
     bodies = electrolyte(30_000)
     hw, hh = bodies["hw"], bodies["hh"]
-    sim = make_sim(bodies)
+    sim = make_sim(bodies, parity_mode=parity_mode)
     o = oracle_for(bodies)
     sim.reset_acc()
     forces.prepare_spatial_structures(sim)
