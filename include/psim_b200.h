@@ -172,6 +172,17 @@ int32_t psim_field(psim_ctx *ctx, float k_e, float bg_x, float bg_y, int32_t wri
  * Quadtree::field_at_point (quadtree.rs:504-507) */
 int32_t psim_acc_points(psim_ctx *ctx, uint64_t m, const float *pts_xy, const float *q_opt,
                         const float *radius_opt, float k_e, float *out_xy);
+/* collision::collide (src/simulation/collision.rs:62-372), `passes` passes (Simulation::step runs COLLISION_PASSES of
+ * them, simulation.rs:1025-1028), each with correction scale 1 / num_passes.  Broad phase on the cell list (cell =
+ * the largest diameter present), then resolve() for every pair of intersecting bounding squares from the state at
+ * the start of the pass, the changes of a body's pairs summed (the reference resolves the pairs in whatever order its
+ * thread pool reaches them, on shared mutable state - there is no order to reproduce; for a body in one pair the
+ * result is resolve()'s, see csrc/collide.cuh).  li_collision_softness / soft_collision_* are SimConfig's
+ * (config.rs:235,358-362,483-485).  Moves bodies: tree and grid are stale afterwards.  *touching_pairs (opt)
+ * receives the number of touching pairs found by the LAST pass. */
+int32_t psim_collide(psim_ctx *ctx, float hw, float hh, float domain_depth, uint32_t passes, uint32_t num_passes,
+                     float li_collision_softness, int32_t soft_collision_lithium_ion, int32_t soft_collision_anion,
+                     uint64_t *touching_pairs);
 /* Electron hopping, the field part of the candidate predicate (simulation/electron_hopping.rs:283-329), batched:
  * m_src donors (indices in the current body order), their candidate acceptors in CSR form (pair_offsets[m_src + 1]
  * into dst_idx).  For every donor: local_field = (bg_x, bg_y) + Quadtree::field_at_point(bodies[src].pos)

@@ -1363,6 +1363,196 @@ void orc_direct_f64(const OrcSim *s, uint64_t m, const float *pts_xy, const floa
   }
 }
 
+// ---- collision.rs ---------------------------------------------------------------------------------
+namespace {
+struct CollideCfg {
+  float softness;
+  bool soft_li, soft_an;
+  float domain_depth;
+  uint32_t num_passes;
+};
+inline bool finite_f(float v) { return std::isfinite(v); }
+// apply_collision_modifiers, collision.rs:16-60
+void collision_modifiers(const Body &bi, const Body &bj, float wi, float wj, const CollideCfg &c, float &mi, float &mj) {
+  const bool i_metal = bi.species == 1 || bi.species == 2, j_metal = bj.species == 1 || bj.species == 2;
+  const float stiffness = rmin(rmax(c.softness, 0.0f), 1.0f);
+  if (i_metal && !j_metal) {
+    mj = wj + (wi * stiffness);
+    mi = wi * (1.0f - stiffness);
+    return;
+  }
+  if (j_metal && !i_metal) {
+    mi = wi + (wj * stiffness);
+    mj = wj * (1.0f - stiffness);
+    return;
+  }
+  const bool i_li = c.soft_li && bi.species == 0, j_li = c.soft_li && bj.species == 0;
+  const bool i_an = c.soft_an && bi.species == 3, j_an = c.soft_an && bj.species == 3;
+  if (i_li || j_li || i_an || j_an) {
+    const float scale = 1.0f - stiffness;
+    mi = wi * scale, mj = wj * scale;
+    return;
+  }
+  mi = wi, mj = wj;
+}
+void sanitize_body(Body &b, bool with_az) {
+  if (!finite_f(b.pos.x)) b.pos.x = 0.0f;
+  if (!finite_f(b.pos.y)) b.pos.y = 0.0f;
+  if (!finite_f(b.vel.x)) b.vel.x = 0.0f;
+  if (!finite_f(b.vel.y)) b.vel.y = 0.0f;
+  if (!finite_f(b.z)) b.z = 0.0f;
+  if (!finite_f(b.vz)) b.vz = 0.0f;
+  if (with_az && !finite_f(b.az)) b.az = 0.0f;
+}
+// resolve, collision.rs:158-372; returns whether the pair touched
+bool collide_resolve(std::vector<Body> &bodies, size_t i, size_t j, const CollideCfg &c) {
+  V2 p1 = bodies[i].pos, p2 = bodies[j].pos;
+  float z1 = bodies[i].z, z2 = bodies[j].z;
+  const float r1 = bodies[i].radius, r2 = bodies[j].radius;
+  V2 d_xy = p2 - p1;
+  float dz = z2 - z1;
+  const float r = r1 + r2;
+  float dist_sq = mag_sq(d_xy) + dz * dz;
+  V2 v1 = bodies[i].vel, v2b = bodies[j].vel;
+  float v1z = bodies[i].vz, v2z = bodies[j].vz;
+  bool need = !(finite_f(p1.x) && finite_f(p1.y) && finite_f(z1) && finite_f(v1.x) && finite_f(v1.y) && finite_f(v1z)) ||
+              !(finite_f(p2.x) && finite_f(p2.y) && finite_f(z2) && finite_f(v2b.x) && finite_f(v2b.y) && finite_f(v2z));
+  if (need || !finite_f(dist_sq)) {
+    sanitize_body(bodies[i], true), sanitize_body(bodies[j], true);
+    p1 = bodies[i].pos, p2 = bodies[j].pos, z1 = bodies[i].z, z2 = bodies[j].z;
+    d_xy = p2 - p1, dz = z2 - z1;
+    dist_sq = mag_sq(d_xy) + dz * dz;
+    v1 = bodies[i].vel, v2b = bodies[j].vel, v1z = bodies[i].vz, v2z = bodies[j].vz;
+  }
+  if (dist_sq > r * r) return false;
+  const V2 v_xy = v2b - v1;
+  const float vz = v2z - v1z;
+  const float d_dot_v = (d_xy.x * v_xy.x + d_xy.y * v_xy.y) + dz * vz;
+  const float m1 = bodies[i].mass, m2 = bodies[j].mass;
+  const float weight1 = m2 / (m1 + m2), weight2 = m1 / (m1 + m2);
+  if (d_dot_v >= 0.0f && dist_sq > 0.0f && finite_f(dist_sq)) {
+    const float dist = sqrtf(dist_sq);
+    const float corr = r / dist - 1.0f;
+    const float sep_x = d_xy.x * corr, sep_y = d_xy.y * corr, sep_z = dz * corr;
+    float mw1, mw2;
+    collision_modifiers(bodies[i], bodies[j], weight1, weight2, c, mw1, mw2);
+    bodies[i].pos.x -= mw1 * sep_x, bodies[i].pos.y -= mw1 * sep_y, bodies[i].z -= mw1 * sep_z;
+    bodies[j].pos.x += mw2 * sep_x, bodies[j].pos.y += mw2 * sep_y, bodies[j].z += mw2 * sep_z;
+    return true;
+  }
+  const float v_sq = mag_sq(v_xy) + vz * vz;
+  const float d_sq = dist_sq;
+  if (!finite_f(d_sq) || d_sq <= 1.0e-8f || !finite_f(v_sq)) {
+    const uint64_t jj = (uint64_t)j;
+    const float angle = (float)(((uint64_t)i) ^ ((jj << 13) | (jj >> 51))) * (6.28318530717958647692f / 1024.0f);
+    const float s = sinf(angle), co = cosf(angle);
+    const V2 dir = v2(co, s);
+    const float sep = r * 1.001f;
+    const V2 mid = (bodies[i].pos + bodies[j].pos) * 0.5f;
+    bodies[i].pos = mid - dir * (sep * weight1);
+    bodies[j].pos = mid + dir * (sep * weight2);
+    const float depth = c.domain_depth;
+    const float midz = rmin(rmax((bodies[i].z + bodies[j].z) * 0.5f, -depth), depth);
+    bodies[i].z = midz, bodies[j].z = midz;
+    for (size_t k : {i, j}) {
+      Body &b = bodies[k];
+      if (!finite_f(b.vel.x)) b.vel.x = 0.0f;
+      if (!finite_f(b.vel.y)) b.vel.y = 0.0f;
+      if (!finite_f(b.vz)) b.vz = 0.0f;
+    }
+    return true;
+  }
+  const float r_sq = r * r;
+  const float correction_scale = 1.0f / (float)c.num_passes;
+  const float disc_term = rmax(d_dot_v * d_dot_v - v_sq * (d_sq - r_sq), 0.0f);
+  const float sqrt_disc = sqrtf(disc_term);
+  const float numerator = d_dot_v + sqrt_disc;
+  const float t = correction_scale * numerator / v_sq;
+  if (!finite_f(t)) {
+    const float dist = sqrtf(d_sq);
+    if (finite_f(dist) && dist > 0.0f) {
+      const float corr = r / dist - 1.0f;
+      const float sep_x = d_xy.x * corr, sep_y = d_xy.y * corr, sep_z = dz * corr;
+      bodies[i].pos.x -= weight1 * sep_x, bodies[i].pos.y -= weight1 * sep_y, bodies[i].z -= weight1 * sep_z;
+      bodies[j].pos.x += weight2 * sep_x, bodies[j].pos.y += weight2 * sep_y, bodies[j].z += weight2 * sep_z;
+    }
+    return true;
+  }
+  bodies[i].pos = bodies[i].pos - v1 * t, bodies[i].z -= v1z * t;
+  bodies[j].pos = bodies[j].pos - v2b * t, bodies[j].z -= v2z * t;
+  const V2 q1 = bodies[i].pos, q2 = bodies[j].pos;
+  const float zz1 = bodies[i].z, zz2 = bodies[j].z;
+  const V2 d2 = q2 - q1;
+  const float dz2 = zz2 - zz1;
+  const float ddv = (d2.x * v_xy.x + d2.y * v_xy.y) + dz2 * vz;
+  const float dsq2 = mag_sq(d2) + dz2 * dz2;
+  float scale = (finite_f(dsq2) && dsq2 > 0.0f) ? 1.5f * ddv / dsq2 : 0.0f;
+  if (!finite_f(scale)) scale = 0.0f;
+  const float sep_x = d2.x * scale, sep_y = d2.y * scale, sep_z = dz2 * scale;
+  float mw1, mw2;
+  collision_modifiers(bodies[i], bodies[j], weight1, weight2, c, mw1, mw2);
+  const float v1x = v1.x + sep_x * mw1, v1y = v1.y + sep_y * mw1, v1z_new = v1z + sep_z * mw1;
+  const float v2x = v2b.x - sep_x * mw2, v2y = v2b.y - sep_y * mw2, v2z_new = v2z - sep_z * mw2;
+  bodies[i].vel = v2(v1x, v1y), bodies[i].vz = v1z_new;
+  bodies[j].vel = v2(v2x, v2y), bodies[j].vz = v2z_new;
+  bodies[i].pos = bodies[i].pos + v2(v1x, v1y) * t, bodies[i].z += v1z_new * t;
+  bodies[j].pos = bodies[j].pos + v2(v2x, v2y) * t, bodies[j].z += v2z_new * t;
+  sanitize_body(bodies[i], false), sanitize_body(bodies[j], false);
+  return true;
+}
+}  // namespace
+
+// collide, collision.rs:62-156: the broad phase is broccoli's (un-vendored, Cargo.lock: broccoli 6.3) "all pairs of
+// intersecting axis-aligned rectangles, each once"; here a uniform grid finds the same pairs and they are resolved in
+// index order.
+uint64_t orc_collide(OrcSim *s, float domain_depth, uint32_t num_passes, float li_collision_softness,
+                     int soft_collision_lithium_ion, int soft_collision_anion) {
+  auto &bodies = s->bodies;
+  const size_t n = bodies.size();
+  if (n == 0) return 0;
+  CollideCfg c{li_collision_softness, soft_collision_lithium_ion != 0, soft_collision_anion != 0, domain_depth,
+               num_passes ? num_passes : 1u};
+  float rmaxv = 0.0f, mnx = 3.4e38f, mny = 3.4e38f, mxx = -3.4e38f, mxy = -3.4e38f;
+  for (const Body &b : bodies) {
+    if (!(finite_f(b.pos.x) && finite_f(b.pos.y))) continue;
+    rmaxv = rmax(rmaxv, b.radius);
+    mnx = rmin(mnx, b.pos.x), mny = rmin(mny, b.pos.y), mxx = rmax(mxx, b.pos.x), mxy = rmax(mxy, b.pos.y);
+  }
+  if (!(rmaxv > 0.0f) || !(mxx >= mnx)) return 0;
+  const double cell = 2.0 * (double)rmaxv;
+  const int64_t gx = (int64_t)std::floor(((double)mxx - mnx) / cell) + 1, gy = (int64_t)std::floor(((double)mxy - mny) / cell) + 1;
+  std::vector<std::vector<uint32_t>> cells((size_t)(gx * gy));
+  auto cell_of = [&](const Body &b, int64_t &cx, int64_t &cy) {
+    cx = (int64_t)std::floor(((double)b.pos.x - mnx) / cell), cy = (int64_t)std::floor(((double)b.pos.y - mny) / cell);
+  };
+  for (size_t i = 0; i < n; ++i) {
+    if (!(finite_f(bodies[i].pos.x) && finite_f(bodies[i].pos.y))) continue;
+    int64_t cx, cy;
+    cell_of(bodies[i], cx, cy);
+    cells[(size_t)(cy * gx + cx)].push_back((uint32_t)i);
+  }
+  // pairs from the positions at the start of the pass (the BVH is built once per pass, collision.rs:148)
+  std::vector<std::pair<uint32_t, uint32_t>> pairs;
+  for (size_t i = 0; i < n; ++i) {
+    const Body &a = bodies[i];
+    if (!(finite_f(a.pos.x) && finite_f(a.pos.y))) continue;
+    int64_t cx, cy;
+    cell_of(a, cx, cy);
+    for (int64_t y = std::max<int64_t>(cy - 1, 0); y <= std::min<int64_t>(cy + 1, gy - 1); ++y)
+      for (int64_t x = std::max<int64_t>(cx - 1, 0); x <= std::min<int64_t>(cx + 1, gx - 1); ++x)
+        for (uint32_t j : cells[(size_t)(y * gx + x)]) {
+          if (j <= i) continue;
+          const Body &b = bodies[j];
+          const float rr = a.radius + b.radius;
+          if (fabsf(b.pos.x - a.pos.x) <= rr && fabsf(b.pos.y - a.pos.y) <= rr) pairs.emplace_back((uint32_t)i, j);
+        }
+  }
+  std::sort(pairs.begin(), pairs.end());
+  uint64_t touched = 0;
+  for (auto &pr : pairs) touched += collide_resolve(bodies, pr.first, pr.second, c) ? 1 : 0;
+  return touched;
+}
+
 // simulation/electron_hopping.rs:283-329: what the hopping loop computes per candidate before the rate tests
 void orc_hop_alignment(const OrcSim *s, uint64_t m_src, const uint32_t *src_idx, const uint32_t *pair_offsets,
                        const uint32_t *dst_idx, float k_e, float bg_x, float bg_y, float alignment_bias,

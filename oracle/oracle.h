@@ -156,6 +156,11 @@ void orc_enforce_metal_z_boundaries(OrcSim *, float max_z, float hw, float hh, f
 void orc_direct_f64(const OrcSim *, uint64_t m, const float *pts_xy, const float *target_radius,
                     double k_e, double epsilon, double *out_xy, int threads);
 
+/* collision::collide (simulation/collision.rs:62-372), one pass: every pair of intersecting bounding squares is
+ * handed to resolve() - here in index order (i ascending, j ascending), one of the orders the reference's thread pool
+ * may produce.  Returns the number of pairs that touched. */
+uint64_t orc_collide(OrcSim *, float domain_depth, uint32_t num_passes, float li_collision_softness,
+                     int soft_collision_lithium_ion, int soft_collision_anion);
 /* simulation/electron_hopping.rs:283-329, the field part of the candidate predicate for a batch of (donor, acceptor)
  * pairs in CSR form; local_field_xy may be NULL */
 void orc_hop_alignment(const OrcSim *, uint64_t m_src, const uint32_t *src_idx, const uint32_t *pair_offsets,

@@ -123,6 +123,7 @@ def load(variant: str = "") -> C.CDLL:
         "orc_get_surrounded": (None, [vp, vp, vp, vp]),
         "orc_enforce_metal_z_boundaries": (None, [vp, f, f, f, f]),
         "orc_direct_f64": (None, [vp, u64, pf, pf, C.c_double, C.c_double, pd, i]),
+        "orc_collide": (u64, [vp, f, u32, f, i, i]),
         "orc_hop_alignment": (None, [vp, u64, vp, vp, vp, f, f, f, f, vp, vp]),
         "orc_max_threads": (i, []),
         "orc_uv_fma": (i, []),
@@ -323,6 +324,12 @@ class OracleSim:
 
     def iterate(self, dt, damping_base, hw, hh, hd=1.0, enable_out_of_plane=False, threads=0):
         self.lib.orc_iterate(self.h, dt, damping_base, hw, hh, hd, int(enable_out_of_plane), threads)
+
+    def collide(self, domain_depth=1.0, num_passes=7, li_collision_softness=0.8, soft_collision_lithium_ion=True,
+                soft_collision_anion=False):
+        """one pass of collision::collide (pairs resolved in index order); returns the touching pairs"""
+        return int(self.lib.orc_collide(self.h, domain_depth, num_passes, li_collision_softness,
+                                        int(soft_collision_lithium_ion), int(soft_collision_anion)))
 
     def hop_alignment(self, src_idx, candidates, k_e, bg=(0.0, 0.0), alignment_bias=1.0):
         """simulation/electron_hopping.rs:283-329 per candidate: (local_field per donor, alignment per candidate)"""

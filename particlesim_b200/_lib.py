@@ -99,6 +99,7 @@ SIGNATURES = {
     "psim_field": (_i32, [_vp, _f, _f, _f, _i32, _vp, _vp]),
     "psim_acc_points": (_i32, [_vp, _u64, _vp, _vp, _vp, _f, _vp]),
     "psim_update_electrons": (_i32, [_vp, _f, _f, _f, _f]),
+    "psim_collide": (_i32, [_vp, _f, _f, _f, _u32, _u32, _f, _i32, _i32, C.POINTER(_u64)]),
     "psim_hop_alignment": (_i32, [_vp, _u64, _vp, _vp, _vp, _f, _f, _f, _f, _vp, _vp]),
     "psim_cell_build": (_i32, [_vp, _f, _f, _f]),
     "psim_cell_download": (_i32, [_vp, C.POINTER(_u64), C.POINTER(_u64), _vp, _vp]),

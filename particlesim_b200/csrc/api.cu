@@ -14,6 +14,7 @@
 
 #include "../../include/psim_b200.h"
 #include "cells.cuh"
+#include "collide.cuh"
 #include "comm.h"
 #include "hopping.cuh"
 #include "polar.cuh"
@@ -1707,6 +1708,55 @@ int32_t psim_acc_points(psim_ctx* ctx, uint64_t m, const float* pts_xy, const fl
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out_xy, sb + o_o, 8 * m, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return PSIM_OK;
+}
+
+int32_t psim_collide(psim_ctx* ctx, float hw, float hh, float domain_depth, uint32_t passes, uint32_t num_passes,
+                     float li_collision_softness, int32_t soft_li, int32_t soft_an, uint64_t* touching_pairs) {
+  if (!ctx) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
+  if (touching_pairs) *touching_pairs = 0;
+  const uint32_t n = ctx->n;
+  if (n == 0 || passes == 0) return PSIM_OK;
+  if (num_passes == 0) return fail(ctx, PSIM_E_ARG, "psim_collide: num_passes must be positive");
+  // broad-phase cell: the largest diameter among the species present (bodies carry their species' radius)
+  float rmax = 0.0f;
+  for (uint32_t s = 0; s < ctx->nspecies; ++s)
+    if (ctx->species_present & (1u << s)) rmax = fmaxf(rmax, ctx->table_h[s].radius);
+  if (!(rmax > 0.0f)) rmax = 1.0f;
+  cudaStream_t st = ctx->stream;
+  int32_t rc = ensure_stage(ctx, 2 * (size_t)n * sizeof(float4) + 256);
+  if (rc) return rc;
+  float4* recA = static_cast<float4*>(ctx->stage);
+  float4* recB = recA + n;
+  unsigned long long* counter = reinterpret_cast<unsigned long long*>(recB + n);
+  CollideParams P;
+  P.correction_scale = 1.0f / (float)num_passes;
+  P.softness = fminf(fmaxf(li_collision_softness, 0.0f), 1.0f);
+  P.soft_li = soft_li ? 1u : 0u, P.soft_an = soft_an ? 1u : 0u;
+  P.domain_depth = domain_depth;
+  uint32_t first, count;
+  body_range(ctx, first, count);
+  for (uint32_t pass = 0; pass < passes; ++pass) {
+    if ((rc = cell_build_async(ctx, hw, hh, 2.0f * rmax))) return rc;
+    BodyArrays& b = ctx->b[ctx->cur];
+    P.g = ctx->grid;
+    collide_records_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(ctx->order, n, b.pqr, b.velz, b.accm, recA, recB);
+    CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+    if (count)
+      collide_kernel<<<(count + 127) / 128, 128, 0, st>>>(first, first + count, ctx->cell_start, ctx->cell_end,
+                                                          ctx->body_cell, ctx->cpos, recA, recB, b.species, b.accm, P,
+                                                          b.pqr, b.velz, counter);
+    ctx->launches += 2;
+    ctx->tree_valid = ctx->grid_valid = false;
+  }
+  CK(cudaGetLastError());
+  if (touching_pairs) {
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, counter, sizeof h, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *touching_pairs = h / 2;
+  }
   return PSIM_OK;
 }
 

@@ -354,6 +354,17 @@ class Simulation:
         self._call("psim_enforce_metal_z_boundaries", np.float32(max_z), self.domain_width, self.domain_height)
         self.download(("z", "vz"))
 
+    def collide(self, passes=None, num_passes=7, li_collision_softness=0.8, soft_collision_lithium_ion=True,
+                soft_collision_anion=False):
+        """collision::collide, `passes` passes (default: num_passes of them, like Simulation::step,
+        simulation.rs:1025-1028); returns the number of touching pairs the last pass found"""
+        tp = C.c_uint64()
+        self._call("psim_collide", self.domain_width, self.domain_height, self.domain_depth,
+                   int(num_passes if passes is None else passes), int(num_passes), np.float32(li_collision_softness),
+                   int(soft_collision_lithium_ion), int(soft_collision_anion), C.byref(tp))
+        self.download(("pos", "vel", "z", "vz"))
+        return int(tp.value)
+
     def hop_alignment(self, src_idx, candidates, alignment_bias=1.0):
         """simulation/electron_hopping.rs:283-329 for a batch: `candidates[i]` lists the acceptor indices of donor
         src_idx[i] (current body order).  Returns (local_field per donor, list of alignment arrays)."""

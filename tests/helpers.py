@@ -210,7 +210,7 @@ def _dedupe(pos, rng, L):
 
 def oracle_for(bodies, theta=1.0, epsilon=2.0, leaf=1, thread=1024, variant=""):
     s = OracleSim(theta, epsilon, leaf, thread, variant=variant)
-    s.set_bodies(bodies["pos"], z=bodies.get("z"), vel=bodies.get("vel"), mass=bodies.get("mass"),
+    s.set_bodies(bodies["pos"], z=bodies.get("z"), vel=bodies.get("vel"), vz=bodies.get("vz"), mass=bodies.get("mass"),
                  radius=bodies.get("radius"), charge=bodies.get("charge"), species=bodies.get("species"))
     if "ebody" in bodies:
         s.set_electrons(bodies["ebody"], bodies["erel"])
