@@ -158,6 +158,7 @@ struct psim_ctx {
   size_t qstage_bytes = 0;
 
   unsigned long long* step_counter = nullptr;
+  unsigned int* grid_barrier = nullptr;  // aggregate_levels_kernel
   uint64_t launches = 0;
   // multi-GPU: the slice of bodies / electrons this rank computes (default: everything)
   bool tgt_set = false, etgt_set = false;
@@ -705,10 +706,10 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
   LAUNCHED(ctx);
   // bottom-up sweeps over the cells that straddle the emit slabs (a few thousand per level at most),
   // deepest level first; a level's node count is only known on the device
-  for (int level = kMaxLevels - 1; level >= 0; --level) {
-    aggregate_level_kernel<<<ctx->sm_count, 128, 0, st>>>(level, ctx->meta, b.pqr, b.accm, ctx->t, se.direct);
-    LAUNCHED(ctx);
-  }
+  // one CTA per SM, all resident (128 threads each): the kernel's grid barrier needs every CTA running
+  CK(cudaMemsetAsync(ctx->grid_barrier, 0, sizeof(unsigned int), st));
+  aggregate_levels_kernel<<<ctx->sm_count, 128, 0, st>>>(ctx->meta, b.pqr, b.accm, ctx->t, se.direct, ctx->grid_barrier);
+  LAUNCHED(ctx);
   if (ctx->cfg.strict_centres) {
     const int32_t rc = strict_stage(ctx);
     if (rc) return rc;
@@ -1162,7 +1163,7 @@ void free_all(psim_ctx* c) {
   F(c->perm), F(c->inv);
   F(c->surround.last_pos), F(c->surround.last_frame), F(c->surround.flag);
   F(c->cell_start), F(c->cell_end), F(c->order), F(c->body_cell), F(c->cpos), F(c->polarB), F(c->polar_cutoff), F(c->cell_off);
-  F(c->table_d), F(c->stage), F(c->qstage), F(c->step_counter);
+  F(c->table_d), F(c->stage), F(c->qstage), F(c->step_counter), F(c->grid_barrier);
   F(c->strict.cidx), F(c->strict.cw), F(c->strict.chains), F(c->strict.hist), F(c->strict.longs), F(c->strict.counters);
   F(c->strict.item_first), F(c->strict.pblk), F(c->strict.fns), F(c->strict.cand);
 }
@@ -1247,7 +1248,7 @@ int32_t psim_create(int32_t device, uint64_t max_bodies, uint64_t max_electrons,
   A(&ctx->surround.last_pos, nb), A(&ctx->surround.last_frame, nb), A(&ctx->surround.flag, nb);
   A(&ctx->order, nb), A(&ctx->body_cell, nb), A(&ctx->cpos, nb);
   A(&ctx->polarB, nb), A(&ctx->polar_cutoff, 1);
-  A(&ctx->table_d, kMaxSpecies), A(&ctx->step_counter, 1);
+  A(&ctx->table_d, kMaxSpecies), A(&ctx->step_counter, 1), A(&ctx->grid_barrier, 1);
   if (!ok) {
     cudaGetLastError();
     free_all(ctx);

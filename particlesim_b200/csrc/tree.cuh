@@ -264,6 +264,40 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// The same sweep as ONE launch of one CTA per SM (all resident), with a grid-wide barrier between the levels: the
+// straddling cells are ~2 x depth per slab, far too few per level to amortise 32 launch latencies each build.
+// `barrier` is a zeroed counter; empty levels are skipped by every CTA alike.
+__global__ void __launch_bounds__(128)
+    aggregate_levels_kernel(const TreeMeta* __restrict__ meta, const float4* __restrict__ pqr,
+                            const float4* __restrict__ accm, TreeArrays t, uint32_t strict_direct,
+                            unsigned int* __restrict__ barrier) {
+  const uint32_t M = meta->num_nodes;
+  if (M > t.node_cap) return;
+  const float root_size = meta->root.size;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  unsigned int target = 0;
+  for (int level = kMaxLevels - 1; level >= 0; --level) {
+    const uint32_t begin = meta->level_start[level], end = meta->level_start[level + 1];
+    if (begin == end) continue;
+    for (uint32_t k = begin + blockIdx.x * blockDim.x + threadIdx.x; k < end; k += stride) {
+      const uint32_t node = t.level_nodes[k];
+      aggregate_node_ranged(node, level, t);
+      finalize_node(node, root_size, pqr, accm, t, SubtreeEndCount{}, strict_direct);
+    }
+    // grid barrier: the next (shallower) level reads this level's records
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      target += gridDim.x;
+      __threadfence();
+      atomicAdd(barrier, 1u);
+      while (*reinterpret_cast<volatile unsigned int*>(barrier) < target) {
+      }
+      __threadfence();
+    }
+    __syncthreads();
+  }
+}
+
 // psim_download_nodes only: the export sweep visits EVERY internal node level by level, so the buckets are
 // rebuilt to hold them all (the build only buckets the cells its level sweeps visit)
 __global__ void __launch_bounds__(256)

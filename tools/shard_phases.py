@@ -22,7 +22,7 @@ bd = electrolyte(n)
 b = Bodies(bd["pos"], vel=bd["vel"], mass=bd["mass"], radius=bd["radius"], charge=bd["charge"],
            species=bd["species"], ebody=bd["ebody"], erel=bd["erel"])
 sim = ShardedSimulation(b, bd["hw"], bd["hh"], device=lr, stream=torch.cuda.current_stream().cuda_stream,
-                        rank=rank, world=world, parity_mode=0)
+                        rank=rank, world=world, parity_mode=0, orchestration="python")
 sim.config.coulomb_constant = float(KE)
 for _ in range(3):
     sim.step_device()
