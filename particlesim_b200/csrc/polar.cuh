@@ -107,22 +107,14 @@ __device__ __forceinline__ bool polar_pair_force(float ix, float iy, float irad,
   return true;
 }
 
-// Three steps per batch, so that the expensive part runs on full warps:
-//   (1) every lane sweeps the candidates of its body's 3 x 3 (or wider) cell block at its own pace, only measuring
-//       distances, and notes the few that are inside the largest cutoff present in its shared-memory list;
-//   (2) the warp pools the lists: each noted (body, candidate) pair is two work items - the body as the polar body i,
-//       and the candidate as i with the body taking the reaction - and the lanes take items round-robin, whoever noted
-//       them; an item is one pair force (two to six softened point-source fields) written to the owner's result slot;
-//   (3) every lane adds up its own slots in list order, so a body's sum has the cell order of the reference's
-//       neighbour query whichever lane evaluated the terms: no atomics, deterministic, same bits as a private loop.
-// A list holds kPolarList candidates; a lane whose list is full waits for the warp's next drain.
+// Two passes per body so that the lanes of a warp stay together: (1) a cheap sweep over the candidates of the
+// 3 x 3 (or wider) cell block that only measures distances and notes the few that are inside either partner's
+// cutoff (~1 in 7 at the reference's densities), (2) the pair forces of the noted candidates - six softened
+// point-source fields with IEEE sqrt and divisions each - in cell order, as a dense loop of similar length in every
+// lane.  The candidate list lives in shared memory (kPolarList slots per thread) and is drained whenever it is full,
+// so the order of the additions is the cell order whatever its capacity.
 constexpr int kPolarThreads = 128;
-constexpr int kPolarList = 16;
-
-struct PolarMe {  // a lane's own body, readable by the whole warp
-  float x, y, q, r, relx, rely, qeff, inv_mass, mass;
-  uint32_t dip;
-};
+constexpr int kPolarList = 24;
 
 template <bool IEEE>
 __global__ void __launch_bounds__(kPolarThreads)
@@ -136,13 +128,8 @@ __global__ void __launch_bounds__(kPolarThreads)
                         float4* __restrict__ acc_mass) {
   __shared__ float s_polar_charge[kMaxSpecies];
   __shared__ uint32_t s_list[kPolarList][kPolarThreads];
-  __shared__ float2 s_res[2 * kPolarList][kPolarThreads];
-  __shared__ PolarMe s_me[kPolarThreads];
-  __shared__ int s_start[kPolarThreads];
   if (threadIdx.x < kMaxSpecies) s_polar_charge[threadIdx.x] = table_g[threadIdx.x].polar_charge;
   __syncthreads();
-  const uint32_t FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
   const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
   const float max_cutoff = __uint_as_float(*max_cutoff_bits);
   if (!(max_cutoff > 0.0f)) return;  // no polar body with an electron: the reference loop does nothing
@@ -152,120 +139,76 @@ __global__ void __launch_bounds__(kPolarThreads)
   const bool me_dip = live && (msp == 4u || msp == 5u) && ecount[i] != 0;
   float2 mrel = make_float2(0.f, 0.f);
   if (me_dip) mrel = erel[eoff[i]];
+  const float me_qeff = s_polar_charge[msp];
+  const float my_cut = __fmul_rn(3.0f, me.w), my_cut_sq = __fmul_rn(my_cut, my_cut);
   float4 am = live ? acc_mass[i] : make_float4(0.f, 0.f, 0.f, 1.f);
-  {
-    PolarMe m;
-    m.x = me.x, m.y = me.y, m.q = me.z, m.r = me.w, m.relx = mrel.x, m.rely = mrel.y, m.qeff = s_polar_charge[msp];
-    m.inv_mass = __frcp_rn(am.w), m.mass = am.w, m.dip = me_dip ? 1u : 0u;
-    s_me[threadIdx.x] = m;
-  }
-  __syncwarp();
+  const float inv_mass = __frcp_rn(am.w);
   float ax = 0.0f, ay = 0.0f;
   int filled = 0;
 
-  // steps (2) and (3) for what the lanes of this warp have noted so far; called by all 32 lanes together
   auto drain = [&]() {
-    int incl = 2 * filled;  // items of lane l occupy [start_l, start_l + 2 * filled_l)
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const int v = __shfl_up_sync(FULL, incl, off);
-      if (lane >= off) incl += v;
-    }
-    const int total = __shfl_sync(FULL, incl, 31);
-    s_start[threadIdx.x] = incl - 2 * filled;
-    __syncwarp();
-    for (int t = lane; t < total; t += 32) {
-      int owner = 0;  // the last lane whose start is <= t (lanes without items share their successor's start)
-#pragma unroll
-      for (int step = 16; step > 0; step >>= 1)
-        if (s_start[wbase + owner + step] <= t) owner += step;
-      const int item = t - s_start[wbase + owner], slot = item >> 1, dir = item & 1;
-      const uint32_t k = s_list[slot][wbase + owner];
-      const PolarMe m = s_me[wbase + owner];
-      const float4 a4 = __ldg(&recA[k]);
+    for (int t = 0; t < filled; ++t) {
+      const uint32_t k = s_list[t][threadIdx.x];
       const float4 b4 = __ldg(&recB[k]);
+      const float4 a4 = __ldg(&recA[k]);
       const uint32_t jbits = __float_as_uint(b4.x);
       const bool j_dip = (jbits & kPolarHasDipole) != 0;
+      const float rx = __fsub_rn(a4.x, me.x), ry = __fsub_rn(a4.y, me.y);
+      const float r2 = __fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry));
       uint32_t jsp = jbits & 0xffu;
       if (jsp >= kMaxSpecies) jsp = 0;
-      const float j_qeff = s_polar_charge[jsp];
-      const float rx = __fsub_rn(a4.x, m.x), ry = __fsub_rn(a4.y, m.y);
-      const float r2 = __fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry));
-      float fx = 0.0f, fy = 0.0f;
-      float2 out = make_float2(0.0f, 0.0f);
-      if (dir == 0) {
-        // the owner as the polar body i, the candidate as its neighbour j
-        const float cut = __fmul_rn(3.0f, m.r);
-        if (m.dip && r2 < __fmul_rn(cut, cut) &&
-            polar_pair_force<IEEE>(m.x, m.y, m.r, m.relx, m.rely, m.qeff, a4.x, a4.y, a4.w, a4.z, j_dip, b4.z, b4.w,
-                                   j_dip ? j_qeff : 0.0f, P, fx, fy))
-          out = make_float2(IEEE ? __fdiv_rn(fx, m.mass) : fx * m.inv_mass, IEEE ? __fdiv_rn(fy, m.mass) : fy * m.inv_mass);
-      } else {
-        // the candidate as the polar body i, the owner as its neighbour j: reaction  -force / m_owner
-        const float jc = __fmul_rn(3.0f, a4.w);
-        if (j_dip && r2 < __fmul_rn(jc, jc) &&
-            polar_pair_force<IEEE>(a4.x, a4.y, a4.w, b4.z, b4.w, j_qeff, m.x, m.y, m.r, m.q, m.dip != 0, m.relx, m.rely,
-                                   m.dip ? m.qeff : 0.0f, P, fx, fy))
-          out = make_float2(-(IEEE ? __fdiv_rn(fx, m.mass) : fx * m.inv_mass), -(IEEE ? __fdiv_rn(fy, m.mass) : fy * m.inv_mass));
+      const float j_qeff_tab = s_polar_charge[jsp];
+      float fx, fy;
+      // me as the polar body i, the candidate as its neighbour j
+      if (me_dip && r2 < my_cut_sq) {
+        if (polar_pair_force<IEEE>(me.x, me.y, me.w, mrel.x, mrel.y, me_qeff, a4.x, a4.y, a4.w, a4.z, j_dip, b4.z, b4.w,
+                             j_dip ? j_qeff_tab : 0.0f, P, fx, fy)) {
+          ax = __fadd_rn(ax, IEEE ? __fdiv_rn(fx, am.w) : fx * inv_mass);
+          ay = __fadd_rn(ay, IEEE ? __fdiv_rn(fy, am.w) : fy * inv_mass);
+        }
       }
-      s_res[item][wbase + owner] = out;
-    }
-    __syncwarp();
-    for (int t = 0; t < 2 * filled; ++t) {
-      const float2 r = s_res[t][threadIdx.x];
-      ax = __fadd_rn(ax, r.x), ay = __fadd_rn(ay, r.y);
+      // the candidate as the polar body i, me as its neighbour j: reaction  -force / m_me
+      if (j_dip) {
+        const float jc = __fmul_rn(3.0f, a4.w);
+        if (r2 < __fmul_rn(jc, jc)) {
+          if (polar_pair_force<IEEE>(a4.x, a4.y, a4.w, b4.z, b4.w, j_qeff_tab, me.x, me.y, me.w, me.z, me_dip, mrel.x, mrel.y,
+                               me_dip ? me_qeff : 0.0f, P, fx, fy)) {
+            ax = __fsub_rn(ax, IEEE ? __fdiv_rn(fx, am.w) : fx * inv_mass);
+            ay = __fsub_rn(ay, IEEE ? __fdiv_rn(fy, am.w) : fy * inv_mass);
+          }
+        }
+      }
     }
     filled = 0;
-    __syncwarp();
   };
 
-  // step (1): each lane scans on its own until its list is full or its cells are exhausted, then the warp drains
-  uint32_t k = 0, k1 = 0;
-  int x0 = 0, x1 = -1, y1 = -1, xx = 0, yy = 0;
-  float any_cut_sq = 0.0f;
-  bool scanning = live;
   if (live) {
     const uint32_t c = body_cell[i];
     const int cx = (int)(c % P.g.gx), cy = (int)(c / P.g.gx);
     const int range = (int)ceilf(max_cutoff / P.g.cell_size);
-    const int y0 = max(cy - range, 0);
-    y1 = min(cy + range, (int)P.g.gy - 1);
-    x0 = max(cx - range, 0), x1 = min(cx + range, (int)P.g.gx - 1);
+    const int y0 = max(cy - range, 0), y1 = min(cy + range, (int)P.g.gy - 1);
+    const int x0 = max(cx - range, 0), x1 = min(cx + range, (int)P.g.gx - 1);
     // any pair closer than this may interact (either partner's 3 * radius, bounded by the largest one present)
-    any_cut_sq = __fmul_rn(max_cutoff, max_cutoff);
-    xx = x0, yy = y0;
-    const uint32_t cc = (uint32_t)xx + (uint32_t)yy * P.g.gx;
-    k = cell_start[cc], k1 = cell_end[cc];
-  }
-  do {
-    while (scanning && filled < kPolarList) {
-      if (k < k1) {
-        const float4 a4 = __ldg(&recA[k]);
-        const float rx = __fsub_rn(a4.x, me.x), ry = __fsub_rn(a4.y, me.y);
-        const float r2 = __fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry));
-        if (r2 < any_cut_sq) {
+    const float any_cut_sq = __fmul_rn(max_cutoff, max_cutoff);
+    for (int y = y0; y <= y1; ++y) {
+      for (int x = x0; x <= x1; ++x) {
+        const uint32_t cc = (uint32_t)x + (uint32_t)y * P.g.gx;
+        const uint32_t k1 = cell_end[cc];
+        for (uint32_t k = cell_start[cc]; k < k1; ++k) {
+          const float4 a4 = __ldg(&recA[k]);
+          const float rx = __fsub_rn(a4.x, me.x), ry = __fsub_rn(a4.y, me.y);
+          const float r2 = __fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry));
+          if (!(r2 < any_cut_sq)) continue;
           const float4 b4 = __ldg(&recB[k]);
-          if (__float_as_uint(b4.y) != i && (me_dip || (__float_as_uint(b4.x) & kPolarHasDipole))) {
-            s_list[filled][threadIdx.x] = k;
-            ++filled;
-          }
+          if (__float_as_uint(b4.y) == i) continue;
+          if (!me_dip && !(__float_as_uint(b4.x) & kPolarHasDipole)) continue;
+          s_list[filled][threadIdx.x] = k;
+          if (++filled == kPolarList) drain();
         }
-        ++k;
-      } else if (xx < x1) {
-        ++xx;
-        const uint32_t cc = (uint32_t)xx + (uint32_t)yy * P.g.gx;
-        k = cell_start[cc], k1 = cell_end[cc];
-      } else if (yy < y1) {
-        ++yy, xx = x0;
-        const uint32_t cc = (uint32_t)xx + (uint32_t)yy * P.g.gx;
-        k = cell_start[cc], k1 = cell_end[cc];
-      } else {
-        scanning = false;
       }
     }
-    __syncwarp();
-    drain();
-  } while (__any_sync(FULL, scanning));
+  }
+  drain();
   if (live) {
     am.x = __fadd_rn(am.x, ax);
     am.y = __fadd_rn(am.y, ay);
