@@ -62,7 +62,7 @@ typedef struct {
                                bit (csrc/strict.cuh) - node centres equal the reference's for leaf_capacity 1
                                and fields meet the 1e-5 bar against it; 0: f64 sums carried up the tree
                                (~10 % faster builds, fields ~1e-4 from the reference: its own summation noise).
-                               Sharded builds (psim_shard_phase) support 0 only. */
+                               Both modes work in sharded builds (each rank sums the centres of its own piece). */
   uint32_t reserved[4];
 } psim_config;
 
@@ -330,8 +330,8 @@ int32_t psim_shard_ptrs(psim_ctx *ctx, uint64_t *out8);
  *   psim_step_sharded  = psim_step with both builds sharded, each rank computing field / polar / short-range /
  *                        integrator for its slice of the Morton order and an equal slice of the electrons, the slices
  *                        all-gathered in place (positions at once, velocities behind the next build's first phases).
- * Results are bit-identical to psim_step on one GPU with strict_centres = 0 (the sharded build carries f64 centre
- * sums).  psim_phase_times works after psim_step_sharded (the exchanges are inside the phases they follow). */
+ * Results are bit-identical to psim_step on one GPU (same psim_config; strict_centres included: every rank sums the
+ * reference's serial f32 centres for the nodes of its own piece).  psim_phase_times works after psim_step_sharded (the exchanges are inside the phases they follow). */
 uint64_t psim_shard_capacity(uint64_t n, uint32_t nranks);
 int32_t psim_comm_unique_id(uint8_t *out128);
 int32_t psim_comm_init(psim_ctx *ctx, const uint8_t *unique_id128, uint32_t rank, uint32_t nranks);

@@ -613,13 +613,21 @@ int32_t ensure_strict(psim_ctx* ctx) {
 
 // psim_config.strict_centres: overwrite the centres of all charged internal nodes with the reference's
 // serial f32 sums (strict.cuh); runs after the tree is complete and before the traversal compaction
-int32_t strict_stage(psim_ctx* ctx) {
+int32_t strict_stage(psim_ctx* ctx, bool sharded = false) {
   const int32_t rc = ensure_strict(ctx);
   if (rc) return rc;
   const uint32_t n = ctx->n;
   cudaStream_t st = ctx->stream;
   BodyArrays& b = ctx->b[ctx->cur];
   StrictArrays& S = ctx->strict;
+  if (sharded) {
+    // the rank's own piece of the tree: its chains with a node of more than kStrictDirect bodies (the single-GPU emit
+    // kernel reports them itself).  Body indices are global (the sorted bodies are replicated), node indices local.
+    CK(cudaMemsetAsync(S.counters + 4, 0, sizeof(uint32_t), st));
+    strict_candidates_shard_kernel<<<grid_for(ctx, ctx->sh.n_local, 256, 16), 256, 0, st>>>(
+        ctx->sh.meta, ctx->le, ctx->nodebase, ctx->t, kStrictDirect, S.cand, S.counters + 4, S.cand_cap);
+    LAUNCHED(ctx);
+  }
   CK(exclusive_scan(ChargedBodyFn{b.pqr}, n, S.cidx, ctx->scan_partials, S.cidx + n, st));
   strict_addends_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(b.pqr, n, S.cidx, S.cw, S.hist, S.counters);
   strict_chain_count_kernel<<<grid_for(ctx, n / 16 + 1, 256, 8), 256, 0, st>>>(S.cand, S.counters + 4, S.cand_cap, S.cidx,
@@ -742,7 +750,6 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
 int32_t shard_phase(psim_ctx* ctx, int phase, int mode, float hw, float hh, uint32_t* out) {
   auto& S = ctx->sh;
   if (!S.on) return fail(ctx, PSIM_E_STATE, "psim_shard_phase: call psim_shard_init first");
-  if (ctx->cfg.strict_centres) return fail(ctx, PSIM_E_ARG, "sharded build: strict_centres is a single-GPU parity switch");
   if (ctx->cfg.parity_mode == 2)
     return fail(ctx, PSIM_E_ARG, "sharded build: parity_mode 2 walks the whole node array, which only a single-GPU build has");
   if (phase != 0 && phase != S.phase) return fail(ctx, PSIM_E_STATE, "psim_shard_phase: phases must run in order");
@@ -848,7 +855,13 @@ int32_t shard_phase(psim_ctx* ctx, int phase, int mode, float hw, float hh, uint
         heap_sweep_kernel<<<grid_for(ctx, 1u << (2 * d), 256, 1), 256, 0, st>>>(S.heap, d);
       heap_writeback_kernel<<<grid_for(ctx, kTopSlots, 256, 2), 256, 0, st>>>(S.meta, S.heap, ctx->t);
       finalize_nodes_shard_kernel<<<grid_for(ctx, (uint64_t)nl * 2 + 1, 256, 16), 256, 0, st>>>(
-          ctx->meta, S.meta, b.pqr, b.accm, S.lkeys, S.binprefix, ctx->t);
+          ctx->meta, S.meta, b.pqr, b.accm, S.lkeys, S.binprefix, ctx->t, ctx->cfg.strict_centres ? kStrictDirect : 0u);
+      if (ctx->cfg.strict_centres) {
+        // node centres by the reference's serial f32 sums (strict.cuh) for this rank's piece, the cells above the
+        // bins included: each belongs to the piece of the rank that owns its first body
+        const int32_t rc = strict_stage(ctx, true);
+        if (rc) return rc;
+      }
       CK(exclusive_scan_dyn(ChargedFlagFn{ctx->t.ndepth}, &S.meta->M_local, ctx->node_cap, ctx->trav_rank,
                             ctx->scan_partials, &S.meta->T_local, st));
       CK(cudaMemsetAsync(S.xbuf, 0, (kBins + kMaxRanks) * sizeof(unsigned long long), st));

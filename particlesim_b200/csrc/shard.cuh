@@ -26,6 +26,7 @@
 
 #include "shard_logic.cuh"
 #include "sort.cuh"
+#include "strict.cuh"
 #include "tree.cuh"
 
 namespace psim {
@@ -376,15 +377,43 @@ __global__ void __launch_bounds__(256)
     finalize_nodes_shard_kernel(const TreeMeta* __restrict__ meta, const ShardMeta* __restrict__ sm,
                                 const float4* __restrict__ pqr, const float4* __restrict__ accm,
                                 const uint64_t* __restrict__ lkeys, const uint32_t* __restrict__ binprefix,
-                                TreeArrays t) {
+                                TreeArrays t, uint32_t strict_direct) {
   const uint32_t ml = sm->M_local, noff = sm->node_off;
   if (ml > t.node_cap) return;
   t.nodeA -= noff, t.nodeB -= noff, t.rec -= noff, t.ndepth -= noff;
   const float root_size = meta->root.size;
   const SubtreeEndShard end{noff, noff + ml, sm->M_total, meta->n, sm->body_base, t.nodeB, lkeys, binprefix};
   const uint32_t stride = gridDim.x * blockDim.x;
+  // the subtree end of a node is read from its successor's record: a node's own B.z may be written concurrently,
+  // B.y (what SubtreeEndShard reads) never is
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < ml; k += stride)
-    finalize_node(noff + k, root_size, pqr, accm, t, end);
+    finalize_node(noff + k, root_size, pqr, accm, t, end, strict_direct, strict_direct != 0);
+}
+
+// psim_config.strict_centres in the sharded build: the chains (nodes that start at the same body) of this rank's
+// piece that own a node of more than `direct` bodies, in the format the single-GPU emit kernel reports them
+// (tree.cuh StrictEmit; node and body indices are global)
+__global__ void __launch_bounds__(256)
+    strict_candidates_shard_kernel(const ShardMeta* __restrict__ sm, const uint16_t* __restrict__ le,
+                                   const uint32_t* __restrict__ nodebase, TreeArrays t, uint32_t direct,
+                                   uint4* __restrict__ cand, uint32_t* __restrict__ cand_count, uint32_t cand_cap) {
+  const uint32_t first = sm->hl, count = sm->n_local, noff = sm->node_off, body_base = sm->body_base;
+  if (sm->M_local > t.node_cap) return;
+  t.nodeB -= noff;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) {
+    const uint32_t a = first + k;
+    const uint16_t lev = le[a];
+    const int K = le_ell(lev) - le_lambda(lev) - 1;  // internal nodes base .. base + K - 1, shallowest first
+    if (K < 1) continue;
+    const uint32_t base = nodebase[a];  // global (globalize_nodebase_kernel)
+    uint32_t big = 0;
+    while ((int)big < K && t.nodeB[base + big].z > direct) ++big;  // counts shrink with depth
+    if (big == 0) continue;
+    const uint32_t slot = atomicAdd(cand_count, 1u);
+    // the strict kernels index the rank's own node arrays: local node index
+    if (slot < cand_cap) cand[slot] = make_uint4(a + body_base, base - noff, big - 1u, t.nodeB[base].z);
+  }
 }
 
 // table 2: (local traversal rank of the first node of each owned, non-empty bin) + 1, and T_local

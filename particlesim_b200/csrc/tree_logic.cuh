@@ -327,15 +327,18 @@ PSIM_HD void strict_centre_direct(uint32_t b0, uint32_t b1, const float4* pqr, c
 // strict_direct > 0 (psim_config.strict_centres, single-GPU build): nodes of at most that many bodies get
 // the reference's serial sums right here, where their bodies are still in cache; larger ones are left to
 // strict.cuh.
+// set_count (sharded build, whose emit does not know the ranges of internal cells): the body count goes into B.z.
 template <class SubtreeEnd>
 PSIM_HD void finalize_node(uint32_t node, float root_size, const float4* pqr, const float4* accm,
-                           const TreeArrays& t, const SubtreeEnd& subtree_end, uint32_t strict_direct = 0) {
+                           const TreeArrays& t, const SubtreeEnd& subtree_end, uint32_t strict_direct = 0,
+                           bool set_count = false) {
   uint4 nb = t.nodeB[node];
   if (nb.w & kNodeLeaf) return;
   const NodeRec r = t.rec[node];
   const uint32_t c = r.next & kNextMask;
   nb.x = c;
   if (r.aq > 0.0) nb.w |= kNodeCharged;
+  if (set_count) nb.z = subtree_end(c, nb) - nb.y;
   t.nodeB[node] = nb;
   float px = 0.0f, py = 0.0f;
   if (strict_direct && nb.z <= strict_direct) {

@@ -241,7 +241,6 @@ class ShardedSimulation(Simulation):
         self.wb, self.we = shard_width(n, world), shard_width(m, world)
         kw["max_bodies"] = max(self.wb * world, 1)
         kw["max_electrons"] = max(self.we * world, 1)
-        kw.setdefault("strict_centres", False)  # the key-range sharded build carries f64 centre sums only
         super().__init__(bodies, domain_width, domain_height, **kw)
         import torch
         import torch.distributed as dist

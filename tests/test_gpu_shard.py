@@ -22,7 +22,6 @@ def make_sim(bodies, **kw):
 
 
 def make_ranks(bodies, world, **kw):
-    kw.setdefault("strict_centres", False)  # sharded builds carry f64 centre sums only
     sims = []
     for r in range(world):
         s = make_sim(bodies, **kw)
@@ -68,7 +67,7 @@ def test_sharded_build_equals_single_gpu_build(cuda_device, name, gen, kw, mode,
     from particlesim_b200.parallel import LoopbackComm, sharded_build
     bodies = gen()
     hw, hh = np.float32(bodies["hw"]), np.float32(bodies["hh"])
-    one = make_sim(bodies, strict_centres=False, **kw)
+    one = make_sim(bodies, **kw)
     one._call("psim_shard_init", 0, 1)
     one.rank, one.world, one._shard_nb = 0, 1, max(len(bodies["pos"]), 1)
     one._call("psim_build", mode, hw, hh)
@@ -98,7 +97,7 @@ def test_sharded_steps_equal_single_gpu_steps(cuda_device):
     from particlesim_b200.parallel import LoopbackComm, sharded_build
     bodies = electrolyte(40_000)
     bodies["species"][:4000] = 1
-    one = make_sim(bodies, strict_centres=False)
+    one = make_sim(bodies)
     sims = make_ranks(bodies, 4)
     comm = LoopbackComm()
     # psim_step bins the LJ pass at the largest LJ cutoff (the pair sets do not depend on the cell size, the
@@ -137,7 +136,7 @@ def test_sharded_build_at_scale(cuda_device):
     from particlesim_b200.parallel import LoopbackComm, sharded_build
     bodies = clustered(4_000_000)
     hw, hh = np.float32(bodies["hw"]), np.float32(bodies["hh"])
-    one = make_sim(bodies, strict_centres=False)
+    one = make_sim(bodies)
     one._call("psim_shard_init", 0, 1)
     one.rank, one.world, one._shard_nb = 0, 1, len(bodies["pos"])
     one._call("psim_build", 0, hw, hh)

@@ -1,6 +1,6 @@
 """torchrun --nproc-per-node G tools/check_sharded.py [n] [library|python|repl]: three sharded hot-path steps (both
-builds, field, polar, LJ, integrator, electrons) over real NCCL must leave exactly the single-GPU state (same centre
-mode: the sharded build carries f64 centre sums).  Exits non-zero on a mismatch; tests/test_gpu_multi.py runs it."""
+builds, field, polar, LJ, integrator, electrons) over real NCCL must leave exactly the single-GPU state (default
+configuration: the reference's serial-sum node centres on both sides).  Exits non-zero on a mismatch; tests/test_gpu_multi.py runs it."""
 import os
 import sys
 
@@ -52,7 +52,7 @@ torch.cuda.synchronize()
 a = state(sh)
 ok = True
 if rank == 0:
-    one = mk(Simulation, strict_centres=False)
+    one = mk(Simulation)
     for _ in range(3):
         one.step_device()
     b = state(one)
