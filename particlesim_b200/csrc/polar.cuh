@@ -107,6 +107,78 @@ __device__ __forceinline__ bool polar_pair_force(float ix, float iy, float irad,
   return true;
 }
 
+// Both directions of a dipole-dipole pair at once.  The four site-to-site separations (nucleus / electron of A against
+// nucleus / electron of B) are the same whichever body plays "i": d changes sign, dist, min_sep (a + b = b + a) and the
+// denominator do not.  So the square roots and denominators (IEEE) or reciprocals (fast) are taken once per site pair
+// and the two directions only differ in the source charge - term by term the values polar_pair_force gives.
+struct SitePair {
+  float dx, dy, w;  // d = point - source; w = denominator (IEEE) or its reciprocal (fast); w = 0: no field (r_eff == 0)
+};
+template <bool IEEE>
+__device__ __forceinline__ SitePair site_pair(float px, float py, float pr, float sx, float sy, float sr, float eps_sq) {
+  SitePair g;
+  if (!IEEE) {
+    g.dx = px - sx, g.dy = py - sy;
+    const float d2 = fmaf(g.dx, g.dx, g.dy * g.dy);
+    const float dist = d2 > 0.0f ? d2 * rsqrtf(d2) : 0.0f;
+    const float r_eff = fmaxf(dist, pr + sr);
+    g.w = r_eff == 0.0f ? 0.0f : __frcp_rn(fmaf(r_eff, r_eff, eps_sq) * r_eff);
+    return g;
+  }
+  g.dx = __fsub_rn(px, sx), g.dy = __fsub_rn(py, sy);
+  const float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(g.dx, g.dx), __fmul_rn(g.dy, g.dy)));
+  const float r_eff = fmaxf(dist, __fadd_rn(pr, sr));
+  g.w = r_eff == 0.0f ? 0.0f : __fmul_rn(__fadd_rn(__fmul_rn(r_eff, r_eff), eps_sq), r_eff);
+  return g;
+}
+// field at the pair's point from charge q at its source (sign = +1), or at its source from q at its point (-1)
+template <bool IEEE>
+__device__ __forceinline__ float2 site_field(const SitePair& g, float sign, float q, float k_e) {
+  if (fabsf(q) < 1.1920929e-07f || g.w == 0.0f) return make_float2(0.f, 0.f);
+  if (!IEEE) {
+    const float s = sign * (k_e * q) * g.w;
+    return make_float2(g.dx * s, g.dy * s);
+  }
+  const float s = __fdiv_rn(__fmul_rn(k_e, q), g.w);
+  return make_float2(sign * __fmul_rn(g.dx, s), sign * __fmul_rn(g.dy, s));
+}
+// A and B both EC / DMC with an electron, ConjugatePair model: f0 = force on A as the polar body (B its neighbour),
+// f1 = force on B as the polar body (A its neighbour); ok0 / ok1 false where the reference skips (all fields zero)
+template <bool IEEE>
+__device__ __forceinline__ void polar_pair_both(float ax_, float ay_, float ar, float aq, float arx, float ary, float a_qeff,
+                                                float bx, float by, float br, float bq, float brx, float bry, float b_qeff,
+                                                const PolarParams& P, float2& f0, bool& ok0, float2& f1, bool& ok1) {
+  const float aex = __fadd_rn(ax_, arx), aey = __fadd_rn(ay_, ary), bex = __fadd_rn(bx, brx), bey = __fadd_rn(by, bry);
+  const SitePair NN = site_pair<IEEE>(ax_, ay_, ar, bx, by, br, P.epsilon_sq);      // A nucleus  <- B nucleus
+  const SitePair EN = site_pair<IEEE>(aex, aey, 0.0f, bx, by, br, P.epsilon_sq);    // A electron <- B nucleus
+  const SitePair NE = site_pair<IEEE>(ax_, ay_, ar, bex, bey, 0.0f, P.epsilon_sq);  // A nucleus  <- B electron
+  const SitePair EE = site_pair<IEEE>(aex, aey, 0.0f, bex, bey, 0.0f, P.epsilon_sq);
+  auto add = [](float2& a, const float2 t) { a.x = __fadd_rn(a.x, t.x), a.y = __fadd_rn(a.y, t.y); };
+  auto subt = [](float2& a, const float2 t) { a.x = __fsub_rn(a.x, t.x), a.y = __fsub_rn(a.y, t.y); };
+  {  // A as i (forces.rs:99-158 with i = A, j = B)
+    float2 fn = make_float2(0.f, 0.f), fe = make_float2(0.f, 0.f);
+    add(fn, site_field<IEEE>(NN, 1.0f, bq, P.k_e));
+    add(fe, site_field<IEEE>(EN, 1.0f, bq, P.k_e));
+    add(fn, site_field<IEEE>(NN, 1.0f, b_qeff, P.k_e));
+    subt(fn, site_field<IEEE>(NE, 1.0f, b_qeff, P.k_e));
+    add(fe, site_field<IEEE>(EN, 1.0f, b_qeff, P.k_e));
+    subt(fe, site_field<IEEE>(EE, 1.0f, b_qeff, P.k_e));
+    ok0 = !(fn.x == 0.0f && fn.y == 0.0f && fe.x == 0.0f && fe.y == 0.0f);
+    f0 = make_float2(__fmul_rn(__fsub_rn(fn.x, fe.x), a_qeff), __fmul_rn(__fsub_rn(fn.y, fe.y), a_qeff));
+  }
+  {  // B as i, A as j: the same site pairs seen from the other end
+    float2 fn = make_float2(0.f, 0.f), fe = make_float2(0.f, 0.f);
+    add(fn, site_field<IEEE>(NN, -1.0f, aq, P.k_e));       // B nucleus  <- A nucleus
+    add(fe, site_field<IEEE>(NE, -1.0f, aq, P.k_e));       // B electron <- A nucleus
+    add(fn, site_field<IEEE>(NN, -1.0f, a_qeff, P.k_e));
+    subt(fn, site_field<IEEE>(EN, -1.0f, a_qeff, P.k_e));  // B nucleus  <- A electron
+    add(fe, site_field<IEEE>(NE, -1.0f, a_qeff, P.k_e));
+    subt(fe, site_field<IEEE>(EE, -1.0f, a_qeff, P.k_e));  // B electron <- A electron
+    ok1 = !(fn.x == 0.0f && fn.y == 0.0f && fe.x == 0.0f && fe.y == 0.0f);
+    f1 = make_float2(__fmul_rn(__fsub_rn(fn.x, fe.x), b_qeff), __fmul_rn(__fsub_rn(fn.y, fe.y), b_qeff));
+  }
+}
+
 // Two passes per body so that the lanes of a warp stay together: (1) a cheap sweep over the candidates of the
 // 3 x 3 (or wider) cell block that only measures distances and notes the few that are inside either partner's
 // cutoff (~1 in 7 at the reference's densities), (2) the pair forces of the noted candidates - six softened
@@ -159,6 +231,23 @@ __global__ void __launch_bounds__(kPolarThreads)
       if (jsp >= kMaxSpecies) jsp = 0;
       const float j_qeff_tab = s_polar_charge[jsp];
       float fx, fy;
+      const float jc = __fmul_rn(3.0f, a4.w);
+      if (me_dip && j_dip && P.dipole_model == 1 && r2 < my_cut_sq && r2 < __fmul_rn(jc, jc)) {
+        // dipole against dipole inside both cutoffs (the bulk of the work): both directions from shared geometry
+        float2 f0, f1;
+        bool ok0, ok1;
+        polar_pair_both<IEEE>(me.x, me.y, me.w, me.z, mrel.x, mrel.y, me_qeff, a4.x, a4.y, a4.w, a4.z, b4.z, b4.w,
+                              j_qeff_tab, P, f0, ok0, f1, ok1);
+        if (ok0) {
+          ax = __fadd_rn(ax, IEEE ? __fdiv_rn(f0.x, am.w) : f0.x * inv_mass);
+          ay = __fadd_rn(ay, IEEE ? __fdiv_rn(f0.y, am.w) : f0.y * inv_mass);
+        }
+        if (ok1) {
+          ax = __fsub_rn(ax, IEEE ? __fdiv_rn(f1.x, am.w) : f1.x * inv_mass);
+          ay = __fsub_rn(ay, IEEE ? __fdiv_rn(f1.y, am.w) : f1.y * inv_mass);
+        }
+        continue;
+      }
       // me as the polar body i, the candidate as its neighbour j
       if (me_dip && r2 < my_cut_sq) {
         if (polar_pair_force<IEEE>(me.x, me.y, me.w, mrel.x, mrel.y, me_qeff, a4.x, a4.y, a4.w, a4.z, j_dip, b4.z, b4.w,
@@ -169,7 +258,6 @@ __global__ void __launch_bounds__(kPolarThreads)
       }
       // the candidate as the polar body i, me as its neighbour j: reaction  -force / m_me
       if (j_dip) {
-        const float jc = __fmul_rn(3.0f, a4.w);
         if (r2 < __fmul_rn(jc, jc)) {
           if (polar_pair_force<IEEE>(a4.x, a4.y, a4.w, b4.z, b4.w, j_qeff_tab, me.x, me.y, me.w, me.z, me_dip, mrel.x, mrel.y,
                                me_dip ? me_qeff : 0.0f, P, fx, fy)) {

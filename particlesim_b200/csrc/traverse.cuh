@@ -350,7 +350,13 @@ __device__ __forceinline__ float2 bh_group_walk(const float4* __restrict__ nodeA
       // traversal records of internal nodes carry their children (link_children_kernel): B.y, B.z and the
       // bits of A.w are children 1..3; the cell size is the root's halved `depth` times, exactly
       c3 = __float_as_uint(na.w);
-      na.w = ldexpf(root_size, -(int)(nb.w & kNodeDepthMask));
+      {
+        // root_size * 2^-depth: an exponent subtraction while the result stays a normal number (always, for any
+        // root a simulation can have: depth <= 32), ldexpf otherwise
+        const uint32_t rb = __float_as_uint(root_size), dep = nb.w & kNodeDepthMask;
+        const uint32_t ex = (rb >> 23) & 0xffu;
+        na.w = (ex > dep && ex != 0xffu) ? __uint_as_float(rb - (dep << 23)) : ldexpf(root_size, -(int)dep);
+      }
       cls = 0;
       if (box_ok) {
         const float s_t = na.w * P.inv_theta;

@@ -22,6 +22,10 @@ for gen, n in ((electrolyte, 30_011), (clustered, 20_003)):
         for _ in range(2):
             sim.step_device()
         sim.sync()
+        sim.collide(passes=2)
+        sim.quadtree.build(sim.bodies)
+        don = np.arange(0, n, 501).astype(np.uint32)
+        sim.hop_alignment(don, [np.array([(d + 1) % n, (d + 7) % n], np.uint32) for d in don])
         nodes = sim.quadtree.nodes
         sim._call("psim_cell_build", bd["hw"], bd["hh"], 11.88)
         sim._neighbors(np.arange(0, n, 97), 3.96, False)
