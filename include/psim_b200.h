@@ -330,12 +330,21 @@ int32_t psim_shard_ptrs(psim_ctx *ctx, uint64_t *out8);
  *   psim_step_sharded  = psim_step with both builds sharded, each rank computing field / polar / short-range /
  *                        integrator for its slice of the Morton order and an equal slice of the electrons, the slices
  *                        all-gathered in place (positions at once, velocities behind the next build's first phases).
+ * Traversal exchange: by default each rank sends every other rank only the traversal records that rank's own targets
+ * (its slice of the bodies, the sample points of its slice of the electrons) can reach - the locally essential tree,
+ * a geometric superset test on the parent cell against the destination's bins (csrc/let.cuh); the records keep their
+ * global indices, so the walks and their results are unchanged.  Consequence: after such a build a rank answers
+ * field queries for ITS targets only; psim_acc_points / psim_hop_alignment return PSIM_E_STATE.  PSIM_LET=0 in the
+ * environment at psim_comm_init time restores the full all-gather (every rank can then query any point).
+ * psim_comm_stats: out[0] = records this rank sent in the last exchange, out[1] = what the full all-gather would have
+ * sent, out[2] = LET enabled, out[3] = the current tree is a LET.
  * Results are bit-identical to psim_step on one GPU (same psim_config; strict_centres included: every rank sums the
  * reference's serial f32 centres for the nodes of its own piece).  psim_phase_times works after psim_step_sharded (the exchanges are inside the phases they follow). */
 uint64_t psim_shard_capacity(uint64_t n, uint32_t nranks);
 int32_t psim_comm_unique_id(uint8_t *out128);
 int32_t psim_comm_init(psim_ctx *ctx, const uint8_t *unique_id128, uint32_t rank, uint32_t nranks);
 int32_t psim_comm_destroy(psim_ctx *ctx);
+int32_t psim_comm_stats(psim_ctx *ctx, uint64_t *out4);
 int32_t psim_build_sharded(psim_ctx *ctx, int32_t mode, float hw, float hh);
 int32_t psim_step_sharded(psim_ctx *ctx, const psim_step_params *p);
 /* the caller wrote positions into the device arrays (e.g. an all-gather): tree and grid are stale */

@@ -121,6 +121,7 @@ SIGNATURES = {
     "psim_comm_unique_id": (_i32, [_vp]),
     "psim_comm_init": (_i32, [_vp, _vp, _u32, _u32]),
     "psim_comm_destroy": (_i32, [_vp]),
+    "psim_comm_stats": (_i32, [_vp, _vp]),
     "psim_build_sharded": (_i32, [_vp, _i32, _f, _f]),
     "psim_step_sharded": (_i32, [_vp, _vp]),
     "psim_step_host": (_i32, [_vp, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

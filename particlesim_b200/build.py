@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpsim_b200.so")
 SOURCES = ["api.cu"]
-HEADERS = ["psim_core.cuh", "sort.cuh", "tree_logic.cuh", "tree.cuh", "traverse.cuh", "cells.cuh", "shard.cuh", "shard_logic.cuh", "polar.cuh", "neighbors.cuh", "strict.cuh", "strict_logic.cuh", "hopping.cuh", "comm.h", "collide.cuh",
+HEADERS = ["psim_core.cuh", "sort.cuh", "tree_logic.cuh", "tree.cuh", "traverse.cuh", "cells.cuh", "shard.cuh", "shard_logic.cuh", "polar.cuh", "neighbors.cuh", "strict.cuh", "strict_logic.cuh", "hopping.cuh", "comm.h", "collide.cuh", "let.cuh",
            os.path.join("..", "..", "include", "psim_b200.h")]
 
 

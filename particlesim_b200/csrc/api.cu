@@ -17,6 +17,7 @@
 #include "collide.cuh"
 #include "comm.h"
 #include "hopping.cuh"
+#include "let.cuh"
 #include "polar.cuh"
 #include "sort.cuh"
 #include "traverse.cuh"
@@ -104,6 +105,7 @@ struct psim_ctx {
   struct Shard {
     bool on = false;
     bool tree_is_sharded = false;  // the node array holds this rank's piece only
+    bool tree_is_let = false;      // ... and the traversal arrays only what this rank's own targets can reach
     uint32_t rank = 0, world = 1;
     int phase = 0, mode = 0;
     uint32_t halo = 0, n_local = 0, hl = 0, L = 0, s_lo = 0;
@@ -131,6 +133,13 @@ struct psim_ctx {
     void* stage = nullptr;  // padded all-gather staging
     size_t stage_bytes = 0;
     bool vel_pending = false;
+    // locally essential traversal tree (let.cuh)
+    bool let = true, let_poison = false;
+    LetRegions* regions = nullptr;
+    LetRec *send = nullptr, *recv = nullptr;
+    uint32_t *cnt = nullptr, *cnt_all = nullptr;
+    uint32_t cap_per_rank = 0;
+    uint64_t let_sent = 0, let_full = 0;  // records sent by the last exchange / what the full all-gather would send
   } comm;
 
   // cells
@@ -613,6 +622,21 @@ int32_t ensure_strict(psim_ctx* ctx) {
 
 // psim_config.strict_centres: overwrite the centres of all charged internal nodes with the reference's
 // serial f32 sums (strict.cuh); runs after the tree is complete and before the traversal compaction
+// charged-body index and addends of the sorted bodies (needed from the emit kernel on); resets the stage's counters
+int32_t strict_prepare(psim_ctx* ctx) {
+  const int32_t rc = ensure_strict(ctx);
+  if (rc) return rc;
+  const uint32_t n = ctx->n;
+  cudaStream_t st = ctx->stream;
+  BodyArrays& b = ctx->b[ctx->cur];
+  StrictArrays& S = ctx->strict;
+  CK(exclusive_scan(ChargedBodyFn{b.pqr}, n, S.cidx, ctx->scan_partials, S.cidx + n, st));
+  strict_addends_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(b.pqr, n, S.cidx, S.cw, S.hist, S.counters);
+  CK(cudaMemsetAsync(S.counters + 4, 0, sizeof(uint32_t), st));
+  ctx->launches += 4;
+  return PSIM_OK;
+}
+
 int32_t strict_stage(psim_ctx* ctx, bool sharded = false) {
   const int32_t rc = ensure_strict(ctx);
   if (rc) return rc;
@@ -623,13 +647,10 @@ int32_t strict_stage(psim_ctx* ctx, bool sharded = false) {
   if (sharded) {
     // the rank's own piece of the tree: its chains with a node of more than kStrictDirect bodies (the single-GPU emit
     // kernel reports them itself).  Body indices are global (the sorted bodies are replicated), node indices local.
-    CK(cudaMemsetAsync(S.counters + 4, 0, sizeof(uint32_t), st));
     strict_candidates_shard_kernel<<<grid_for(ctx, ctx->sh.n_local, 256, 16), 256, 0, st>>>(
         ctx->sh.meta, ctx->le, ctx->nodebase, ctx->t, kStrictDirect, S.cand, S.counters + 4, S.cand_cap);
     LAUNCHED(ctx);
   }
-  CK(exclusive_scan(ChargedBodyFn{b.pqr}, n, S.cidx, ctx->scan_partials, S.cidx + n, st));
-  strict_addends_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(b.pqr, n, S.cidx, S.cw, S.hist, S.counters);
   strict_chain_count_kernel<<<grid_for(ctx, n / 16 + 1, 256, 8), 256, 0, st>>>(S.cand, S.counters + 4, S.cand_cap, S.cidx,
                                                                                S.hist, S.counters);
   strict_chain_scatter_kernel<<<grid_for(ctx, n / 16 + 1, 1024, 8), 256, 0, st>>>(S.cand, S.counters + 4, S.cand_cap, 1024,
@@ -640,7 +661,7 @@ int32_t strict_stage(psim_ctx* ctx, bool sharded = false) {
   strict_blockfn_kernel<<<grid_for(ctx, (uint64_t)n / 16 + 1, kStreamThreads, 3), kStreamThreads, kStreamSmem, st>>>(S);
   strict_compose_kernel<<<ctx->sm_count * 4, 96, 0, st>>>(ctx->meta, ctx->t, S);
   strict_slow_kernel<<<grid_for(ctx, (uint64_t)n * 2, 128, 16), 128, 0, st>>>(ctx->meta, b.pqr, b.accm, ctx->t, S.counters);
-  ctx->launches += 12;
+  ctx->launches += 8;
   return PSIM_OK;
 }
 
@@ -700,12 +721,12 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
   ctx->launches += 3;
   level_scan_kernel<<<1, 32, 0, st>>>(ctx->meta, ctx->node_cap);
   LAUNCHED(ctx);
-  StrictEmit se = {0, nullptr, nullptr, 0};
+  StrictEmit se = {0, nullptr, nullptr, nullptr, nullptr, 0};
   if (ctx->cfg.strict_centres) {
-    const int32_t rc = ensure_strict(ctx);
+    const int32_t rc = strict_prepare(ctx);
     if (rc) return rc;
-    se = StrictEmit{kStrictDirect, ctx->strict.cand, ctx->strict.counters + 4, ctx->strict.cand_cap};
-    CK(cudaMemsetAsync(ctx->strict.counters + 4, 0, sizeof(uint32_t), st));
+    se = StrictEmit{kStrictDirect, ctx->strict.cidx, ctx->strict.cw, ctx->strict.cand, ctx->strict.counters + 4,
+                    ctx->strict.cand_cap};
   }
   tree_emit_kernel<<<emit_grid, 128, 0, st>>>(
       ctx->keys[1], ctx->keys[1], ctx->tree_plan, kTreePasses, n, per_block, ctx->le, ctx->nodebase, b.pqr,
@@ -716,7 +737,8 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
   // deepest level first; a level's node count is only known on the device
   // one CTA per SM, all resident (128 threads each): the kernel's grid barrier needs every CTA running
   CK(cudaMemsetAsync(ctx->grid_barrier, 0, sizeof(unsigned int), st));
-  aggregate_levels_kernel<<<ctx->sm_count, 128, 0, st>>>(ctx->meta, b.pqr, b.accm, ctx->t, se.direct, ctx->grid_barrier);
+  aggregate_levels_kernel<<<ctx->sm_count, 128, 0, st>>>(ctx->meta, b.pqr, b.accm, ctx->t,
+                                                        StrictDirect{se.direct, se.cidx, se.cw}, ctx->grid_barrier);
   LAUNCHED(ctx);
   if (ctx->cfg.strict_centres) {
     const int32_t rc = strict_stage(ctx);
@@ -763,6 +785,7 @@ int32_t shard_phase(psim_ctx* ctx, int phase, int mode, float hw, float hh, uint
     case 0: {
       ctx->tree_valid = ctx->perm_valid = ctx->host_map_valid = ctx->grid_valid = false;
       S.tree_is_sharded = true;
+      S.tree_is_let = false;
       S.mode = mode;
       BodyArrays& in = ctx->b[ctx->cur];
       int nb = 1;
@@ -854,8 +877,14 @@ int32_t shard_phase(psim_ctx* ctx, int phase, int mode, float hw, float hh, uint
       for (int d = kShardDepth - 1; d >= 0; --d)
         heap_sweep_kernel<<<grid_for(ctx, 1u << (2 * d), 256, 1), 256, 0, st>>>(S.heap, d);
       heap_writeback_kernel<<<grid_for(ctx, kTopSlots, 256, 2), 256, 0, st>>>(S.meta, S.heap, ctx->t);
+      StrictDirect sd;
+      if (ctx->cfg.strict_centres) {
+        const int32_t rc = strict_prepare(ctx);
+        if (rc) return rc;
+        sd = StrictDirect{kStrictDirect, ctx->strict.cidx, ctx->strict.cw};
+      }
       finalize_nodes_shard_kernel<<<grid_for(ctx, (uint64_t)nl * 2 + 1, 256, 16), 256, 0, st>>>(
-          ctx->meta, S.meta, b.pqr, b.accm, S.lkeys, S.binprefix, ctx->t, ctx->cfg.strict_centres ? kStrictDirect : 0u);
+          ctx->meta, S.meta, b.pqr, b.accm, S.lkeys, S.binprefix, ctx->t, sd);
       if (ctx->cfg.strict_centres) {
         // node centres by the reference's serial f32 sums (strict.cuh) for this rank's piece, the cells above the
         // bins included: each belongs to the piece of the rank that owns its first body
@@ -1705,6 +1734,9 @@ int32_t psim_acc_points(psim_ctx* ctx, uint64_t m, const float* pts_xy, const fl
   if (!ctx) return PSIM_E_ARG;
   DeviceGuard guard(ctx->device);
   if (m == 0) return PSIM_OK;
+  if (ctx->sh.tree_is_sharded && ctx->sh.tree_is_let)
+    return fail(ctx, PSIM_E_STATE, "psim_acc_points: the last sharded build kept only the records this rank's own targets "
+                                   "can reach (locally essential tree); set PSIM_LET=0 to query arbitrary points");
   if (!pts_xy || !out_xy || m >= (1ull << 30)) return fail(ctx, PSIM_E_ARG, "psim_acc_points: null array or m too large");
   const size_t o_p = 0, o_q = o_p + align256(8 * m), o_r = o_q + align256(4 * m), o_o = o_r + align256(4 * m),
                total = o_o + align256(8 * m);
@@ -1784,6 +1816,8 @@ int32_t psim_hop_alignment(psim_ctx* ctx, uint64_t m_src, const uint32_t* src_id
   const uint64_t np = pair_offsets[m_src];
   if (np >= (1ull << 31) || (np && (!dst_idx || !out_alignment))) return fail(ctx, PSIM_E_ARG, "psim_hop_alignment: pair arrays");
   if (!ctx->tree_valid) return fail(ctx, PSIM_E_STATE, "psim_hop_alignment: no tree (call psim_build first)");
+  if (ctx->sh.tree_is_sharded && ctx->sh.tree_is_let)
+    return fail(ctx, PSIM_E_STATE, "psim_hop_alignment: locally essential tree (see psim_acc_points)");
   const uint32_t m = (uint32_t)m_src;
   const size_t o_src = 0, o_off = o_src + align256(4 * m_src), o_dst = o_off + align256(4 * (m_src + 1)),
                o_pts = o_dst + align256(4 * np), o_fld = o_pts + align256(8 * m_src), o_loc = o_fld + align256(8 * m_src),
@@ -2051,6 +2085,13 @@ static int32_t build_sharded(psim_ctx* ctx, int mode, float hw, float hh, const 
     K.vel_pending = false;
   }
   if ((rc = shard_phase(ctx, 2, mode, hw, hh, nullptr))) return rc;
+  const uint32_t world = S.world;
+  if (K.let) {  // who can reach what: the bins of every rank's targets (bodies are in sorted order from here on)
+    const uint32_t wb = shard_width(ctx->n, world), we = shard_width(ctx->m, world);
+    let_regions_kernel<<<1, kMaxRanks, 0, st>>>(S.binprefix, ctx->n, ctx->m, wb, we, ctx->m ? ctx->ebody[ctx->ecur] : nullptr,
+                                                 world, K.regions);
+    LAUNCHED(ctx);
+  }
   NCK(nccl_api().AllReduce(S.xbuf, S.xbuf, kBins + kMaxRanks, ncclUint64, ncclSum, K.comm, st));
   if ((rc = shard_phase(ctx, 3, mode, hw, hh, nullptr))) return rc;
   NCK(nccl_api().AllReduce(S.heap, S.heap, (size_t)kTopSlots * (sizeof(TopRec) / 8), ncclUint64, ncclSum, K.comm, st));
@@ -2060,10 +2101,57 @@ static int32_t build_sharded(psim_ctx* ctx, int mode, float hw, float hh, const 
   // traversal pieces on the side stream, the cell list on the main one
   CK(cudaEventRecord(K.ev_main, st));
   CK(cudaStreamWaitEvent(K.side, K.ev_main, 0));
-  if ((rc = all_gatherv(ctx, ctx->travA, sizeof(float4), ctx->node_cap, tl, K.side))) return rc;
-  if ((rc = all_gatherv(ctx, ctx->travB, sizeof(uint4), ctx->node_cap, tl, K.side))) return rc;
-  CK(cudaEventRecord(K.ev_side, K.side));
+  bool full = !K.let;
+  uint32_t h_cnt[kMaxRanks * kMaxRanks];
+  if (K.let) {
+    // each rank selects, per destination, the records that destination's walks can reach (let.cuh)
+    CK(cudaMemsetAsync(K.cnt, 0, kMaxRanks * sizeof(uint32_t), K.side));
+    const float margin_abs = 8.0f;  // largest body radius (4.7 A) + largest electron offset (2.2 A), rounded up
+    let_select_kernel<<<grid_for(ctx, S.meta_h.T_local + 1, 256, 8), 256, 0, K.side>>>(
+        S.meta, ctx->travA, ctx->travB, S.lkeys, K.regions, ctx->meta, ctx->cfg.theta, margin_abs, K.cap_per_rank, K.send,
+        K.cnt);
+    LAUNCHED(ctx);
+    NCK(nccl_api().AllGather(K.cnt, K.cnt_all, world, ncclUint32, K.comm, K.side));
+    CK(cudaMemcpyAsync(h_cnt, K.cnt_all, (size_t)world * world * sizeof(uint32_t), cudaMemcpyDeviceToHost, K.side));
+  }
   if (cell_size > 0.0f && p && (rc = cell_build_async(ctx, p->hw, p->hh, cell_size))) return rc;
+  if (K.let) {
+    CK(cudaStreamSynchronize(K.side));
+    K.let_sent = 0, K.let_full = 0;
+    for (uint32_t a = 0; a < world; ++a)
+      for (uint32_t b = 0; b < world; ++b)
+        if (a != b) {
+          if (h_cnt[a * world + b] > K.cap_per_rank) full = true;  // a send area overflowed somewhere: everyone falls back
+          if (a == S.rank) K.let_sent += h_cnt[a * world + b];
+        }
+    K.let_full = (uint64_t)(tl[S.rank + 1] - tl[S.rank]) * (world - 1);
+  }
+  S.tree_is_let = !full;
+  if (full) {
+    if ((rc = all_gatherv(ctx, ctx->travA, sizeof(float4), ctx->node_cap, tl, K.side))) return rc;
+    if ((rc = all_gatherv(ctx, ctx->travB, sizeof(uint4), ctx->node_cap, tl, K.side))) return rc;
+  } else {
+    if (K.let_poison) {
+      let_poison_kernel<<<grid_for(ctx, ctx->node_cap, 256, 8), 256, 0, K.side>>>(S.meta, ctx->travA, ctx->travB);
+      LAUNCHED(ctx);
+    }
+    NCK(nccl_api().GroupStart());
+    size_t roff = 0;
+    for (uint32_t peer = 0; peer < world; ++peer) {
+      if (peer == S.rank) continue;
+      const uint32_t ns = h_cnt[S.rank * world + peer], nr = h_cnt[peer * world + S.rank];
+      if (ns) NCK(nccl_api().Send(K.send + (size_t)peer * K.cap_per_rank, (size_t)ns * sizeof(LetRec), ncclChar, (int)peer, K.comm, K.side));
+      if (nr) NCK(nccl_api().Recv(K.recv + roff, (size_t)nr * sizeof(LetRec), ncclChar, (int)peer, K.comm, K.side));
+      roff += nr;
+    }
+    NCK(nccl_api().GroupEnd());
+    if (roff) {
+      let_scatter_kernel<<<grid_for(ctx, roff, 256, 8), 256, 0, K.side>>>(K.recv, (uint32_t)roff, ctx->node_cap, ctx->travA,
+                                                                         ctx->travB);
+      LAUNCHED(ctx);
+    }
+  }
+  CK(cudaEventRecord(K.ev_side, K.side));
   CK(cudaStreamWaitEvent(st, K.ev_side, 0));
   return shard_phase(ctx, 6, mode, hw, hh, nullptr);
 }
@@ -2436,6 +2524,24 @@ int32_t psim_comm_init(psim_ctx* ctx, const uint8_t* unique_id128, uint32_t rank
   CK(cudaEventCreateWithFlags(&K.ev_main, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&K.ev_side, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&K.ev_vel, cudaEventDisableTiming));
+  {
+    const char* e = getenv("PSIM_LET");
+    K.let = !(e && e[0] == '0') && nranks > 1;
+    e = getenv("PSIM_LET_POISON");
+    K.let_poison = e && e[0] == '1';
+    if (K.let) {
+      const uint64_t nb = ctx->cap_bodies ? ctx->cap_bodies : 1;
+      K.cap_per_rank = (uint32_t)std::max<uint64_t>(65536, nb / nranks / 2);
+      bool ok = dalloc(&K.regions, 1) == cudaSuccess && dalloc(&K.cnt, kMaxRanks) == cudaSuccess &&
+                dalloc(&K.cnt_all, (size_t)kMaxRanks * kMaxRanks) == cudaSuccess &&
+                dalloc(&K.send, (size_t)nranks * K.cap_per_rank) == cudaSuccess &&
+                dalloc(&K.recv, (size_t)nranks * K.cap_per_rank) == cudaSuccess;
+      if (!ok) {
+        cudaGetLastError();
+        return fail(ctx, PSIM_E_OOM, "psim_comm_init: locally-essential-tree buffers");
+      }
+    }
+  }
   K.on = true;
   return PSIM_OK;
 }
@@ -2451,7 +2557,19 @@ int32_t psim_comm_destroy(psim_ctx* ctx) {
   cudaStreamDestroy(K.side);
   cudaEventDestroy(K.ev_main), cudaEventDestroy(K.ev_side), cudaEventDestroy(K.ev_vel);
   if (K.stage) cudaFree(K.stage);
+  if (K.regions) cudaFree(K.regions);
+  if (K.cnt) cudaFree(K.cnt);
+  if (K.cnt_all) cudaFree(K.cnt_all);
+  if (K.send) cudaFree(K.send);
+  if (K.recv) cudaFree(K.recv);
   K = psim_ctx::Comm();
+  return PSIM_OK;
+}
+
+int32_t psim_comm_stats(psim_ctx* ctx, uint64_t* out4) {
+  if (!ctx || !out4) return PSIM_E_ARG;
+  out4[0] = ctx->comm.let_sent, out4[1] = ctx->comm.let_full;
+  out4[2] = ctx->comm.on && ctx->comm.let ? 1 : 0, out4[3] = ctx->sh.tree_is_let ? 1 : 0;
   return PSIM_OK;
 }
 

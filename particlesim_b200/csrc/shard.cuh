@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(256)
     finalize_nodes_shard_kernel(const TreeMeta* __restrict__ meta, const ShardMeta* __restrict__ sm,
                                 const float4* __restrict__ pqr, const float4* __restrict__ accm,
                                 const uint64_t* __restrict__ lkeys, const uint32_t* __restrict__ binprefix,
-                                TreeArrays t, uint32_t strict_direct) {
+                                TreeArrays t, StrictDirect strict_direct) {
   const uint32_t ml = sm->M_local, noff = sm->node_off;
   if (ml > t.node_cap) return;
   t.nodeA -= noff, t.nodeB -= noff, t.rec -= noff, t.ndepth -= noff;
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(256)
   // the subtree end of a node is read from its successor's record: a node's own B.z may be written concurrently,
   // B.y (what SubtreeEndShard reads) never is
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < ml; k += stride)
-    finalize_node(noff + k, root_size, pqr, accm, t, end, strict_direct, strict_direct != 0);
+    finalize_node(noff + k, root_size, pqr, accm, t, end, strict_direct, strict_direct.limit != 0);
 }
 
 // psim_config.strict_centres in the sharded build: the chains (nodes that start at the same body) of this rank's

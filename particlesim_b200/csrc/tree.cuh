@@ -153,6 +153,8 @@ __global__ void level_scan_kernel(TreeMeta* __restrict__ meta, uint32_t node_cap
 // and then hands slots out of shared-memory counters while it emits.
 struct StrictEmit {        // psim_config.strict_centres (strict.cuh); direct == 0: off
   uint32_t direct;         // nodes of at most this many bodies are summed by finalize_node
+  const uint32_t* cidx;    // see StrictDirect
+  const float4* cw;
   uint4* cand;             // chains with larger nodes: {head body, shallowest node, big nodes - 1, bodies of the largest}
   uint32_t* cand_count;
   uint32_t cand_cap;
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(128)
     for (uint32_t k = begin + threadIdx.x; k < end; k += blockDim.x) {
       const uint32_t node = t.local_nodes[k];
       aggregate_node_ranged(node, level, t);
-      finalize_node(node, root_size, pqr, accm, t, SubtreeEndCount{}, strict.direct);
+      finalize_node(node, root_size, pqr, accm, t, SubtreeEndCount{}, StrictDirect{strict.direct, strict.cidx, strict.cw});
     }
   }
 }
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(128)
 // boundaries; their centres are finished in the same visit
 __global__ void __launch_bounds__(128)
     aggregate_level_kernel(int level, const TreeMeta* __restrict__ meta, const float4* __restrict__ pqr,
-                           const float4* __restrict__ accm, TreeArrays t, uint32_t strict_direct) {
+                           const float4* __restrict__ accm, TreeArrays t, StrictDirect strict_direct) {
   const uint32_t M = meta->num_nodes;
   if (M > t.node_cap) return;
   const uint32_t begin = meta->level_start[level], end = meta->level_start[level + 1];
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(128)
 // `barrier` is a zeroed counter; empty levels are skipped by every CTA alike.
 __global__ void __launch_bounds__(128)
     aggregate_levels_kernel(const TreeMeta* __restrict__ meta, const float4* __restrict__ pqr,
-                            const float4* __restrict__ accm, TreeArrays t, uint32_t strict_direct,
+                            const float4* __restrict__ accm, TreeArrays t, StrictDirect strict_direct,
                             unsigned int* __restrict__ barrier) {
   const uint32_t M = meta->num_nodes;
   if (M > t.node_cap) return;

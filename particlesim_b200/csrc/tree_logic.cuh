@@ -324,13 +324,21 @@ PSIM_HD void strict_centre_direct(uint32_t b0, uint32_t b1, const float4* pqr, c
   }
 }
 
-// strict_direct > 0 (psim_config.strict_centres, single-GPU build): nodes of at most that many bodies get
-// the reference's serial sums right here, where their bodies are still in cache; larger ones are left to
-// strict.cuh.
+// psim_config.strict_centres: nodes of at most `limit` bodies get the reference's serial sums right where the tree
+// is finished; larger ones are left to strict.cuh.  A body with q == 0 adds exactly +-0 to the |q|-weighted sums, so
+// the loop runs over the node's CHARGED bodies only (cidx = exclusive count of charged bodies, cw = their
+// {|q|, x|q|, y|q|} in sorted order, both made before the emit kernel).  A node without any charged body never enters
+// a field sum: its (mass-weighted / centroid) centre is left to the export (strict_chargeless_kernel).
+struct StrictDirect {
+  uint32_t limit = 0;  // 0: off
+  const uint32_t* cidx = nullptr;
+  const float4* cw = nullptr;
+};
+
 // set_count (sharded build, whose emit does not know the ranges of internal cells): the body count goes into B.z.
 template <class SubtreeEnd>
 PSIM_HD void finalize_node(uint32_t node, float root_size, const float4* pqr, const float4* accm,
-                           const TreeArrays& t, const SubtreeEnd& subtree_end, uint32_t strict_direct = 0,
+                           const TreeArrays& t, const SubtreeEnd& subtree_end, StrictDirect sd = StrictDirect(),
                            bool set_count = false) {
   uint4 nb = t.nodeB[node];
   if (nb.w & kNodeLeaf) return;
@@ -341,8 +349,15 @@ PSIM_HD void finalize_node(uint32_t node, float root_size, const float4* pqr, co
   if (set_count) nb.z = subtree_end(c, nb) - nb.y;
   t.nodeB[node] = nb;
   float px = 0.0f, py = 0.0f;
-  if (strict_direct && nb.z <= strict_direct) {
-    strict_centre_direct(nb.y, nb.y + nb.z, pqr, accm, px, py);
+  if (sd.limit && nb.z <= sd.limit) {
+    const uint32_t c0 = sd.cidx[nb.y], c1 = sd.cidx[nb.y + nb.z];
+    float total_abs = 0.0f, wx = 0.0f, wy = 0.0f;
+    for (uint32_t k = c0; k < c1; ++k) {
+      const float4 w = sd.cw[k];
+      total_abs = f_add(total_abs, w.x), wx = f_add(wx, w.y), wy = f_add(wy, w.z);
+    }
+    if (total_abs > 1e-6f) px = f_div(wx, total_abs), py = f_div(wy, total_abs);
+    else if (c1 > c0) strict_centre_direct(nb.y, nb.y + nb.z, pqr, accm, px, py);  // charges too small to weigh
   } else if (r.aq > (double)1e-6f) {
     px = (float)(r.aqx / r.aq), py = (float)(r.aqy / r.aq);
   } else if (r.aq > 0.0) {

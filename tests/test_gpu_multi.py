@@ -1,5 +1,6 @@
 """GPU, more than one device: the sharded hot path over REAL NCCL (psim_comm_init + psim_step_sharded, one process per
-GPU under torch.distributed.run) must leave the single-GPU state, bit for bit.  Skipped on a one-GPU box (NCCL refuses
+GPU under torch.distributed.run; strict node centres, polar pass, locally-essential-tree exchange) must leave the
+single-GPU state, bit for bit.  Skipped on a one-GPU box (NCCL refuses
 two ranks on one device); the one-GPU protocol tests are tests/test_gpu_shard.py."""
 import os
 import subprocess
@@ -26,6 +27,9 @@ def test_sharded_steps_over_nccl_equal_single_gpu(cuda_device, how):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.join(ROOT, "tools", "check_sharded.py"),
            "200001", how]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    # PSIM_LET_POISON: the records the locally-essential-tree exchange does not deliver are overwritten with NaN centres
+    # and dangling pointers, so a walk that reached one could not give the single-GPU bits
+    env = dict(os.environ, PSIM_LET_POISON="1")
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     print(res.stdout[-3000:], res.stderr[-2000:])
     assert res.returncode == 0 and "== SINGLE: True" in res.stdout

@@ -50,6 +50,11 @@ for _ in range(3):
     sh.step_device()
 torch.cuda.synchronize()
 a = state(sh)
+if how == "library":
+    cs = np.zeros(4, np.uint64)
+    sh._call("psim_comm_stats", cs.ctypes.data)
+    print(f"rank {rank}: LET exchange sent {int(cs[0])} of {int(cs[1])} records ({100.0 * cs[0] / max(int(cs[1]), 1):.1f} %), "
+          f"enabled {int(cs[2])}, tree is LET {int(cs[3])}", flush=True)
 ok = True
 if rank == 0:
     one = mk(Simulation)
