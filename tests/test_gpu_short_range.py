@@ -322,3 +322,44 @@ def test_hosted_step_equals_update_step_download(cuda_device, do_electrons):
         b._call("psim_download_bodies", *([None] * 11), d_orig.ctypes.data)
         assert np.array_equal(d_orig, o_orig)
     a.close(), b.close()
+
+
+def test_hand_derived_cases_on_the_device(cuda_device):
+    """the hand-derived polar (ion next to a dipole, two facing dipoles) and first-five-metals cases of
+    tests/test_oracle.py, straight through the C ABI: the device against the numbers derived by hand"""
+    from particlesim_b200 import Bodies, Simulation
+    k = float(KE)
+
+    def polar(pos, charge, radius, mass, species, ebody, erel):
+        b = Bodies(np.array(pos, np.float32), mass=mass, radius=radius, charge=charge, species=np.array(species, np.uint8),
+                   ebody=np.array(ebody, np.uint32), erel=np.array(erel, np.float32))
+        sim = Simulation(b, 50.0, 50.0)
+        sim.config.coulomb_constant = k
+        sim.reset_acc()
+        sim._call("psim_cell_build", 50.0, 50.0, 7.5)
+        sim._call("psim_apply_polar_forces", k, 1)
+        sim.download(("acc",))
+        acc = sim.bodies.acc.copy()
+        sim.close()
+        return acc
+
+    acc = polar([[0, 0], [4, 0]], [0, 1], [2.5, 0.76], [88.06, 6.94], [4, 0], [0], [[0.5, 0.0]])
+    force = (-4.0 * k / (20.0 * 4.0) - (-3.5 * k / (16.25 * 3.5))) * 0.8
+    assert np.allclose(acc[0], [force / 88.06, 0.0], rtol=2e-6, atol=1e-12)
+    assert np.allclose(acc[1], [-force / 6.94, 0.0], rtol=2e-6, atol=1e-12)
+    acc = polar([[0, 0], [4, 0]], [0, 0], [2.5, 2.5], [88.06, 88.06], [4, 4], [0, 1], [[0.5, 0.0], [-0.5, 0.0]])
+    q = 0.8
+    nn, ne = -4.0 * q * k / (29.0 * 5.0), -3.5 * q * k / (16.25 * 3.5)
+    en, ee = ne, -3.0 * q * k / (13.0 * 3.0)
+    total_a = 2.0 * ((nn - ne) - (en - ee)) * q / 88.06
+    assert np.allclose(acc[0], [total_a, 0.0], rtol=5e-6, atol=1e-12)
+    assert np.allclose(acc[1], [-total_a, 0.0], rtol=5e-6, atol=1e-12)
+    # first five metal neighbours (out_of_plane.rs:196-200)
+    pos = np.array([[3, 3], [0, 0], [1, 0], [2, 0], [0, 1], [1, 1], [2, 1], [0, 2]], np.float32)
+    b = Bodies(pos, z=[3.0, 0, 0.5, -0.5, 1.0, 0.2, -3, -3], vz=[0.7] + [0] * 7, mass=[88.06] + [6.94] * 7,
+               radius=[2.5] + [1.52] * 7, charge=np.zeros(8), species=np.array([4] + [1] * 7, np.uint8))
+    sim = Simulation(b, 50.0, 50.0)
+    sim.enforce_metal_z_boundaries(5.0)
+    assert sim.bodies.z[0] == np.float32(np.float32(np.float32(-0.5) + np.float32(1.52)) + np.float32(0.01))
+    assert sim.bodies.vz[0] == 0.0
+    sim.close()
