@@ -247,15 +247,59 @@ class Simulation {
     check(psim_update_electrons(ctx_, background_e_field.x, background_e_field.y, dt, config.coulomb_constant));
     download_electrons();
   }
-  // the hot path of Simulation::step (simulation.rs:1000-1196) without host round trips
-  void step_hot_path() {
+  // collision::collide, COLLISION_PASSES passes (simulation.rs:1025-1028, simulation/collision.rs:62-372); returns the
+  // touching pairs of the last pass
+  uint64_t collide(uint32_t num_passes = 7, float li_collision_softness = 0.8f, bool soft_collision_lithium_ion = true,
+                   bool soft_collision_anion = false) {
     ensure_uploaded();
+    uint64_t touching = 0;
+    check(psim_collide(ctx_, domain_width, domain_height, domain_depth, num_passes, num_passes, li_collision_softness,
+                       soft_collision_lithium_ion, soft_collision_anion, &touching));
+    download_fields(true, false, false);
+    return touching;
+  }
+  // the field part of the hopping predicate for a batch of (donor, acceptor) candidates
+  // (simulation/electron_hopping.rs:283-329): alignment per candidate, local_field per donor
+  std::vector<float> hop_alignment(const std::vector<uint32_t>& src, const std::vector<std::vector<uint32_t>>& candidates,
+                                   float alignment_bias, std::vector<Vec2>* local_field = nullptr) {
+    ensure_uploaded();
+    std::vector<uint32_t> off(src.size() + 1, 0), dst;
+    for (size_t i = 0; i < src.size(); ++i) {
+      off[i + 1] = off[i] + (uint32_t)candidates[i].size();
+      dst.insert(dst.end(), candidates[i].begin(), candidates[i].end());
+    }
+    std::vector<float> lf(2 * src.size() + 2), al(dst.size() + 1);
+    check(psim_hop_alignment(ctx_, src.size(), src.data(), off.data(), dst.data(), config.coulomb_constant,
+                             background_e_field.x, background_e_field.y, alignment_bias, lf.data(), al.data()));
+    if (local_field) {
+      local_field->resize(src.size());
+      for (size_t i = 0; i < src.size(); ++i) (*local_field)[i] = Vec2{lf[2 * i], lf[2 * i + 1]};
+    }
+    al.resize(dst.size());
+    return al;
+  }
+  psim_step_params step_params() const {
     psim_step_params p{};
     p.hw = domain_width, p.hh = domain_height, p.hd = domain_depth, p.dt = dt, p.damping_base = config.damping_base;
     p.k_e = config.coulomb_constant, p.bg_x = background_e_field.x, p.bg_y = background_e_field.y;
     p.density_threshold = config.cell_list_density_threshold;
     p.enable_out_of_plane = config.enable_out_of_plane, p.do_short_range = 1, p.do_electrons = 1, p.do_iterate = 1;
+    p.do_polar = 1;  // forces::apply_polar_forces runs every step (simulation.rs:1007)
+    return p;
+  }
+  // the hot path of Simulation::step (simulation.rs:1000-1196) without host round trips
+  void step_hot_path() {
+    ensure_uploaded();
+    const psim_step_params p = step_params();
     check(psim_step(ctx_, &p));
+  }
+  // multi-GPU (one Simulation per rank, created with psim_shard_capacity(n, nranks) bodies): NCCL communicator from a
+  // 128-byte id made by psim_comm_unique_id on rank 0, then the same step across the ranks
+  void comm_init(const uint8_t id[128], uint32_t rank, uint32_t nranks) { check(psim_comm_init(ctx_, id, rank, nranks)); }
+  void step_hot_path_sharded() {
+    ensure_uploaded();
+    const psim_step_params p = step_params();
+    check(psim_step_sharded(ctx_, &p));
   }
 
  private:

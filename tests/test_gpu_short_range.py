@@ -363,3 +363,22 @@ def test_hand_derived_cases_on_the_device(cuda_device):
     assert sim.bodies.z[0] == np.float32(np.float32(np.float32(-0.5) + np.float32(1.52)) + np.float32(0.01))
     assert sim.bodies.vz[0] == 0.0
     sim.close()
+
+
+def test_hosted_step_after_a_reupload_uses_upload_order(cuda_device):
+    """psim_step_host keeps a row map after a step with electrons (the device order then differs from the order of its
+    outputs).  psim_upload_bodies starts over: the next hosted call takes its inputs in upload order, like a fresh
+    context (a stale map would scatter positions, charges and velocities onto the wrong rows without any error)."""
+    bodies = electrolyte(30_000)
+    n = len(bodies["pos"])
+    rng = np.random.default_rng(9)
+    vel = rng.normal(0, 0.02, (n, 2)).astype(np.float32)
+    a, b = make_sim(bodies), make_sim(bodies)
+    p = a.step_params(do_electrons=True)
+    a.step_host(bodies["pos"].copy(), vel.copy(), bodies["charge"].copy(), params=p)  # leaves a row map behind
+    a.upload()                                                                          # same bodies, upload order again
+    out_a = a.step_host(bodies["pos"].copy(), vel.copy(), bodies["charge"].copy(), params=p)
+    out_b = b.step_host(bodies["pos"].copy(), vel.copy(), bodies["charge"].copy(), params=b.step_params(do_electrons=True))
+    for k in ("orig", "pos", "vel", "e_field"):
+        assert np.array_equal(out_a[k], out_b[k]), k
+    a.close(), b.close()
