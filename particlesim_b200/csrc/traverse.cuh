@@ -410,10 +410,22 @@ __device__ __forceinline__ float2 bh_group_walk(const float4* __restrict__ nodeA
     for (int it = 0; it < scnt; ++it) {
       const float4 nd = ws.s_node[it];
       const uint32_t m = ws.s_mask[it];
-      if ((m >> lane) & 1u) {
-        const float dx = A::sub(px, nd.x), dy = A::sub(py, nd.y);
-        const float d_sq = A::add(A::mul(dx, dx), A::mul(dy, dy));
-        monopole(nd, dx, dy, d_sq, 0.0f, false);
+      if (PARITY) {
+        if ((m >> lane) & 1u) {
+          const float dx = A::sub(px, nd.x), dy = A::sub(py, nd.y);
+          const float d_sq = A::add(A::mul(dx, dx), A::mul(dy, dy));
+          monopole(nd, dx, dy, d_sq, 0.0f, false);
+        }
+      } else {
+        // fast mode: no branch per entry - a lane the node does not reach weighs its term with zero (a sure node is
+        // accepted by every target that reaches it, so d_sq > 0 there; elsewhere the select drops whatever came out)
+        const float dx = px - nd.x, dy = py - nd.y;
+        const float d_sq = fmaf(dx, dx, dy * dy);
+        const float r_eff = fmaxf(d_sq * rsqrt_ftz(d_sq), fmaf(nd.w, 0.5f, radius));
+        const float denom = fmaf(r_eff, r_eff, P.e_sq) * r_eff;
+        const float sc = ((m >> lane) & 1u) ? (kq * nd.z) * rcp_ftz(denom) : 0.0f;
+        ax = fmaf(dx, sc, ax);
+        ay = fmaf(dy, sc, ay);
       }
     }
     for (int it = 0; it < cnt; ++it) {
@@ -438,7 +450,16 @@ __device__ __forceinline__ float2 bh_group_walk(const float4* __restrict__ nodeA
       }
       const uint32_t am = __ballot_sync(FULL, acc);
       if (lane == 0) ws.l_acc[it] = am;
-      if (acc && nd.z != 0.0f) monopole(nd, dx, dy, d_sq, dist, have_dist);
+      if (PARITY) {
+        if (acc && nd.z != 0.0f) monopole(nd, dx, dy, d_sq, dist, have_dist);
+      } else {
+        // fast mode: branch-free like the sure list (a chargeless node weighs zero by itself)
+        const float r_eff = fmaxf(d_sq * rsqrt_ftz(d_sq), fmaf(nd.w, 0.5f, radius));
+        const float denom = fmaf(r_eff, r_eff, P.e_sq) * r_eff;
+        const float sc = acc ? (kq * nd.z) * rcp_ftz(denom) : 0.0f;
+        ax = fmaf(dx, sc, ax);
+        ay = fmaf(dy, sc, ay);
+      }
     }
     __syncwarp();
     if (in_list) acc_mask = ws.l_acc[my_slot];
