@@ -232,7 +232,9 @@ def workload_config(args, n):
             "l2": "device working set (bodies 2 x 61 B + 4 n node slots x ~185 B) >> 126 MB L2, no flush needed",
             "parallelism": f"morton-sharded x{args.gpus}",
             "multi_gpu_build": "n/a" if args.gpus == 1 else ("replicated" if args.replicated_build else
-                                                            "sharded by key range (65536 top-level cells), tree pieces all-gathered")}
+                                                            "psim_step_sharded: builds sharded by key range (65536 top-level "
+                                                            "cells), locally-essential-tree exchange of the traversal records, "
+                                                            "body state replicated")}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -295,8 +297,9 @@ def run_ours(args):
                species=bd["species"], ebody=bd.get("ebody"), erel=bd.get("erel"))
     if world > 1:
         from particlesim_b200.parallel import ShardedSimulation
-        sim = ShardedSimulation(b, hw, hh, theta=args.theta, parity_mode=int(args.ieee), device=local_rank,
-                                stream=stream, rank=rank, world=world, local_build=not args.replicated_build)
+        sim = ShardedSimulation(b, hw, hh, domain_depth=float(bd.get("hd", 1.0)), theta=args.theta,
+                                parity_mode=int(args.ieee), device=local_rank, stream=stream, rank=rank, world=world,
+                                local_build=not args.replicated_build, strict_centres=bool(args.strict))
     else:
         sim = Simulation(b, hw, hh, domain_depth=float(bd.get("hd", 1.0)), theta=args.theta, parity_mode=int(args.ieee),
                          device=local_rank, stream=stream, strict_centres=bool(args.strict))
@@ -557,7 +560,12 @@ def run_ours(args):
             h_vel.copy_(o_vel)
         t = torch.tensor([float(np.mean(ts))], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cs = np.zeros(4, np.uint64)
+        if getattr(sim, "library", False):
+            sim._call("psim_comm_stats", cs.ctypes.data)
         if rank == 0:
+            line["let"] = {"enabled": bool(cs[2]), "records_sent_by_rank0": int(cs[0]), "full_allgather_would_send": int(cs[1]),
+                           "fraction": float(cs[0]) / max(float(cs[1]), 1.0)}
             t_e2e = float(t.item())
             line["e2e"] = {"value": n / t_e2e / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(n * 20),
                            "d2h_bytes_per_step": int(n * 24), "ms_per_step": t_e2e * 1e3,

@@ -600,8 +600,8 @@ int32_t ensure_strict(psim_ctx* ctx) {
   if (ctx->strict_ready) return PSIM_OK;
   StrictArrays& S = ctx->strict;
   const size_t nb = ctx->cap_bodies ? ctx->cap_bodies : 1;
-  S.long_cap = (uint32_t)(nb / 64 + 1024);
-  S.item_cap = (uint32_t)(nb / 16 + nb / 64 + 1024);
+  S.long_cap = (uint32_t)(nb / 32 + 1024);
+  S.item_cap = (uint32_t)(nb / 16 + nb / 32 + 1024);
   S.blk_cap = (uint32_t)(nb / kStrictBlock + 2);
   bool ok = true;
   auto A = [&](auto** p, size_t cnt) {

@@ -33,8 +33,8 @@
 namespace psim {
 
 constexpr uint32_t kStrictDirect = 64;    // nodes up to this many bodies are summed in the emit kernel (tree_logic.cuh)
-constexpr uint32_t kStrictT1 = 2048;      // addends a single thread may walk
-constexpr int kStrictClasses = 13;        // length classes 1..12 (class c: 2^(c-1) <= len < 2^c, capped)
+constexpr uint32_t kStrictT1 = 1024;      // addends a single thread may walk
+constexpr int kStrictClasses = 12;        // length classes 1..11 (class c: 2^(c-1) <= len < 2^c, capped)
 constexpr uint32_t kSlowSentinel = 0x7fc0deadu;
 constexpr uint32_t kChainLenCap = (1u << 27) - 1;  // chain lengths saturate here in the packed record
 
