@@ -2532,6 +2532,8 @@ int32_t psim_comm_init(psim_ctx* ctx, const uint8_t* unique_id128, uint32_t rank
     if (K.let) {
       const uint64_t nb = ctx->cap_bodies ? ctx->cap_bodies : 1;
       K.cap_per_rank = (uint32_t)std::max<uint64_t>(65536, nb / nranks / 2);
+      e = getenv("PSIM_LET_CAP");  // test aid: a small send area forces the fall-back to the full all-gather
+      if (e && atoi(e) > 0) K.cap_per_rank = (uint32_t)atoi(e);
       bool ok = dalloc(&K.regions, 1) == cudaSuccess && dalloc(&K.cnt, kMaxRanks) == cudaSuccess &&
                 dalloc(&K.cnt_all, (size_t)kMaxRanks * kMaxRanks) == cudaSuccess &&
                 dalloc(&K.send, (size_t)nranks * K.cap_per_rank) == cudaSuccess &&

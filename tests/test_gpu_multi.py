@@ -18,18 +18,28 @@ def _gpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("how", ["library", "python"])
-def test_sharded_steps_over_nccl_equal_single_gpu(cuda_device, how):
+CASES = [
+    # orchestration, bodies, generator, theta, extra environment
+    ("library", 200001, "electrolyte", 1.0, {"PSIM_LET_POISON": "1"}),
+    ("python", 200001, "electrolyte", 1.0, {}),
+    ("library", 300000, "clustered", 0.5, {"PSIM_LET_POISON": "1"}),      # deep unbalanced tree, wide opening
+    ("library", 150001, "uniform_pm1", 0.7, {"PSIM_LET_POISON": "1"}),    # every body charged
+    ("library", 200001, "electrolyte", 1.0, {"PSIM_LET_CAP": "100"}),     # send areas overflow: full all-gather fall-back
+]
+
+
+@pytest.mark.parametrize("how,n,gen,theta,extra", CASES)
+def test_sharded_steps_over_nccl_equal_single_gpu(cuda_device, how, n, gen, theta, extra):
     g = _gpus()
     if g < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 8 if g >= 8 else (4 if g >= 4 else 2)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.join(ROOT, "tools", "check_sharded.py"),
-           "200001", how]
+           str(n), how, gen, str(theta)]
     # PSIM_LET_POISON: the records the locally-essential-tree exchange does not deliver are overwritten with NaN centres
     # and dangling pointers, so a walk that reached one could not give the single-GPU bits
-    env = dict(os.environ, PSIM_LET_POISON="1")
+    env = dict(os.environ, **extra)
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     print(res.stdout[-3000:], res.stderr[-2000:])
     assert res.returncode == 0 and "== SINGLE: True" in res.stdout

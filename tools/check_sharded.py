@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node G tools/check_sharded.py [n] [library|python|repl]: three sharded hot-path steps (both
+"""torchrun --nproc-per-node G tools/check_sharded.py [n] [library|python|repl] [electrolyte|clustered|uniform_pm1] [theta]: three sharded hot-path steps (both
 builds, field, polar, LJ, integrator, electrons) over real NCCL must leave exactly the single-GPU state (default
 configuration: the reference's serial-sum node centres on both sides).  Exits non-zero on a mismatch; tests/test_gpu_multi.py runs it."""
 import os
@@ -11,7 +11,8 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from helpers import KE, electrolyte  # noqa: E402
+import helpers  # noqa: E402
+from helpers import KE  # noqa: E402
 from particlesim_b200 import Bodies, Simulation  # noqa: E402
 from particlesim_b200.parallel import ShardedSimulation  # noqa: E402
 
@@ -19,15 +20,17 @@ rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 200_001
-bd = electrolyte(n)
-if os.environ.get("NO_LJ") != "1":
+gen = sys.argv[3] if len(sys.argv) > 3 else "electrolyte"
+theta = float(sys.argv[4]) if len(sys.argv) > 4 else 1.0
+bd = getattr(helpers, gen)(n)
+if os.environ.get("NO_LJ") != "1" and gen == "electrolyte":
     bd["species"][: n // 10] = 1  # some LJ bodies
 
 
 def mk(cls, **kw):
-    b = Bodies(bd["pos"], vel=bd["vel"], mass=bd["mass"], radius=bd["radius"], charge=bd["charge"],
-               species=bd["species"], ebody=bd["ebody"], erel=bd["erel"])
-    s = cls(b, bd["hw"], bd["hh"], device=lr, stream=torch.cuda.current_stream().cuda_stream, **kw)
+    b = Bodies(bd["pos"], vel=bd.get("vel"), mass=bd["mass"], radius=bd["radius"], charge=bd["charge"],
+               species=bd["species"], ebody=bd.get("ebody"), erel=bd.get("erel"))
+    s = cls(b, bd["hw"], bd["hh"], device=lr, stream=torch.cuda.current_stream().cuda_stream, theta=theta, **kw)
     s.config.coulomb_constant = float(KE)
     return s
 
@@ -72,7 +75,7 @@ if rank == 0:
             rows = np.unique(np.argwhere(d > 0)[:, 0])
             extra = f"  differing rows {len(rows)} of {len(x)} (first {rows[:4].tolist()}, last {rows[-1]}), max |diff| {d.max():.3e}"
         print(f"{nm}: identical={same}{extra}")
-    print(f"SHARDED ({how}, {world} ranks, n = {n}) == SINGLE:", ok, flush=True)
+    print(f"SHARDED ({how}, {world} ranks, n = {n}, {gen}, theta {theta}) == SINGLE:", ok, flush=True)
 flag = torch.tensor([1 if (rank != 0 or ok) else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.barrier()
