@@ -35,7 +35,8 @@ T = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "nsecond": 1e-6, "usecond": 1e-3, "mseco
 table = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_table.py"), os.path.join(src, f"{tag}_metrics.csv")],
                        capture_output=True, text=True, check=True).stdout
 with open(os.path.join(out_dir, f"{tag}_kernel_table_16M.txt"), "w") as f:
-    f.write("# per-kernel ncu counters of ONE hot-path step (psim_step), 16 M-body electrolyte, theta 1.0, parity_mode 0\n"
+    f.write("# per-kernel ncu counters of ONE hot-path step (psim_step: polar pass and strict node centres included from\n"
+            "# round 2 on), 16 M-body electrolyte, theta 1.0, parity_mode 0\n"
             "# (tools/refresh_profiles.py has the command line; table by tools/ncu_table.py)\n" + table)
 
 # launch list
@@ -50,7 +51,8 @@ for r in rows:
 tot, n = sum(v[0] for v in agg.values()), sum(v[1] for v in agg.values())
 bench = {}
 try:
-    bench = json.load(open(os.path.join(src, "bench_n1.json")))
+    bench_file = os.path.join(src, f"{tag}_bench_n1.json")
+    bench = json.load(open(bench_file if os.path.exists(bench_file) else os.path.join(src, "bench_n1.json")))
 except Exception:
     pass
 lines = ["# ncu launch list of ONE hot-path step (psim_step), 16 M-body electrolyte, theta = 1.0, parity_mode 0",
