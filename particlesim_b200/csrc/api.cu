@@ -467,6 +467,9 @@ FieldParams field_params(const psim_ctx* ctx, float k_e, float bg_x, float bg_y)
   P.bg_x = bg_x;
   P.bg_y = bg_y;
   P.inv_theta = 1.0f / ctx->cfg.theta;
+  const char* off = getenv("PSIM_ONE_MUFU");
+  P.one_mufu = ctx->cfg.parity_mode == 0 && ctx->cfg.theta <= 1.0f && ctx->cfg.theta > 0.0f && ctx->cfg.epsilon >= 1e-2f &&
+               ctx->cfg.epsilon <= 1e3f && !(off && off[0] == '0');
   return P;
 }
 

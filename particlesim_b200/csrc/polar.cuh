@@ -11,6 +11,7 @@
 #include <stdint.h>
 
 #include "cells.cuh"
+#include "traverse.cuh"
 
 namespace psim {
 
@@ -218,7 +219,65 @@ __global__ void __launch_bounds__(kPolarThreads)
   float ax = 0.0f, ay = 0.0f;
   int filled = 0;
 
+  // fast arithmetic: per-thread source weights of `me` (k_e q with the reference's |q| < EPSILON guard folded in; the
+  // dipole terms only exist in the ConjugatePair model)
+  const float kEps = 1.1920929e-07f;
+  const float me_kq = fabsf(me.z) < kEps ? 0.0f : P.k_e * me.z;
+  const float me_ke = (me_dip && P.dipole_model == 1 && !(fabsf(me_qeff) < kEps)) ? P.k_e * me_qeff : 0.0f;
+  const float mex = __fadd_rn(me.x, mrel.x), mey = __fadd_rn(me.y, mrel.y);
+
   auto drain = [&]() {
+    if constexpr (!IEEE) {
+      // One branch-free body for every kind of pair (dipole / dipole, dipole / ion, inside one cutoff or both): the
+      // four site-to-site geometries are always taken, a partner without a dipole has its electron site on its nucleus
+      // and weight zero there, and the two directions are added under a select.  The lanes of a warp stay together
+      // whatever mix of species their lists hold.
+      for (int t = 0; t < filled; ++t) {
+        const uint32_t k = s_list[t][threadIdx.x];
+        const float4 b4 = __ldg(&recB[k]);
+        const float4 a4 = __ldg(&recA[k]);
+        const uint32_t jbits = __float_as_uint(b4.x);
+        const bool j_dip = (jbits & kPolarHasDipole) != 0;
+        uint32_t jsp = jbits & 0xffu;
+        if (jsp >= kMaxSpecies) jsp = 0;
+        const float j_qeff = s_polar_charge[jsp];
+        const float rx = __fsub_rn(a4.x, me.x), ry = __fsub_rn(a4.y, me.y);
+        const float r2 = __fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry));
+        const float jc = __fmul_rn(3.0f, a4.w);
+        const bool use0 = me_dip && r2 < my_cut_sq;              // me as the polar body i
+        const bool use1 = j_dip && r2 < __fmul_rn(jc, jc);       // the candidate as i, me its neighbour: reaction
+        const float j_kq = fabsf(a4.z) < kEps ? 0.0f : P.k_e * a4.z;
+        const float j_ke = (j_dip && P.dipole_model == 1 && !(fabsf(j_qeff) < kEps)) ? P.k_e * j_qeff : 0.0f;
+        const float jex = __fadd_rn(a4.x, b4.z), jey = __fadd_rn(a4.y, b4.w);
+        // geometry of (point of me) <- (source of j): d = point - source, w = 1 / ((r_eff^2 + eps^2) r_eff)
+        auto geom = [&](float px, float py, float sx, float sy, float min_sep, float& dx, float& dy) {
+          dx = px - sx, dy = py - sy;
+          const float d2 = fmaf(dx, dx, dy * dy);
+          const float r_eff = fmaxf(d2 * rsqrt_ftz(d2), min_sep);  // fmaxf drops the NaN of d2 == 0
+          const float den = fmaf(r_eff, r_eff, P.epsilon_sq) * r_eff;
+          return den >= 1.17549435e-38f ? rcp_ftz(den) : 0.0f;     // coincident zero-radius sites: no field
+        };
+        float nnx, nny, enx, eny, nex, ney, eex, eey;
+        const float wNN = geom(me.x, me.y, a4.x, a4.y, me.w + a4.w, nnx, nny);  // my nucleus  <- its nucleus
+        const float wEN = geom(mex, mey, a4.x, a4.y, a4.w, enx, eny);           // my electron <- its nucleus
+        const float wNE = geom(me.x, me.y, jex, jey, me.w, nex, ney);           // my nucleus  <- its electron
+        const float wEE = geom(mex, mey, jex, jey, 0.0f, eex, eey);             // my electron <- its electron
+        // me as i (forces.rs:99-158): (field at my nucleus - field at my electron) * my q_eff
+        const float cNN0 = (j_kq + j_ke) * wNN, cEN0 = (j_kq + j_ke) * wEN, cNE0 = j_ke * wNE, cEE0 = j_ke * wEE;
+        const float f0x = (fmaf(cNN0, nnx, -cNE0 * nex) - fmaf(cEN0, enx, -cEE0 * eex)) * me_qeff;
+        const float f0y = (fmaf(cNN0, nny, -cNE0 * ney) - fmaf(cEN0, eny, -cEE0 * eey)) * me_qeff;
+        // the candidate as i: the same site pairs seen from the other end (d changes sign)
+        const float cNN1 = (me_kq + me_ke) * wNN, cNE1 = (me_kq + me_ke) * wNE, cEN1 = me_ke * wEN, cEE1 = me_ke * wEE;
+        const float f1x = (fmaf(cNE1, nex, -cEE1 * eex) - fmaf(cNN1, nnx, -cEN1 * enx)) * j_qeff;
+        const float f1y = (fmaf(cNE1, ney, -cEE1 * eey) - fmaf(cNN1, nny, -cEN1 * eny)) * j_qeff;
+        float tx = use0 ? f0x : 0.0f, ty = use0 ? f0y : 0.0f;
+        tx -= use1 ? f1x : 0.0f, ty -= use1 ? f1y : 0.0f;
+        ax = fmaf(tx, inv_mass, ax);
+        ay = fmaf(ty, inv_mass, ay);
+      }
+      filled = 0;
+      return;
+    } else {
     for (int t = 0; t < filled; ++t) {
       const uint32_t k = s_list[t][threadIdx.x];
       const float4 b4 = __ldg(&recB[k]);
@@ -268,6 +327,7 @@ __global__ void __launch_bounds__(kPolarThreads)
       }
     }
     filled = 0;
+    }
   };
 
   if (live) {

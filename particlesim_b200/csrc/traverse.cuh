@@ -27,6 +27,8 @@ struct FieldParams {
   float t_sq, e_sq, k_e;
   float bg_x, bg_y;
   float inv_theta;  // 1 / theta, only used by conservative pre-tests (never decides a borderline case)
+  int one_mufu;     // fast mode only: theta <= 1, epsilon and root size in the range where 1 / ((d^2 + e^2) d) is taken
+                    // as ONE rsqrt of (d^2 + e^2)^2 d^2 (see bh_group_walk)
 };
 
 // PARITY = true: IEEE sqrt/div, no FMA contraction, the reference's operation order.
@@ -273,7 +275,11 @@ struct WarpShared {
   uint32_t s_mask[32];
 };
 
-template <bool PARITY>
+// ONE (fast mode, theta <= 1): a target that accepts a node has dist - radius > size (quadtree.rs:361-371 with
+// theta <= 1), so r_eff = max(dist, radius + size / 2) IS dist and the monopole weight q / ((d^2 + e^2) d) is one
+// MUFU rsqrt of (d^2 + e^2)^2 d^2; k_e q_target is factored out of the whole sum.  The host only selects it where that
+// product can neither overflow nor underflow (FieldParams::one_mufu).
+template <bool PARITY, bool ONE = false>
 __device__ __forceinline__ float2 bh_group_walk(const float4* __restrict__ nodeA,
                                                 const uint4* __restrict__ nodeB,
                                                 const float4* __restrict__ pqr, uint32_t M, float px,
@@ -311,8 +317,9 @@ __device__ __forceinline__ float2 bh_group_walk(const float4* __restrict__ nodeA
   // group takes the exact test everywhere
   const bool finite_me = !live || (fabsf(px) < INF && fabsf(py) < INF && fabsf(radius) < INF);
   const bool box_ok = __all_sync(FULL, finite_me);
-  const float kq = A::mul(P.k_e, q);
+  const float kq = ONE ? 1.0f : A::mul(P.k_e, q);
   const float my_lim_r = radius;
+  const uint32_t lanebit = 1u << lane;
   if (lane == 0) ws.st_node[0] = 0, ws.st_mask[0] = live_mask;
   __syncwarp();
   // Ring buffer served first-in-first-out (wide rounds).  Capacity: a FIFO round pops k <= 32 entries
@@ -382,8 +389,12 @@ __device__ __forceinline__ float2 bh_group_walk(const float4* __restrict__ nodeA
     const int my_slot = __popc(lm & lt);
     if (in_sure) {
       const int sl = __popc(sm & lt);
-      ws.s_node[sl] = na;
-      ws.s_mask[sl] = mask;
+      if (ONE) {
+        ws.s_node[sl] = make_float4(na.x, na.y, na.z, __uint_as_float(mask));  // the size is not needed: r_eff = dist
+      } else {
+        ws.s_node[sl] = na;
+        ws.s_mask[sl] = mask;
+      }
     }
     if (in_list) {
       ws.l_node[my_slot] = na;
@@ -407,7 +418,21 @@ __device__ __forceinline__ float2 bh_group_walk(const float4* __restrict__ nodeA
         ay = fmaf(dy, sc, ay);
       }
     };
-    for (int it = 0; it < scnt; ++it) {
+    if (ONE) {
+#pragma unroll 2
+      for (int it = 0; it < scnt; ++it) {
+        const float4 nd = ws.s_node[it];
+        const float dx = px - nd.x, dy = py - nd.y;
+        const float d_sq = fmaf(dx, dx, dy * dy);
+        const float t = d_sq + P.e_sq;
+        const float w = rsqrt_ftz((t * t) * d_sq);
+        // a lane the node does not reach weighs its term with zero (whatever came out of the rsqrt)
+        const float sc = (__float_as_uint(nd.w) & lanebit) ? nd.z * w : 0.0f;
+        ax = fmaf(dx, sc, ax);
+        ay = fmaf(dy, sc, ay);
+      }
+    }
+    for (int it = 0; !ONE && it < scnt; ++it) {
       const float4 nd = ws.s_node[it];
       const uint32_t m = ws.s_mask[it];
       if (PARITY) {
@@ -428,7 +453,35 @@ __device__ __forceinline__ float2 bh_group_walk(const float4* __restrict__ nodeA
         ay = fmaf(dy, sc, ay);
       }
     }
-    for (int it = 0; it < cnt; ++it) {
+    if (ONE) {
+#pragma unroll 2
+      for (int it = 0; it < cnt; ++it) {
+        const float4 nd = ws.l_node[it];
+        const uint32_t m = ws.l_mask[it];
+        const float dx = px - nd.x, dy = py - nd.y;
+        const float d_sq = fmaf(dx, dx, dy * dy);
+        const bool reach = (m & lanebit) != 0;
+        // conservative pre-test with this target's own radius (its 2e-5 margins cover the contraction of d_sq); only
+        // the band in between takes the reference's test on the reference's d_sq, which alone decides a borderline case
+        const float lim = fmaf(nd.w, P.inv_theta, my_lim_r);
+        const float lim2 = lim * lim;
+        bool acc = reach && d_sq > lim2 * 1.00002f;
+        if (reach && !acc && !(d_sq < lim2 * 0.99998f)) {
+          const float ex = __fsub_rn(px, nd.x), ey = __fsub_rn(py, nd.y);
+          const float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)));
+          const float dist_adj = fmaxf(__fsub_rn(dist, radius), 0.0f);
+          acc = __fmul_rn(nd.w, nd.w) < __fmul_rn(__fmul_rn(dist_adj, dist_adj), P.t_sq);
+        }
+        const uint32_t am = __ballot_sync(FULL, acc);
+        if (lane == 0) ws.l_acc[it] = am;
+        const float t = d_sq + P.e_sq;
+        const float w = rsqrt_ftz((t * t) * d_sq);
+        const float sc = acc ? nd.z * w : 0.0f;
+        ax = fmaf(dx, sc, ax);
+        ay = fmaf(dy, sc, ay);
+      }
+    }
+    for (int it = 0; !ONE && it < cnt; ++it) {
       const float4 nd = ws.l_node[it];
       const uint32_t m = ws.l_mask[it];
       // the distance feeds the opening decision: reference arithmetic in every mode
@@ -522,7 +575,20 @@ __device__ __forceinline__ float2 bh_group_walk(const float4* __restrict__ nodeA
   }
   nodes_out = visited;
   if (lost) return make_float2(lost_value, lost_value);
+  if (ONE) {
+    const float kq1 = P.k_e * q;
+    ax *= kq1, ay *= kq1;
+  }
   return make_float2(ax, ay);
+}
+
+// Warp-uniform: may this group take the one-rsqrt monopole?  (t^2 d^2 with t = d^2 + e^2 must stay a normal number for
+// every distance a walk of this tree can meet: d <= ~1.3e6 from the bounds below, d > the smallest cell otherwise.)
+__device__ __forceinline__ bool one_mufu_ok(const FieldParams& P, const RootQuad& root, float px, float py, bool live) {
+  const bool tree_ok = P.one_mufu && root.size >= 1e-3f && root.size <= 262144.0f && fabsf(root.cx) <= 262144.0f &&
+                       fabsf(root.cy) <= 262144.0f;
+  const bool me_ok = !live || (fabsf(px) <= 524288.0f && fabsf(py) <= 524288.0f);
+  return __all_sync(0xffffffffu, tree_ok && me_ok);
 }
 
 template <bool PARITY>
@@ -543,8 +609,13 @@ __global__ void __launch_bounds__(128)
   float4 me = make_float4(0, 0, 0, 0);
   if (live) me = pqr[i];
   uint32_t visited;
-  float2 e = bh_group_walk<PARITY>(nodeA, nodeB, pqr, M, me.x, me.y, 1.0f, me.w, live, P,
-                                   ws[threadIdx.x >> 5], visited, root_size);
+  float2 e;
+  if (!PARITY && one_mufu_ok(P, meta->root, me.x, me.y, live))
+    e = bh_group_walk<PARITY, !PARITY>(nodeA, nodeB, pqr, M, me.x, me.y, 1.0f, me.w, live, P, ws[threadIdx.x >> 5], visited,
+                                       root_size);
+  else
+    e = bh_group_walk<PARITY>(nodeA, nodeB, pqr, M, me.x, me.y, 1.0f, me.w, live, P, ws[threadIdx.x >> 5], visited,
+                              root_size);
   if (live) {
     e.x = __fadd_rn(e.x, P.bg_x);
     e.y = __fadd_rn(e.y, P.bg_y);
@@ -582,8 +653,12 @@ __global__ void __launch_bounds__(128)
     if (radius) rr = radius[i];
   }
   uint32_t visited;
-  const float2 e = bh_group_walk<PARITY>(nodeA, nodeB, pqr, M, p.x, p.y, qq, rr, live, P,
-                                         ws[threadIdx.x >> 5], visited, root_size);
+  float2 e;
+  if (!PARITY && one_mufu_ok(P, meta->root, p.x, p.y, live))
+    e = bh_group_walk<PARITY, !PARITY>(nodeA, nodeB, pqr, M, p.x, p.y, qq, rr, live, P, ws[threadIdx.x >> 5], visited,
+                                       root_size);
+  else
+    e = bh_group_walk<PARITY>(nodeA, nodeB, pqr, M, p.x, p.y, qq, rr, live, P, ws[threadIdx.x >> 5], visited, root_size);
   if (live) out[i] = e;
   if (step_counter && lane == 0 && visited) atomicAdd(step_counter, (unsigned long long)visited);
 }
