@@ -731,10 +731,13 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
     se = StrictEmit{kStrictDirect, ctx->strict.cidx, ctx->strict.cw, ctx->strict.cand, ctx->strict.counters + 4,
                     ctx->strict.cand_cap};
   }
-  tree_emit_kernel<<<emit_grid, 128, 0, st>>>(
-      ctx->keys[1], ctx->keys[1], ctx->tree_plan, kTreePasses, n, per_block, ctx->le, ctx->nodebase, b.pqr,
-      b.accm, ctx->cfg.leaf_capacity, ctx->cfg.thread_capacity,
-      ctx->meta, ctx->t, se);
+  {
+    static const int minb = getenv("PSIM_EMIT_MINB") ? atoi(getenv("PSIM_EMIT_MINB")) : 10;
+    auto kern = minb >= 12 ? tree_emit_kernel<12> : minb >= 10 ? tree_emit_kernel<10> : minb >= 8 ? tree_emit_kernel<8> : tree_emit_kernel<5>;
+    kern<<<emit_grid, 128, 0, st>>>(ctx->keys[1], ctx->keys[1], ctx->tree_plan, kTreePasses, n, per_block, ctx->le,
+                                    ctx->nodebase, b.pqr, b.accm, ctx->cfg.leaf_capacity, ctx->cfg.thread_capacity,
+                                    ctx->meta, ctx->t, se);
+  }
   LAUNCHED(ctx);
   // bottom-up sweeps over the cells that straddle the emit slabs (a few thousand per level at most),
   // deepest level first; a level's node count is only known on the device

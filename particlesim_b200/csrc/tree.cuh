@@ -187,7 +187,8 @@ struct DeviceSink {
 // itself, level by level, right after writing the leaves - the records are still in L1 / L2 - and finishes
 // their centres (finalize_node).  Only the cells that straddle a slab boundary (about depth x 2 per CTA)
 // are left to the level sweeps.
-__global__ void __launch_bounds__(128)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
     tree_emit_kernel(const uint64_t* __restrict__ keys0, const uint64_t* __restrict__ keys1,
                      const SortPlan* __restrict__ plan, int npass, uint32_t n, uint32_t per_block,
                      const uint16_t* __restrict__ le, const uint32_t* __restrict__ nodebase,
@@ -230,10 +231,74 @@ __global__ void __launch_bounds__(128)
   const float root_size = meta->root.size;
   const int dcap = (int)meta->dcap;
   DeviceSink sink{strict, meta, s_cursor, s_local, t.local_nodes};
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const int straddle = has_next ? lcp_levels(keys[i], key_hi) : -1;
-    emit_nodes_for_body(keys, n, i, le[i], nodebase, M, pqr, accm, leaf_capacity, thread_capacity,
-                        root_size, dcap, t, sink, 0u, 0, straddle, true);
+  // Leaves: one thread per body.  Internal cells: the chains of a warp's 32 bodies (0 .. 31 cells each, ~0.7 on
+  // average) are dealt out to its lanes one cell at a time, so that a body at a large cell boundary does not keep 31
+  // lanes waiting; every cell finds its own range end by a galloping search that starts at its leaf's end.
+  __shared__ uint32_t s_big[4][32], s_top[4][32];
+  const uint32_t FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const uint32_t strict_limit = sink.strict_direct();
+  for (uint32_t i0 = lo; i0 < hi; i0 += blockDim.x) {  // trip count uniform over the CTA
+    const uint32_t i = i0 + threadIdx.x;
+    const bool valid = i < hi;
+    const uint16_t lev = valid ? le[i] : (uint16_t)0;
+    const int lam = le_lambda(lev), ell = le_ell(lev);
+    const bool head = valid && lam < ell;
+    const int straddle = (head && has_next) ? lcp_levels(keys[i], key_hi) : -1;
+    uint32_t base = 0, jleaf = 0;
+    if (head) {
+      base = nodebase[i];
+      jleaf = emit_leaf_for_body(keys, n, i, lam, ell, base, nodebase, M, pqr, leaf_capacity, thread_capacity, root_size,
+                                 dcap, t, sink);
+    }
+    const int len = head ? ell - lam - 1 : 0;
+    int incl = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int off = incl - len, total = __shfl_sync(FULL, incl, 31);
+    if (total == 0) continue;  // warp-uniform
+    s_big[wrp][lane] = 0;
+    __syncwarp();
+    for (int t0 = 0; t0 < total; t0 += 32) {
+      const int tt = t0 + lane;
+      // owner = the last lane whose exclusive offset is <= tt (lanes without cells share their successor's offset)
+      int o = 0;
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) {
+        const int cand = o + sft;
+        const int v = __shfl_sync(FULL, off, cand & 31);
+        if (cand < 32 && v <= tt) o = cand;
+      }
+      const int o_off = __shfl_sync(FULL, off, o);
+      const uint32_t o_lev = __shfl_sync(FULL, (uint32_t)lev, o);
+      const uint32_t o_base = __shfl_sync(FULL, base, o);
+      const uint32_t o_jleaf = __shfl_sync(FULL, jleaf, o);
+      const int o_straddle = __shfl_sync(FULL, straddle, o);
+      if (tt < total) {
+        const uint32_t oi = i - (uint32_t)lane + (uint32_t)o;
+        const int o_lam = le_lambda((uint16_t)o_lev), o_ell = le_ell((uint16_t)o_lev);
+        const int d = o_ell - 1 - (tt - o_off);
+        const uint32_t node = o_base + (uint32_t)(d - o_lam - 1);
+        const uint32_t jd = run_end(keys, n, oi, o_jleaf, d);
+        const uint32_t nx = (jd < n) ? nodebase[jd] : M;
+        const uint32_t cnt = jd - oi;
+        t.nodeB[node] = make_uint4(nx, oi, cnt, (uint32_t)d);
+        t.ndepth[node] = (uint8_t)d;
+        if (d <= o_straddle) t.level_nodes[sink.level_slot(d)] = node;
+        else sink.local_node(d, node);
+        if (cnt > strict_limit) atomicAdd(&s_big[wrp][o], 1u);
+        if (d == o_lam + 1) s_top[wrp][o] = cnt;
+      }
+    }
+    __syncwarp();
+    if (head && len > 0) {
+      const uint32_t big = s_big[wrp][lane];
+      if (big) sink.strict_chain(i, base, big, s_top[wrp][lane]);
+    }
+    __syncwarp();
   }
   // the slab's own cells, deepest level first
   for (int level = kLevels - 1; level >= 0; --level) {

@@ -146,6 +146,50 @@ PSIM_HD void level_scan(TreeMeta* meta, uint32_t node_cap) {
   if (meta->num_nodes > node_cap) meta->err |= 1u;
 }
 
+// The leaf whose first body is i (the first half of emit_nodes_for_body, for the single-GPU emit kernel, which deals the
+// internal cells of a warp's chains out to its lanes): returns the end of the leaf's body range.
+template <class Sink>
+PSIM_HD uint32_t emit_leaf_for_body(const uint64_t* keys, uint32_t n, uint32_t i, int lam, int ell, uint32_t base,
+                                    const uint32_t* nodebase, uint32_t M, const float4* pqr, uint32_t leaf_capacity,
+                                    uint32_t thread_capacity, float root_size, int dcap, const TreeArrays& t, Sink& sink) {
+  const int d = ell;
+  const uint32_t j = run_end(keys, n, i, i + 1, d);
+  const uint32_t node = base + (uint32_t)(d - lam - 1);
+  const uint32_t next = (j < n) ? nodebase[j] : M;
+  const uint32_t count = j - i;
+  const float size = ldexpf(root_size, -d);  // size *= 0.5 per level, exact
+  const bool agg = leaf_is_aggregated(count, leaf_capacity, thread_capacity);
+  float tq = 0.0f, wx = 0.0f, wy = 0.0f;
+  double aq = 0.0, aqx = 0.0, aqy = 0.0;
+  for (uint32_t b = i; b < j; ++b) {
+    const float4 p = pqr[b];
+    const double a = fabs((double)p.z);
+    aq += a, aqx += a * (double)p.x, aqy += a * (double)p.y;
+    if (agg) {
+      wx = f_add(wx, f_mul(p.x, p.z));
+      wy = f_add(wy, f_mul(p.y, p.z));
+      tq = f_add(tq, p.z);
+    }
+  }
+  if (agg) {
+    if (fabsf(tq) > 1e-6f) {
+      wx = f_div(wx, tq);
+      wy = f_div(wy, tq);
+    }
+  } else {
+    sink.zero_leaf();
+  }
+  if (count > 1 && d == dcap) sink.cap_leaf();
+  t.nodeA[node] = make_float4(wx, wy, tq, size);
+  t.nodeB[node] = make_uint4(next, i, count, (uint32_t)d | kNodeLeaf | (agg ? 0u : kNodeZeroAgg) | (aq > 0.0 ? kNodeCharged : 0u));
+  const bool last = (j >= n) || lcp_levels(keys[i], keys[j]) < d - 1;
+  NodeRec r;
+  r.aq = aq, r.aqx = aqx, r.aqy = aqy, r.charge = tq, r.next = next | (last ? kLastSibling : 0u);
+  t.rec[node] = r;
+  t.ndepth[node] = (uint8_t)((uint32_t)d | (aq > 0.0 ? kDepthCharged : 0u));
+  return j;
+}
+
 // All nodes whose first body is i: the leaf at depth ℓ_i and the internal cells above it down to
 // depth λ_i + 1.  The leaf is finished here (range end by galloping search, aggregates per
 // quadtree.rs:281-306, Σ|q| sums for its ancestors); internal cells only get their depth and first
