@@ -611,6 +611,7 @@ int32_t ensure_strict(psim_ctx* ctx) {
     if (ok && dalloc(p, cnt) != cudaSuccess) ok = false;
   };
   S.cand_cap = (uint32_t)(nb / 16 + 4096);  // chains with a node of more than kStrictDirect bodies: <= 32 levels * nb / 64
+  A(&S.qstat, 3), A(&S.qc, nb + 2);
   A(&S.cidx, nb + 1), A(&S.cw, nb), A(&S.chains, S.cand_cap), A(&S.cand, S.cand_cap), A(&S.hist, 96), A(&S.longs, S.long_cap), A(&S.counters, 8);
   A(&S.item_first, (size_t)S.long_cap + 1), A(&S.pblk, 3 * ((size_t)S.blk_cap + 1)), A(&S.fns, 3 * (size_t)S.item_cap);
   if (!ok) {
@@ -634,9 +635,13 @@ int32_t strict_prepare(psim_ctx* ctx) {
   BodyArrays& b = ctx->b[ctx->cur];
   StrictArrays& S = ctx->strict;
   CK(exclusive_scan(ChargedBodyFn{b.pqr}, n, S.cidx, ctx->scan_partials, S.cidx + n, st));
-  strict_addends_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(b.pqr, n, S.cidx, S.cw, S.hist, S.counters);
+  CK(cudaMemsetAsync(S.qstat, 0, 3 * sizeof(unsigned long long), st));
+  strict_addends_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(b.pqr, n, S.cidx, S.cw, S.hist, S.counters, S.qstat);
   CK(cudaMemsetAsync(S.counters + 4, 0, sizeof(uint32_t), st));
-  ctx->launches += 4;
+  // integer prefix of the charges over the charged bodies (tree.cuh StrictEmit::qc); its length only exists on the device
+  CK(exclusive_scan_dyn(ChargeIntFn{S.cw, S.cidx + n}, reinterpret_cast<const uint32_t*>(S.qstat + 2), n + 1, S.qc,
+                        ctx->scan_partials, nullptr, st));
+  ctx->launches += 7;
   return PSIM_OK;
 }
 
@@ -718,18 +723,20 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
   const uint32_t per_block = 512u;
   const int emit_grid = (int)((n + per_block - 1) / per_block);
   tree_count_kernel<<<grid_for(ctx, n, 256, 8), 256, 0, st>>>(
-      ctx->keys[1], ctx->keys[1], ctx->tree_plan, kTreePasses, b.pqr, n, c_eff, per_block, ctx->meta, ctx->le);
+      ctx->keys[1], ctx->keys[1], ctx->tree_plan, kTreePasses, b.pqr, n, c_eff, per_block, ctx->meta, ctx->le,
+      ctx->cfg.leaf_capacity, ctx->cfg.thread_capacity);
   LAUNCHED(ctx);
   CK(exclusive_scan(LeCountFn{ctx->le}, n, ctx->nodebase, ctx->scan_partials, &ctx->meta->num_nodes, st));
   ctx->launches += 3;
   level_scan_kernel<<<1, 32, 0, st>>>(ctx->meta, ctx->node_cap);
   LAUNCHED(ctx);
-  StrictEmit se = {0, nullptr, nullptr, nullptr, nullptr, 0};
+  StrictEmit se = {0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr};
   if (ctx->cfg.strict_centres) {
     const int32_t rc = strict_prepare(ctx);
     if (rc) return rc;
+    static const bool no_intq = getenv("PSIM_INTEGER_CHARGES") && getenv("PSIM_INTEGER_CHARGES")[0] == '0';
     se = StrictEmit{kStrictDirect, ctx->strict.cidx, ctx->strict.cw, ctx->strict.cand, ctx->strict.counters + 4,
-                    ctx->strict.cand_cap};
+                    ctx->strict.cand_cap, no_intq ? nullptr : ctx->strict.qstat, ctx->strict.qc};
   }
   {
     static const int minb = getenv("PSIM_EMIT_MINB") ? atoi(getenv("PSIM_EMIT_MINB")) : 10;
@@ -744,7 +751,7 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
   // one CTA per SM, all resident (128 threads each): the kernel's grid barrier needs every CTA running
   CK(cudaMemsetAsync(ctx->grid_barrier, 0, sizeof(unsigned int), st));
   aggregate_levels_kernel<<<ctx->sm_count, 128, 0, st>>>(ctx->meta, b.pqr, b.accm, ctx->t,
-                                                        StrictDirect{se.direct, se.cidx, se.cw}, ctx->grid_barrier);
+                                                        StrictDirect{se.direct, se.cidx, se.cw}, ctx->grid_barrier, se.qstat);
   LAUNCHED(ctx);
   if (ctx->cfg.strict_centres) {
     const int32_t rc = strict_stage(ctx);
@@ -1212,7 +1219,7 @@ void free_all(psim_ctx* c) {
   F(c->surround.last_pos), F(c->surround.last_frame), F(c->surround.flag);
   F(c->cell_start), F(c->cell_end), F(c->order), F(c->body_cell), F(c->cpos), F(c->polarB), F(c->polar_cutoff), F(c->cell_off);
   F(c->table_d), F(c->stage), F(c->qstage), F(c->step_counter), F(c->grid_barrier);
-  F(c->strict.cidx), F(c->strict.cw), F(c->strict.chains), F(c->strict.hist), F(c->strict.longs), F(c->strict.counters);
+  F(c->strict.qstat), F(c->strict.qc), F(c->strict.cidx), F(c->strict.cw), F(c->strict.chains), F(c->strict.hist), F(c->strict.longs), F(c->strict.counters);
   F(c->strict.item_first), F(c->strict.pblk), F(c->strict.fns), F(c->strict.cand);
 }
 

@@ -49,7 +49,9 @@ struct StrictLong {  // a chain handed over to the block machinery
 
 struct StrictArrays {
   uint32_t* cidx;        // n + 1
-  float4* cw;            // charged bodies: {|q|, x|q|, y|q|, 0}
+  float4* cw;            // charged bodies: {|q|, x|q|, y|q|, q}
+  unsigned long long* qstat;  // 3 words, see strict_addends_kernel
+  uint32_t* qc;          // charged bodies + 1: integer prefix of the charges
   uint4* chains;         // per chain {head body, shallowest node, first addend, length | (nodes - 1) << 27},
                          // by length class, longest first
   uint32_t* hist;        // [0, 32): class counts, [32]: chains, [64, 96): scatter cursors
@@ -68,21 +70,49 @@ struct ChargedBodyFn {
   __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return pqr[i].z != 0.0f ? 1u : 0u; }
 };
 
+// Besides the addends: cw.w carries the signed charge, and qstat collects what the emit kernel needs to know whether
+// node charges can be taken as exact integer prefix differences (IntegerCharges below): [0] = sum of |q| over the
+// bodies whose charge is an integer below 2^20, [1] = number of charged bodies whose charge is not, and the word at
+// qstat + 2 = number of charged bodies + 1 (length of the prefix array).
 __global__ void __launch_bounds__(256)
     strict_addends_kernel(const float4* __restrict__ pqr, uint32_t n, const uint32_t* __restrict__ cidx,
-                          float4* __restrict__ cw, uint32_t* __restrict__ hist, uint32_t* __restrict__ counters) {
+                          float4* __restrict__ cw, uint32_t* __restrict__ hist, uint32_t* __restrict__ counters,
+                          unsigned long long* __restrict__ qstat) {
   const uint32_t stride = gridDim.x * blockDim.x;
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid < 96) hist[tid] = 0;
   if (tid < 4) counters[tid] = 0;
+  if (tid == 0) *reinterpret_cast<uint32_t*>(qstat + 2) = cidx[n] + 1u;
+  unsigned long long abs_sum = 0;
+  uint32_t bad = 0;
   for (uint32_t i = tid; i < n; i += stride) {
     const float4 p = pqr[i];
     if (p.z != 0.0f) {
       const float a = fabsf(p.z);
-      cw[cidx[i]] = make_float4(a, f_mul(p.x, a), f_mul(p.y, a), 0.0f);
+      cw[cidx[i]] = make_float4(a, f_mul(p.x, a), f_mul(p.y, a), p.z);
+      if (a < 1048576.0f && p.z == rintf(p.z)) abs_sum += (unsigned long long)a;
+      else ++bad;
     }
   }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    abs_sum += __shfl_xor_sync(0xffffffffu, abs_sum, off);
+    bad += __shfl_xor_sync(0xffffffffu, bad, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (abs_sum) atomicAdd(&qstat[0], abs_sum);
+    if (bad) atomicAdd(&qstat[1], (unsigned long long)bad);
+  }
 }
+
+// integer charge of the k-th charged body, for the prefix array qc (0 beyond the last one)
+struct ChargeIntFn {
+  const float4* cw;
+  const uint32_t* ncharged;
+  __device__ __forceinline__ uint32_t operator()(uint32_t k) const {
+    return k < *ncharged ? (uint32_t)__float2int_rn(cw[k].w) : 0u;
+  }
+};
 
 __device__ __forceinline__ int chain_class(uint32_t len) {
   const int c = 32 - __clz(len);

@@ -107,14 +107,17 @@ __global__ void __launch_bounds__(256)
     tree_count_kernel(const uint64_t* __restrict__ keys0, const uint64_t* __restrict__ keys1,
                       const SortPlan* __restrict__ plan, int npass, const float4* __restrict__ pqr,
                       uint32_t n, uint32_t c_eff, uint32_t per_block, TreeMeta* __restrict__ meta,
-                      uint16_t* __restrict__ le) {
+                      uint16_t* __restrict__ le, uint32_t leaf_capacity, uint32_t thread_capacity) {
   const uint64_t* __restrict__ keys = plan->src[npass] ? keys1 : keys0;
   __shared__ uint32_t s_cnt[kLevels];
-  __shared__ uint32_t s_maxd, s_internal;
+  __shared__ uint32_t s_maxd, s_internal, s_zero_agg;
   if (threadIdx.x < kLevels) s_cnt[threadIdx.x] = 0;
-  if (threadIdx.x == 0) s_maxd = 0, s_internal = 0;
+  if (threadIdx.x == 0) s_maxd = 0, s_internal = 0, s_zero_agg = 0;
   __syncthreads();
   const int dcap = (int)meta->dcap;
+  // a leaf of at least this many bodies is not aggregated (leaf_is_aggregated)
+  const uint64_t min_zero = (uint64_t)leaf_capacity + 1 < (uint64_t)thread_capacity ? (uint64_t)leaf_capacity + 1
+                                                                                    : (uint64_t)thread_capacity;
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const uint16_t lev = body_levels(keys, pqr, n, i, c_eff, dcap);
@@ -129,9 +132,12 @@ __global__ void __launch_bounds__(256)
         for (int d = lam + 1; d <= top; ++d) atomicAdd(&s_cnt[d], 1u);
       }
       atomicMax(&s_maxd, (uint32_t)ell);
+      if (min_zero <= 1 || ((uint64_t)i + min_zero - 1 < n && lcp_levels(keys[i], keys[i + (uint32_t)min_zero - 1]) >= ell))
+        s_zero_agg = 1u;
     }
   }
   __syncthreads();
+  if (threadIdx.x == 0 && s_zero_agg) meta->zero_agg_hint = 1u;
   if (threadIdx.x < kLevels && s_cnt[threadIdx.x]) atomicAdd(&meta->level_count[threadIdx.x], s_cnt[threadIdx.x]);
   if (threadIdx.x == 0 && s_maxd) atomicMax(&meta->max_depth, s_maxd);
   if (threadIdx.x == 0 && s_internal) atomicAdd(&meta->internal_total, s_internal);
@@ -158,7 +164,15 @@ struct StrictEmit {        // psim_config.strict_centres (strict.cuh); direct ==
   uint4* cand;             // chains with larger nodes: {head body, shallowest node, big nodes - 1, bodies of the largest}
   uint32_t* cand_count;
   uint32_t cand_cap;
+  // Integer charges (what Body::update_charge_from_electrons produces): while every partial sum of the reference's
+  // nested f32 additions ((c0 + c1) + c2) + c3 (quadtree.rs:142-149) is an integer below 2^24 it is exact, so a node's
+  // charge is the difference of an integer prefix over its charged bodies, whatever the order - no bottom-up sweep.
+  const unsigned long long* qstat;  // strict_addends_kernel; null: never
+  const uint32_t* qc;               // qc[k] = sum of the charges of the first k charged bodies (mod 2^32)
 };
+__device__ __forceinline__ bool integer_charges(const unsigned long long* qstat, const TreeMeta* meta) {
+  return qstat && qstat[1] == 0ull && qstat[0] < (1ull << 24) && meta->zero_agg_hint == 0u;
+}
 
 struct DeviceSink {
   static constexpr bool kTop = false;
@@ -207,7 +221,9 @@ __global__ void __launch_bounds__(128, MINB)
   const uint32_t hi = (lo + per_block < n) ? lo + per_block : n;
   const bool has_next = hi < n;
   const uint64_t key_hi = has_next ? keys[hi] : 0ull;
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+  // integer charges: every internal cell is finished where it is emitted (no lists, no sweep, no NodeRec)
+  const bool fastq = strict.direct != 0 && integer_charges(strict.qstat, meta);
+  for (uint32_t i = lo + threadIdx.x; !fastq && i < hi; i += blockDim.x) {
     const uint16_t lev = le[i];
     const int lam = le_lambda(lev), ell = le_ell(lev);
     if (ell - lam > 1) {
@@ -249,7 +265,7 @@ __global__ void __launch_bounds__(128, MINB)
     if (head) {
       base = nodebase[i];
       jleaf = emit_leaf_for_body(keys, n, i, lam, ell, base, nodebase, M, pqr, leaf_capacity, thread_capacity, root_size,
-                                 dcap, t, sink);
+                                 dcap, t, sink, !fastq);
     }
     const int len = head ? ell - lam - 1 : 0;
     int incl = len;
@@ -285,10 +301,28 @@ __global__ void __launch_bounds__(128, MINB)
         const uint32_t jd = run_end(keys, n, oi, o_jleaf, d);
         const uint32_t nx = (jd < n) ? nodebase[jd] : M;
         const uint32_t cnt = jd - oi;
-        t.nodeB[node] = make_uint4(nx, oi, cnt, (uint32_t)d);
-        t.ndepth[node] = (uint8_t)d;
-        if (d <= o_straddle) t.level_nodes[sink.level_slot(d)] = node;
-        else sink.local_node(d, node);
+        if (fastq) {
+          const uint32_t c0 = strict.cidx[oi], c1 = strict.cidx[jd];
+          const uint32_t chg = c1 > c0 ? 1u : 0u;
+          const float q = (float)(int32_t)(strict.qc[c1] - strict.qc[c0]);
+          float px = 0.0f, py = 0.0f;
+          if (cnt <= strict_limit && chg) {  // the reference's serial sums over the cell's charged bodies (finalize_node)
+            float total_abs = 0.0f, wx = 0.0f, wy = 0.0f;
+            for (uint32_t k = c0; k < c1; ++k) {
+              const float4 w = strict.cw[k];
+              total_abs = f_add(total_abs, w.x), wx = f_add(wx, w.y), wy = f_add(wy, w.z);
+            }
+            px = f_div(wx, total_abs), py = f_div(wy, total_abs);  // total_abs >= 1: integer charges
+          }
+          t.nodeA[node] = make_float4(px, py, q, ldexpf(root_size, -d));
+          t.nodeB[node] = make_uint4(nx, oi, cnt, (uint32_t)d | (chg ? kNodeCharged : 0u));
+          t.ndepth[node] = (uint8_t)((uint32_t)d | (chg ? kDepthCharged : 0u));
+        } else {
+          t.nodeB[node] = make_uint4(nx, oi, cnt, (uint32_t)d);
+          t.ndepth[node] = (uint8_t)d;
+          if (d <= o_straddle) t.level_nodes[sink.level_slot(d)] = node;
+          else sink.local_node(d, node);
+        }
         if (cnt > strict_limit) atomicAdd(&s_big[wrp][o], 1u);
         if (d == o_lam + 1) s_top[wrp][o] = cnt;
       }
@@ -301,7 +335,7 @@ __global__ void __launch_bounds__(128, MINB)
     __syncwarp();
   }
   // the slab's own cells, deepest level first
-  for (int level = kLevels - 1; level >= 0; --level) {
+  for (int level = kLevels - 1; !fastq && level >= 0; --level) {
     const uint32_t begin = s_in_off[level], end = s_in_off[level + 1];
     if (begin == end) continue;  // uniform over the CTA
     __threadfence_block();
@@ -337,9 +371,10 @@ __global__ void __launch_bounds__(128)
 __global__ void __launch_bounds__(128)
     aggregate_levels_kernel(const TreeMeta* __restrict__ meta, const float4* __restrict__ pqr,
                             const float4* __restrict__ accm, TreeArrays t, StrictDirect strict_direct,
-                            unsigned int* __restrict__ barrier) {
+                            unsigned int* __restrict__ barrier, const unsigned long long* __restrict__ qstat) {
   const uint32_t M = meta->num_nodes;
   if (M > t.node_cap) return;
+  if (strict_direct.limit && integer_charges(qstat, meta)) return;  // the emit kernel has finished every cell
   const float root_size = meta->root.size;
   const uint32_t stride = gridDim.x * blockDim.x;
   unsigned int target = 0;

@@ -28,6 +28,7 @@ struct TreeMeta {
   uint32_t level_start[kLevels + 1];
   uint32_t level_cursor[kLevels];
   uint32_t internal_total;  // all internal nodes (level_count only covers the ones the level sweeps visit)
+  uint32_t zero_agg_hint;   // some leaf holds more bodies than it aggregates: set by tree_count_kernel
 };
 
 struct NodeSums {  // per internal node: running sums over its body range
@@ -116,6 +117,7 @@ PSIM_HD void meta_reset(TreeMeta* meta, RootQuad r, uint32_t n) {
   meta->num_zero_leaves = 0;
   meta->num_cap_leaves = 0;
   meta->internal_total = 0;
+  meta->zero_agg_hint = 0;
   for (int l = 0; l < kLevels; ++l) meta->level_count[l] = 0, meta->level_cursor[l] = 0;
 }
 
@@ -151,7 +153,8 @@ PSIM_HD void level_scan(TreeMeta* meta, uint32_t node_cap) {
 template <class Sink>
 PSIM_HD uint32_t emit_leaf_for_body(const uint64_t* keys, uint32_t n, uint32_t i, int lam, int ell, uint32_t base,
                                     const uint32_t* nodebase, uint32_t M, const float4* pqr, uint32_t leaf_capacity,
-                                    uint32_t thread_capacity, float root_size, int dcap, const TreeArrays& t, Sink& sink) {
+                                    uint32_t thread_capacity, float root_size, int dcap, const TreeArrays& t, Sink& sink,
+                                    bool write_rec = true) {
   const int d = ell;
   const uint32_t j = run_end(keys, n, i, i + 1, d);
   const uint32_t node = base + (uint32_t)(d - lam - 1);
@@ -185,7 +188,7 @@ PSIM_HD uint32_t emit_leaf_for_body(const uint64_t* keys, uint32_t n, uint32_t i
   const bool last = (j >= n) || lcp_levels(keys[i], keys[j]) < d - 1;
   NodeRec r;
   r.aq = aq, r.aqx = aqx, r.aqy = aqy, r.charge = tq, r.next = next | (last ? kLastSibling : 0u);
-  t.rec[node] = r;
+  if (write_rec) t.rec[node] = r;
   t.ndepth[node] = (uint8_t)((uint32_t)d | (aq > 0.0 ? kDepthCharged : 0u));
   return j;
 }
@@ -456,7 +459,7 @@ PSIM_HD void aggregate_node(uint32_t node, float root_size, const float4* pqr, c
   t.sums[node] = s;
   t.node_mass[node] = msum;
   t.nodeB[node].z = count;
-  if (write_chargeless_centres && !(t.rec[node].aq > 0.0)) {
+  if (write_chargeless_centres && !(nb.w & kNodeCharged)) {
     float px = 0.0f, py = 0.0f;
     if (s.m > (double)1e-6f) {
       px = (float)(s.mx / s.m), py = (float)(s.my / s.m);

@@ -111,6 +111,17 @@ def uniform_pm1(n, seed=SEED, rho=RHO):
     return dict(pos=pos, charge=q, radius=radius, species=species, mass=mass, hw=L / 2, hh=L / 2)
 
 
+def fractional(n, seed=SEED, rho=RHO):
+    """uniform_pm1 with non-integer charges (some zero): node charges then need the bottom-up sweep in the reference's
+    child order; integer charges take the exact prefix-difference path of the emit kernel"""
+    b = uniform_pm1(n, seed=seed, rho=rho)
+    rng = np.random.default_rng(seed + 1)
+    f = rng.uniform(0.05, 3.0, n).astype(np.float32)
+    f[rng.random(n) < 0.3] = 0.0
+    b["charge"] = (b["charge"] * f).astype(np.float32)
+    return b
+
+
 def electrolyte(n, seed=SEED, rho=RHO):
     """config 4: Li+ / PF6- / EC / DMC at 342:342:2393:2394 (scenario.rs:180-200)."""
     rng = np.random.default_rng(seed)

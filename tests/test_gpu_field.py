@@ -13,7 +13,7 @@ plus the BH-vs-FP64-direct error, which must be the same for device and oracle.
 import numpy as np
 import pytest
 
-from helpers import KE, canonical_from_nodes, clustered, electrolyte, oracle_for, rel_l2, uniform_pm1
+from helpers import KE, canonical_from_nodes, clustered, electrolyte, fractional, oracle_for, rel_l2, uniform_pm1
 from test_gpu_tree import make_sim
 
 pytestmark = pytest.mark.gpu
@@ -253,6 +253,7 @@ def test_nonfinite_target_does_not_hang(cuda_device):
     ("uniform_50k", lambda: uniform_pm1(50_000), 0, 1.0),
     ("electrolyte_50k", lambda: electrolyte(50_000), 1, 0.5),
     ("clustered_60k", lambda: clustered(60_000), 0, 1.0),
+    ("fractional_70k", lambda: fractional(70_000), 0, 1.0),
 ])
 def test_strict_centres_reproduce_the_reference_bit_for_bit(cuda_device, name, gen, mode, theta):
     """psim_config.strict_centres + parity_mode 2: node centres by the reference's serial f32 running sums,

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from helpers import (KE, Emu, assert_same_topology, canonical_from_nodes, check_next_pointers, clustered,
-                     electrolyte, oracle_for, rel_l2, uniform_pm1)
+                     electrolyte, fractional, oracle_for, rel_l2, uniform_pm1)
 
 pytestmark = pytest.mark.gpu
 
@@ -37,6 +37,7 @@ CASES = [
     ("uniform_3", lambda: uniform_pm1(3)), ("uniform_33", lambda: uniform_pm1(33)),
     ("uniform_4097", lambda: uniform_pm1(4097)), ("uniform_100k", lambda: uniform_pm1(100_000)),
     ("electrolyte_50k", lambda: electrolyte(50_000)), ("clustered_60k", lambda: clustered(60_000)),
+    ("fractional_70k", lambda: fractional(70_000)),
 ]
 
 
