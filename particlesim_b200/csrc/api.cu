@@ -1073,6 +1073,20 @@ int32_t electrons_async(psim_ctx* ctx, float bg_x, float bg_y, float dt, float k
   return PSIM_OK;
 }
 
+// exclusive prefix of the cell populations: the bodies of cells [c0, c1] are the slots [cell_off[c0], cell_off[c1 + 1])
+// of the cell order (a row of neighbouring cells is ONE contiguous run)
+int32_t ensure_cell_off(psim_ctx* ctx) {
+  if (ctx->cell_off_valid) return PSIM_OK;
+  const uint64_t ncells = (uint64_t)ctx->grid.gx * ctx->grid.gy;
+  int32_t rc = ensure_qstage(ctx, ((size_t)scan_num_tiles((uint32_t)ncells) + 2) * sizeof(uint32_t));
+  if (rc) return rc;
+  CK(exclusive_scan(CellCountFn{ctx->cell_start, ctx->cell_end}, (uint32_t)ncells, ctx->cell_off,
+                    static_cast<uint32_t*>(ctx->qstage), ctx->cell_off + ncells, ctx->stream));
+  ctx->launches += 3;
+  ctx->cell_off_valid = true;
+  return PSIM_OK;
+}
+
 int32_t short_range_async(psim_ctx* ctx, uint32_t flags) {
   const uint32_t n = ctx->n;
   if (n == 0) return PSIM_OK;
@@ -1105,14 +1119,9 @@ int32_t short_range_async(psim_ctx* ctx, uint32_t flags) {
   P.range = (P.do_lj || P.do_rep) ? (int)ceilf(reach / ctx->grid.cell_size) : 0;
   if (P.range < 0) P.range = 0;
   BodyArrays& b = ctx->b[ctx->cur];
-  if ((P.do_lj || P.do_rep) && !ctx->cell_off_valid) {
-    const uint64_t ncells = (uint64_t)ctx->grid.gx * ctx->grid.gy;
-    int32_t rc = ensure_qstage(ctx, ((size_t)scan_num_tiles((uint32_t)ncells) + 2) * sizeof(uint32_t));
+  if (P.do_lj || P.do_rep) {
+    const int32_t rc = ensure_cell_off(ctx);
     if (rc) return rc;
-    CK(exclusive_scan(CellCountFn{ctx->cell_start, ctx->cell_end}, (uint32_t)ncells, ctx->cell_off,
-                      static_cast<uint32_t*>(ctx->qstage), ctx->cell_off + ncells, ctx->stream));
-    ctx->launches += 3;
-    ctx->cell_off_valid = true;
   }
   uint32_t first, count;
   body_range(ctx, first, count);
@@ -1132,6 +1141,10 @@ int32_t polar_async(psim_ctx* ctx, float k_e, int dipole_model) {
   BodyArrays& b = ctx->b[ctx->cur];
   const int e = ctx->ecur;
   CK(cudaMemsetAsync(ctx->polar_cutoff, 0, sizeof(uint32_t), st));
+  {
+    const int32_t rc = ensure_cell_off(ctx);
+    if (rc) return rc;
+  }
   // cell-ordered records; record A reuses the staging area of the short-range pass layout (x, y, charge, radius)
   int32_t rc = ensure_stage(ctx, (size_t)n * sizeof(float4));
   if (rc) return rc;
@@ -1150,12 +1163,12 @@ int32_t polar_async(psim_ctx* ctx, float k_e, int dipole_model) {
   if (count == 0) return PSIM_OK;
   if (ctx->cfg.parity_mode)
     polar_forces_kernel<true><<<(count + kPolarThreads - 1) / kPolarThreads, kPolarThreads, 0, st>>>(
-        b.pqr, b.species, b.ecount, ctx->eoff[e], ctx->erel[e], ctx->table_d, first, first + count, ctx->cell_start,
-        ctx->cell_end, recA, ctx->polarB, ctx->body_cell, ctx->polar_cutoff, P, b.accm);
+        b.pqr, b.species, b.ecount, ctx->eoff[e], ctx->erel[e], ctx->table_d, first, first + count, ctx->cell_off, recA,
+        ctx->polarB, ctx->body_cell, ctx->polar_cutoff, P, b.accm);
   else
     polar_forces_kernel<false><<<(count + kPolarThreads - 1) / kPolarThreads, kPolarThreads, 0, st>>>(
-        b.pqr, b.species, b.ecount, ctx->eoff[e], ctx->erel[e], ctx->table_d, first, first + count, ctx->cell_start,
-        ctx->cell_end, recA, ctx->polarB, ctx->body_cell, ctx->polar_cutoff, P, b.accm);
+        b.pqr, b.species, b.ecount, ctx->eoff[e], ctx->erel[e], ctx->table_d, first, first + count, ctx->cell_off, recA,
+        ctx->polarB, ctx->body_cell, ctx->polar_cutoff, P, b.accm);
   LAUNCHED(ctx);
   return PSIM_OK;
 }

@@ -194,8 +194,8 @@ __global__ void __launch_bounds__(kPolarThreads)
     polar_forces_kernel(const float4* __restrict__ pqr, const uint8_t* __restrict__ species,
                         const uint8_t* __restrict__ ecount, const uint32_t* __restrict__ eoff,
                         const float2* __restrict__ erel, const SpeciesRow* __restrict__ table_g,
-                        uint32_t first, uint32_t n, const uint32_t* __restrict__ cell_start,
-                        const uint32_t* __restrict__ cell_end, const float4* __restrict__ recA,
+                        uint32_t first, uint32_t n, const uint32_t* __restrict__ cell_off,
+                        const float4* __restrict__ recA,
                         const float4* __restrict__ recB, const uint32_t* __restrict__ body_cell,
                         const uint32_t* __restrict__ max_cutoff_bits, PolarParams P,
                         float4* __restrict__ acc_mass) {
@@ -339,20 +339,19 @@ __global__ void __launch_bounds__(kPolarThreads)
     // any pair closer than this may interact (either partner's 3 * radius, bounded by the largest one present)
     const float any_cut_sq = __fmul_rn(max_cutoff, max_cutoff);
     for (int y = y0; y <= y1; ++y) {
-      for (int x = x0; x <= x1; ++x) {
-        const uint32_t cc = (uint32_t)x + (uint32_t)y * P.g.gx;
-        const uint32_t k1 = cell_end[cc];
-        for (uint32_t k = cell_start[cc]; k < k1; ++k) {
-          const float4 a4 = __ldg(&recA[k]);
-          const float rx = __fsub_rn(a4.x, me.x), ry = __fsub_rn(a4.y, me.y);
-          const float r2 = __fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry));
-          if (!(r2 < any_cut_sq)) continue;
-          const float4 b4 = __ldg(&recB[k]);
-          if (__float_as_uint(b4.y) == i) continue;
-          if (!me_dip && !(__float_as_uint(b4.x) & kPolarHasDipole)) continue;
-          s_list[filled][threadIdx.x] = k;
-          if (++filled == kPolarList) drain();
-        }
+      // the cells x0 .. x1 of a row are one contiguous run of the cell order (same candidate order as cell by cell)
+      const uint32_t row = (uint32_t)y * P.g.gx;
+      const uint32_t k1 = cell_off[row + (uint32_t)x1 + 1u];
+      for (uint32_t k = cell_off[row + (uint32_t)x0]; k < k1; ++k) {
+        const float4 a4 = __ldg(&recA[k]);
+        const float rx = __fsub_rn(a4.x, me.x), ry = __fsub_rn(a4.y, me.y);
+        const float r2 = __fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry));
+        if (!(r2 < any_cut_sq)) continue;
+        const float4 b4 = __ldg(&recB[k]);
+        if (__float_as_uint(b4.y) == i) continue;
+        if (!me_dip && !(__float_as_uint(b4.x) & kPolarHasDipole)) continue;
+        s_list[filled][threadIdx.x] = k;
+        if (++filled == kPolarList) drain();
       }
     }
   }

@@ -561,6 +561,93 @@ void emu_walk_signatures(void* h, uint32_t m, const float* pts_xy, const float* 
   }
 }
 
+// Diagnostic (tools/walk_stats.py): interaction-list statistics of the group walk on the CHARGED nodes only (what the
+// traversal arrays hold), with the group's targets split into `nsub` sub-boxes for the classification.
+// out: [0] walks [1] rounds [2] nodes visited [3] sure entries [4] undecided entries (per-target test) [5] entries decided
+// per sub-box with mixed outcome [6] nodes opened for every target [7] leaves with direct terms [8] accepted (target, node)
+// pairs [9] targets reaching sure entries [10] targets reaching undecided entries [11] direct (target, body) terms
+void emu_group_stats(void* h, uint32_t m, const float* pts_xy, const float* radius, float theta, int nsub, uint64_t* out) {
+  Emu& e = *static_cast<Emu*>(h);
+  const uint32_t M = e.meta.num_nodes;
+  const float inv_theta = 1.0f / theta;
+  const float INF = INFINITY;
+  for (int k = 0; k < 14; ++k) out[k] = 0;
+  const int per = 32 / nsub;
+  for (uint32_t g = 0; g < (m + 31) / 32; ++g) {
+    float px[32], py[32], rad[32];
+    uint32_t live_mask = 0;
+    float bx0[8], bx1[8], by0[8], by1[8], rmin[8], rmax[8];
+    uint32_t submask[8];
+    for (int s2 = 0; s2 < nsub; ++s2) bx0[s2] = by0[s2] = rmin[s2] = INF, bx1[s2] = by1[s2] = rmax[s2] = -INF, submask[s2] = 0;
+    for (int l = 0; l < 32; ++l) {
+      const uint32_t i = g * 32 + l;
+      if (i >= m) continue;
+      live_mask |= 1u << l;
+      px[l] = pts_xy[2 * i], py[l] = pts_xy[2 * i + 1], rad[l] = radius ? radius[i] : 0.f;
+      const int s2 = l / per;
+      submask[s2] |= 1u << l;
+      bx0[s2] = fminf(bx0[s2], px[l]), bx1[s2] = fmaxf(bx1[s2], px[l]), by0[s2] = fminf(by0[s2], py[l]), by1[s2] = fmaxf(by1[s2], py[l]);
+      rmin[s2] = fminf(rmin[s2], rad[l]), rmax[s2] = fmaxf(rmax[s2], rad[l]);
+    }
+    if (!live_mask || !M) continue;
+    out[0]++;
+    std::vector<std::pair<uint32_t, uint32_t>> cur, nxt;
+    cur.emplace_back(0u, live_mask);
+    size_t pos = 0;
+    while (pos < cur.size() || !nxt.empty()) {
+      if (pos >= cur.size()) cur.swap(nxt), nxt.clear(), pos = 0;
+      const size_t k = std::min<size_t>(32, cur.size() - pos);
+      out[1]++;
+      for (size_t l = 0; l < k; ++l) {
+        const uint32_t node = cur[pos + l].first, mask = cur[pos + l].second;
+        out[2]++;
+        const float4 na = e.nodeA[node];
+        const uint4 nb = e.nodeB[node];
+        const bool leaf = (nb.w & kNodeLeaf) != 0;
+        uint32_t sure_m = 0, rej_m = 0, und_m = 0;
+        for (int s2 = 0; s2 < nsub; ++s2) {
+          const uint32_t sm = submask[s2] & mask;
+          if (!sm) continue;
+          const float s_t = na.w * inv_theta;
+          const float ddx = fmaxf(fmaxf(bx0[s2] - na.x, na.x - bx1[s2]), 0.0f), ddy = fmaxf(fmaxf(by0[s2] - na.y, na.y - by1[s2]), 0.0f);
+          const float fx = fmaxf(na.x - bx0[s2], bx1[s2] - na.x), fy = fmaxf(na.y - by0[s2], by1[s2] - na.y);
+          const float dmin2 = ddx * ddx + ddy * ddy, dmax2 = fx * fx + fy * fy;
+          const float la = s_t + rmax[s2], lr = s_t + rmin[s2];
+          if (dmin2 > la * la * 1.00002f) sure_m |= sm;
+          else if (dmax2 < lr * lr * 0.99998f) rej_m |= sm;
+          else und_m |= sm;
+        }
+        uint32_t acc_mask = sure_m;
+        for (int t = 0; t < 32; ++t) {
+          if (!((und_m >> t) & 1u)) continue;
+          const float dx = px[t] - na.x, dy = py[t] - na.y;
+          const float d_sq = (dx * dx) + (dy * dy);
+          const float dist_adj = fmaxf(sqrtf(d_sq) - rad[t], 0.0f);
+          if ((na.w * na.w) < ((dist_adj * dist_adj) * e.t_sq)) acc_mask |= 1u << t;
+        }
+        if (und_m) {
+          out[4]++, out[10] += __builtin_popcount(mask);
+          if ((acc_mask & mask) == mask) out[12]++;       // undecided, yet every reaching target accepts
+          else if ((acc_mask & mask) == 0) out[13]++;     // ... or none does
+        } else if (sure_m && rej_m) out[5]++;
+        else if (sure_m) out[3]++, out[9] += __builtin_popcount(mask);
+        out[8] += __builtin_popcount(acc_mask);
+        const uint32_t rem = mask & ~acc_mask;
+        if (!rem) continue;
+        if (!leaf) {
+          if (!und_m && !sure_m) out[6]++;
+          for (uint32_t c = node + 1; c != nb.x; c = e.nodeB[c].x)
+            if (e.nodeB[c].w & kNodeCharged) nxt.emplace_back(c, rem);
+        } else {
+          out[7]++;
+          out[11] += (uint64_t)__builtin_popcount(rem) * nb.z;
+        }
+      }
+      pos += k;
+    }
+  }
+}
+
 // Serial port of bh_group_walk (traverse.cuh): 32 consecutive targets share one walk; nodes are classified
 // against the group's bounding box with the same conservative margins, undecided nodes take the reference's
 // test per target, the ring buffer switches to last-in-first-out above kLifoAbove like the device's.

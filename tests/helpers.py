@@ -260,6 +260,7 @@ class Emu:
         L.emu_walk_signatures.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_group_walk.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
+        L.emu_group_stats.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p]
         L.emu_strict_sum.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p]
         L.emu_shard_check.restype = C.c_uint32
         L.emu_shard_check.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
@@ -300,6 +301,16 @@ class Emu:
                                 out.ctypes.data, sig.ctypes.data, stats.ctypes.data)
         assert stats[0] != np.uint64(0xFFFFFFFFFFFFFFFF), "ring buffer overflow"
         return out, sig, int(stats[0]), int(stats[1])
+
+    def group_stats(self, pts, radius=None, theta=1.0, epsilon=2.0, nsub=1):
+        """interaction-list statistics of the group walk over the charged nodes (emu_group_stats)"""
+        pts = np.ascontiguousarray(pts, np.float32)
+        rad = None if radius is None else np.ascontiguousarray(radius, np.float32)
+        self.lib.emu_set_params(self.h, np.float32(theta), np.float32(epsilon))
+        out = np.zeros(14, np.uint64)
+        self.lib.emu_group_stats(self.h, len(pts), pts.ctypes.data, None if rad is None else rad.ctypes.data,
+                                 np.float32(theta), nsub, out.ctypes.data)
+        return out
 
     def shard_check(self, world, leaf=1, thread=1024):
         """replay a `world`-rank sharded build of the last build's bodies; returns (node total, mismatch
