@@ -176,6 +176,16 @@ struct psim_ctx {
   bool ev_ok = false, ev_recorded = false;
   // psim_step_host: copy streams, their events, a private staging area and the plan of the call in flight
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  // psim_step: work that the tree build does not wait for (electron regroup, cell list) runs beside it on a side stream
+  struct Overlap {
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    uint32_t* partials = nullptr;  // scan scratch of the side stream
+    bool active = false;           // set by step_async around its builds
+    bool forked = false;           // this build has put work on the side stream
+    bool pending = false;          // the main stream has not waited for the side stream yet
+    float cell_hw = 0.f, cell_hh = 0.f, cell_size = 0.f;  // > 0: rebuild the cell list beside the build
+  } ov;
   cudaEvent_t ev_start = nullptr, ev_q = nullptr, ev_vel = nullptr, ev_mid = nullptr, ev_out = nullptr;
   void* hstage = nullptr;
   size_t hstage_bytes = 0;
@@ -584,12 +594,21 @@ int32_t gather_stage(psim_ctx* ctx, const uint32_t* idx0, const uint32_t* idx1, 
   LAUNCHED(ctx);
   ctx->cur ^= 1;
   BodyArrays& b = ctx->b[ctx->cur];
+  cudaStream_t es = st;
+  uint32_t* e_partials = ctx->scan_partials;
+  ctx->ov.forked = false;
+  if (ctx->ov.active) {  // from here on the side stream may read the permuted bodies
+    CK(cudaEventRecord(ctx->ov.ev_fork, st));
+    CK(cudaStreamWaitEvent(ctx->ov.side, ctx->ov.ev_fork, 0));
+    es = ctx->ov.side, e_partials = ctx->ov.partials;
+    ctx->ov.forked = true;
+  }
   if (ctx->m > 0) {
     // electrons follow their bodies: new offsets from the permuted counts, then a grouped copy
     const int eo = ctx->ecur, en = ctx->ecur ^ 1;
-    CK(exclusive_scan(EcountFn{b.ecount}, n, ctx->eoff[en], ctx->scan_partials, nullptr, st));
+    CK(exclusive_scan(EcountFn{b.ecount}, n, ctx->eoff[en], e_partials, nullptr, es));
     ctx->launches += 3;
-    regroup_electrons_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, st>>>(
+    regroup_electrons_kernel<<<grid_for(ctx, n, 256, 16), 256, 0, es>>>(
         ctx->perm, b.ecount, ctx->eoff[eo], ctx->eoff[en], n, ctx->erel[eo], ctx->evel[eo],
         ctx->ebody[en], ctx->erel[en], ctx->evel[en]);
     LAUNCHED(ctx);
@@ -673,6 +692,26 @@ int32_t strict_stage(psim_ctx* ctx, bool sharded = false) {
   return PSIM_OK;
 }
 
+int32_t cell_build_async(psim_ctx* ctx, float hw, float hh, float cell_size);
+
+// the main stream waits for what the last build left on the side stream (no-op otherwise)
+int32_t overlap_join(psim_ctx* ctx) {
+  if (ctx->ov.pending) {
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ov.ev_join, 0));
+    ctx->ov.pending = false;
+  }
+  return PSIM_OK;
+}
+int32_t overlap_ready(psim_ctx* ctx) {
+  if (ctx->ov.side) return PSIM_OK;
+  bool ok = cudaStreamCreateWithFlags(&ctx->ov.side, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->ov.ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->ov.ev_join, cudaEventDisableTiming) == cudaSuccess &&
+            cudaMalloc(&ctx->ov.partials, ((size_t)scan_num_tiles((uint32_t)ctx->cap_bodies) + 2) * sizeof(uint32_t)) == cudaSuccess;
+  if (!ok) return fail(ctx, PSIM_E_CUDA, "psim_step: side stream", cudaGetLastError());
+  return PSIM_OK;
+}
+
 int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
   const uint32_t n = ctx->n;
   cudaStream_t st = ctx->stream;
@@ -714,6 +753,16 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
   {
     const int32_t rc = gather_stage(ctx, ctx->idx[0], ctx->idx[1], ctx->tree_plan, kTreePasses);
     if (rc) return rc;
+  }
+  if (ctx->ov.forked) {
+    if (ctx->ov.cell_size > 0.0f) {  // the cell list only needs the sorted bodies
+      ctx->stream = ctx->ov.side;
+      const int32_t rc = cell_build_async(ctx, ctx->ov.cell_hw, ctx->ov.cell_hh, ctx->ov.cell_size);
+      ctx->stream = st;
+      if (rc) return rc;
+    }
+    CK(cudaEventRecord(ctx->ov.ev_join, ctx->ov.side));
+    ctx->ov.pending = true;
   }
   BodyArrays& b = ctx->b[ctx->cur];
   const uint32_t c_eff = effective_capacity(ctx->cfg.leaf_capacity, ctx->cfg.thread_capacity);
@@ -1343,6 +1392,10 @@ int32_t psim_destroy(psim_ctx* ctx) {
   psim_comm_destroy(ctx);
   if (ctx->ev_ok)
     for (int k = 0; k < 9; ++k) cudaEventDestroy(ctx->ev[k]);
+  if (ctx->ov.side) cudaStreamSynchronize(ctx->ov.side), cudaStreamDestroy(ctx->ov.side);
+  if (ctx->ov.ev_fork) cudaEventDestroy(ctx->ov.ev_fork);
+  if (ctx->ov.ev_join) cudaEventDestroy(ctx->ov.ev_join);
+  if (ctx->ov.partials) cudaFree(ctx->ov.partials);
   if (ctx->copy_in) cudaStreamSynchronize(ctx->copy_in), cudaStreamDestroy(ctx->copy_in);
   if (ctx->copy_out) cudaStreamSynchronize(ctx->copy_out), cudaStreamDestroy(ctx->copy_out);
   for (cudaEvent_t e : {ctx->ev_start, ctx->ev_q, ctx->ev_vel, ctx->ev_mid, ctx->ev_out})
@@ -2263,7 +2316,16 @@ static int32_t step_async(psim_ctx* ctx, const psim_step_params* p) {
   };
   mark(0);
   if ((rc = psim_reset_acc(ctx))) return rc;
-  if ((rc = build_async(ctx, PSIM_BUILD_CONTAINING, 0.f, 0.f))) return rc;
+  static const bool no_overlap = getenv("PSIM_OVERLAP") && getenv("PSIM_OVERLAP")[0] == '0';
+  const float cell = p->do_short_range ? step_cell_size(ctx, p->do_polar != 0) : 0.0f;
+  if (!no_overlap) {
+    if ((rc = overlap_ready(ctx))) return rc;
+    ctx->ov.active = true;
+    ctx->ov.cell_hw = p->hw, ctx->ov.cell_hh = p->hh, ctx->ov.cell_size = cell;
+  }
+  rc = build_async(ctx, PSIM_BUILD_CONTAINING, 0.f, 0.f);
+  ctx->ov.active = false, ctx->ov.cell_size = 0.0f;
+  if (rc) return rc;
   if (H.active && H.out_orig) {
     results_from_here();
     cudaMemcpyAsync(H.out_orig, ctx->b[ctx->cur].orig, 4 * n, cudaMemcpyDeviceToHost, ctx->copy_out);
@@ -2273,8 +2335,7 @@ static int32_t step_async(psim_ctx* ctx, const psim_step_params* p) {
     // The reference sizes its grid for the polar pass too (3 x the LJ cutoff, forces.rs:17-22).  The
     // pair sets of the LJ / repulsion passes do not depend on the cell size, so the fused step bins at
     // the largest cutoff those passes use: 9x fewer candidates per body than at 3 x cutoff.
-    const float cell = step_cell_size(ctx, p->do_polar != 0);
-    if (cell > 0.0f && (rc = cell_build_async(ctx, p->hw, p->hh, cell))) return rc;
+    if (cell > 0.0f && no_overlap && (rc = cell_build_async(ctx, p->hw, p->hh, cell))) return rc;
   }
   mark(2);
   if ((rc = field_async(ctx, p->k_e, p->bg_x, p->bg_y, 1))) return rc;
@@ -2283,6 +2344,7 @@ static int32_t step_async(psim_ctx* ctx, const psim_step_params* p) {
     cudaMemcpyAsync(H.out_ef, ctx->b[ctx->cur].efield, 8 * n, cudaMemcpyDeviceToHost, ctx->copy_out);
   }
   mark(3);
+  if ((rc = overlap_join(ctx))) return rc;  // cell list and regrouped electrons
   if (p->do_polar && p->do_short_range && (rc = polar_async(ctx, p->k_e, 1))) return rc;
   if (p->do_short_range && (rc = short_range_async(ctx, PSIM_SR_LJ | PSIM_SR_REPULSION | PSIM_SR_STACK_PRESSURE))) return rc;
   mark(4);
@@ -2306,7 +2368,11 @@ static int32_t step_async(psim_ctx* ctx, const psim_step_params* p) {
   }
   mark(5);
   if (p->do_electrons) {
-    if ((rc = build_async(ctx, PSIM_BUILD_DOMAIN, p->hw, p->hh))) return rc;
+    ctx->ov.active = !no_overlap;
+    rc = build_async(ctx, PSIM_BUILD_DOMAIN, p->hw, p->hh);
+    ctx->ov.active = false;
+    if (rc) return rc;
+    if ((rc = overlap_join(ctx))) return rc;  // regrouped electrons
     mark(6);
     if ((rc = electrons_async(ctx, p->bg_x, p->bg_y, p->dt, p->k_e))) return rc;
   } else {
@@ -2321,7 +2387,9 @@ static int32_t step_async(psim_ctx* ctx, const psim_step_params* p) {
 int32_t psim_step(psim_ctx* ctx, const psim_step_params* p) {
   if (!ctx || !p) return PSIM_E_ARG;
   DeviceGuard guard(ctx->device);
-  return step_async(ctx, p);
+  const int32_t rc = step_async(ctx, p);
+  overlap_join(ctx);  // an early error return must not leave side-stream work unordered
+  return rc;
 }
 
 // One hot-path step for a caller whose bodies live in host memory: the state refresh, psim_step and
@@ -2342,7 +2410,7 @@ int32_t psim_step_host(psim_ctx* ctx, const psim_step_params* p, uint64_t n, con
   DeviceGuard guard(ctx->device);
   if (n != ctx->n || (n && !pos_xy)) return fail(ctx, PSIM_E_ARG, "psim_step_host: size mismatch");
   if (ctx->tgt_set || ctx->etgt_set) return fail(ctx, PSIM_E_STATE, "psim_step_host: not available on a sharded context");
-  if (n == 0) return step_async(ctx, p);
+  if (n == 0) return step_async(ctx, p);  // nothing is launched
   if (!ctx->copy_in) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -2389,6 +2457,7 @@ int32_t psim_step_host(psim_ctx* ctx, const psim_step_params* p, uint64_t n, con
   }
   H.active = true;
   int32_t rc = step_async(ctx, p);
+  overlap_join(ctx);
   H.active = false;
   if (rc) {
     cudaStreamSynchronize(ctx->copy_in), cudaStreamSynchronize(ctx->copy_out), cudaStreamSynchronize(st);
