@@ -262,10 +262,10 @@ __global__ void __launch_bounds__(128)
 // reach the node).  A lane that opens a node finds all its children at once (child k+1 is the skip
 // pointer of child k, until it equals the parent's), so the frontier widens by the branching factor
 // every round and a walk takes about as many rounds as the tree is deep.
-constexpr int kStackCap = 640;
-constexpr int kLifoAbove = kStackCap - 288;  // see the capacity argument in bh_group_walk
+constexpr int kStackCap = 512;               // a power of two: ring indices wrap with a mask
+constexpr int kLifoAbove = kStackCap - 192;  // see the capacity argument in bh_group_walk
 struct WarpShared {
-  uint32_t st_node[kStackCap], st_mask[kStackCap];
+  uint2 st[kStackCap];  // {node, mask of targets that reach it}
   // the round's nodes that some target may accept, staged for broadcast reads
   float4 l_node[32];  // {centre.x, centre.y, charge, size}
   uint32_t l_mask[32]; // mask of targets that reach the node
@@ -320,12 +320,12 @@ __device__ __forceinline__ float2 bh_group_walk(const float4* __restrict__ nodeA
   const float kq = ONE ? 1.0f : A::mul(P.k_e, q);
   const float my_lim_r = radius;
   const uint32_t lanebit = 1u << lane;
-  if (lane == 0) ws.st_node[0] = 0, ws.st_mask[0] = live_mask;
+  if (lane == 0) ws.st[0] = make_uint2(0u, live_mask);
   __syncwarp();
   // Ring buffer served first-in-first-out (wide rounds).  Capacity: a FIFO round pops k <= 32 entries
   // and pushes <= 4k, so starting at size <= kLifoAbove it ends at <= kLifoAbove + 96; above that the
   // walk goes last-in-first-out one node per round, where at most 3 siblings per level stay pending
-  // (<= 96 more for 32 levels): kLifoAbove + 96 + 96 <= kStackCap.
+  // (<= 96 more for 32 levels): kLifoAbove + 96 + 96 <= kStackCap (512).
   int head = 0, size = 1;
   uint32_t visited = 0;
   while (size > 0) {
@@ -334,15 +334,11 @@ __device__ __forceinline__ float2 bh_group_walk(const float4* __restrict__ nodeA
     const bool has = lane < k;
     uint32_t node = 0, mask = 0;
     if (has) {
-      int idx = lifo ? head + size - 1 : head + lane;
-      if (idx >= kStackCap) idx -= kStackCap;
-      node = ws.st_node[idx], mask = ws.st_mask[idx];
+      const uint2 ent = ws.st[(lifo ? head + size - 1 : head + lane) & (kStackCap - 1)];
+      node = ent.x, mask = ent.y;
     }
     __syncwarp();
-    if (!lifo) {
-      head += k;
-      if (head >= kStackCap) head -= kStackCap;
-    }
+    if (!lifo) head = (head + k) & (kStackCap - 1);
     size -= k;
     visited += k;
     float4 na = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -531,24 +527,21 @@ __device__ __forceinline__ float2 bh_group_walk(const float4* __restrict__ nodeA
         }
       }
     }
-    int incl = nk;  // inclusive prefix of the child counts over the lanes
+    if (__any_sync(FULL, nk != 0)) {  // rounds near the leaves often push nothing
+      int incl = nk;  // inclusive prefix of the child counts over the lanes
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(FULL, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const int off = incl - nk;
-    const int total = __shfl_sync(FULL, incl, 31);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (j < nk) {
-        int o2 = head + size + off + j;
-        if (o2 >= kStackCap) o2 -= kStackCap;
-        ws.st_node[o2] = kid[j], ws.st_mask[o2] = rem;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
       }
+      const int off = incl - nk;
+      const int total = __shfl_sync(FULL, incl, 31);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nk) ws.st[(head + size + off + j) & (kStackCap - 1)] = make_uint2(kid[j], rem);
+      size += total;
+      __syncwarp();
     }
-    size += total;
-    __syncwarp();
     // direct terms of this round (quadtree.rs:381-395)
     uint32_t nm = __ballot_sync(FULL, has && rem != 0 && leaf);
     while (nm) {

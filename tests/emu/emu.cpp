@@ -656,7 +656,7 @@ void emu_group_walk(void* h, uint32_t m, const float* pts_xy, const float* q, co
                     float theta, float* out_xy, uint64_t* sig, uint64_t* stats /* [0] nodes visited, [1] lifo rounds */) {
   Emu& e = *static_cast<Emu*>(h);
   const uint32_t M = e.meta.num_nodes;
-  constexpr int kCap = 640, kLifo = kCap - 288;
+  constexpr int kCap = 512, kLifo = kCap - 192;
   const float inv_theta = 1.0f / theta;
   const float INF = INFINITY;
   uint64_t visited = 0, lifo_rounds = 0;
