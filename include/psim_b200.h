@@ -122,6 +122,13 @@ int32_t psim_reset_counters(psim_ctx *ctx);
  * out[0] = internal nodes opened, out[1] = monopoles accepted (non-empty nodes), out[2] = direct
  * body terms, out[3] = warp steps.  The reference's node visits are n + 4 * out[0]. */
 int32_t psim_field_counters(psim_ctx *ctx, uint64_t *out4);
+/* how the last psim_build (strict_centres on, single GPU) made the node charges:
+ * out[0] = 1 if every body charge is an integer (what Body::update_charge_from_electrons produces, body/electron.rs)
+ * with sum |q| < 2^24 and no leaf is left unaggregated - node charges are then exact differences of an integer prefix
+ * over the charged bodies, equal to the reference's nested f32 sums (quadtree.rs:142-149) bit for bit; 0 = bottom-up
+ * level sweeps in the reference's child order.  out[1] = charged bodies, out[2] = sum |q| of the integer charges,
+ * out[3] = bodies whose charge is not an integer below 2^20. */
+int32_t psim_build_info(psim_ctx *ctx, uint64_t *out4);
 /* measured FP32 FMA throughput of this device in TFLOP/s (2 flops per FMA), and the SM count */
 int32_t psim_fp32_peak(psim_ctx *ctx, float *tflops, int32_t *sm_count);
 

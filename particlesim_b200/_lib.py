@@ -81,6 +81,7 @@ SIGNATURES = {
     "psim_stats_get": (_i32, [_vp, _vp]),
     "psim_reset_counters": (_i32, [_vp]),
     "psim_field_counters": (_i32, [_vp, _vp]),
+    "psim_build_info": (_i32, [_vp, _vp]),
     "psim_fp32_peak": (_i32, [_vp, C.POINTER(C.c_float), C.POINTER(_i32)]),
     "psim_upload_species_table": (_i32, [_vp, _vp, _u32]),
     "psim_upload_bodies": (_i32, [_vp, _u64] + [_vp] * 8),

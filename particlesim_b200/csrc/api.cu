@@ -1460,6 +1460,25 @@ int32_t psim_field_counters(psim_ctx* ctx, uint64_t* out4) {
   return PSIM_OK;
 }
 
+int32_t psim_build_info(psim_ctx* ctx, uint64_t* out4) {
+  if (!ctx || !out4) return PSIM_E_ARG;
+  DeviceGuard guard(ctx->device);
+  if (!ctx->tree_valid) return fail(ctx, PSIM_E_STATE, "psim_build_info: no tree");
+  out4[0] = out4[1] = out4[2] = out4[3] = 0;
+  if (ctx->n == 0 || !ctx->cfg.strict_centres || !ctx->strict_ready || ctx->sh.tree_is_sharded) return PSIM_OK;
+  const int32_t rc = fetch_meta(ctx);
+  if (rc) return rc;
+  unsigned long long q[3] = {0, 0, 0};
+  CK(cudaMemcpyAsync(q, ctx->strict.qstat, sizeof q, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const bool disabled = getenv("PSIM_INTEGER_CHARGES") && getenv("PSIM_INTEGER_CHARGES")[0] == '0';
+  out4[0] = (!disabled && q[1] == 0 && q[0] < (1ull << 24) && ctx->meta_h.zero_agg_hint == 0) ? 1 : 0;
+  out4[1] = (uint32_t)q[2] ? (uint32_t)q[2] - 1u : 0u;
+  out4[2] = q[0];
+  out4[3] = q[1];
+  return PSIM_OK;
+}
+
 int32_t psim_fp32_peak(psim_ctx* ctx, float* tflops, int32_t* sm_count) {
   if (!ctx || !tflops) return PSIM_E_ARG;
   DeviceGuard guard(ctx->device);

@@ -314,6 +314,13 @@ class Simulation:
         d["root_center"] = tuple(st.root_center)
         return d
 
+    def build_info(self) -> dict:
+        """how the last build made the node charges (psim_build_info)"""
+        out = (C.c_uint64 * 4)()
+        self._call("psim_build_info", out)
+        return {"integer_charges": bool(out[0]), "charged_bodies": int(out[1]), "abs_charge_sum": int(out[2]),
+                "non_integer_charges": int(out[3])}
+
     def sync(self):
         self._call("psim_sync")
 

@@ -1,6 +1,8 @@
 """GPU parity: keys, sort permutation, node topology, leaf membership, aggregates — through the C ABI,
 against the oracle on the same seeded inputs.  Bit-exact for everything integer; charge and mass
 bit-exact; node centres to rounding (see DESIGN.md "node centres")."""
+import os
+
 import numpy as np
 import pytest
 
@@ -63,6 +65,11 @@ def test_topology_permutation_aggregates(cuda_device, name, gen, mode):
     assert_same_topology(dc, oc)
     st = sim.stats()
     assert st["reference_nodes"] == len(oc) and st["max_depth"] == o.max_depth()
+    # both ways of making the node charges are exercised: exact integer prefix differences for the reference's
+    # integer charges, bottom-up level sweeps for the fractional set
+    info = sim.build_info()
+    assert info["integer_charges"] == (not name.startswith("fractional") and os.environ.get("PSIM_INTEGER_CHARGES") != "0")
+    assert info["charged_bodies"] == int(np.count_nonzero(bodies["charge"]))
     # aggregates
     assert np.array_equal(dc["charge"], oc["charge"])
     assert np.array_equal(dc["mass"], oc["mass"])
