@@ -122,6 +122,14 @@ def fractional(n, seed=SEED, rho=RHO):
     return b
 
 
+def big_integer(n, seed=SEED, rho=RHO):
+    """uniform_pm1 with integer charges whose partial sums leave the exactly representable range (sum |q| >= 2^24):
+    the integer-prefix path must stand down"""
+    b = uniform_pm1(n, seed=seed, rho=rho)
+    b["charge"] = (b["charge"] * 1000003.0).astype(np.float32)
+    return b
+
+
 def electrolyte(n, seed=SEED, rho=RHO):
     """config 4: Li+ / PF6- / EC / DMC at 342:342:2393:2394 (scenario.rs:180-200)."""
     rng = np.random.default_rng(seed)

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from helpers import (KE, Emu, assert_same_topology, canonical_from_nodes, check_next_pointers, clustered,
-                     electrolyte, fractional, oracle_for, rel_l2, uniform_pm1)
+                     big_integer, electrolyte, fractional, oracle_for, rel_l2, uniform_pm1)
 
 pytestmark = pytest.mark.gpu
 
@@ -39,7 +39,7 @@ CASES = [
     ("uniform_3", lambda: uniform_pm1(3)), ("uniform_33", lambda: uniform_pm1(33)),
     ("uniform_4097", lambda: uniform_pm1(4097)), ("uniform_100k", lambda: uniform_pm1(100_000)),
     ("electrolyte_50k", lambda: electrolyte(50_000)), ("clustered_60k", lambda: clustered(60_000)),
-    ("fractional_70k", lambda: fractional(70_000)),
+    ("fractional_70k", lambda: fractional(70_000)), ("bigint_4097", lambda: big_integer(4097)),
 ]
 
 
@@ -68,7 +68,8 @@ def test_topology_permutation_aggregates(cuda_device, name, gen, mode):
     # both ways of making the node charges are exercised: exact integer prefix differences for the reference's
     # integer charges, bottom-up level sweeps for the fractional set
     info = sim.build_info()
-    assert info["integer_charges"] == (not name.startswith("fractional") and os.environ.get("PSIM_INTEGER_CHARGES") != "0")
+    assert info["integer_charges"] == (not name.startswith(("fractional", "bigint")) and
+                                       os.environ.get("PSIM_INTEGER_CHARGES") != "0")
     assert info["charged_bodies"] == int(np.count_nonzero(bodies["charge"]))
     # aggregates
     assert np.array_equal(dc["charge"], oc["charge"])
