@@ -342,16 +342,23 @@ __global__ void __launch_bounds__(kPolarThreads)
       // the cells x0 .. x1 of a row are one contiguous run of the cell order (same candidate order as cell by cell)
       const uint32_t row = (uint32_t)y * P.g.gx;
       const uint32_t k1 = cell_off[row + (uint32_t)x1 + 1u];
-      for (uint32_t k = cell_off[row + (uint32_t)x0]; k < k1; ++k) {
-        const float4 a4 = __ldg(&recA[k]);
-        const float rx = __fsub_rn(a4.x, me.x), ry = __fsub_rn(a4.y, me.y);
-        const float r2 = __fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry));
-        if (!(r2 < any_cut_sq)) continue;
-        const float4 b4 = __ldg(&recB[k]);
-        if (__float_as_uint(b4.y) == i) continue;
-        if (!me_dip && !(__float_as_uint(b4.x) & kPolarHasDipole)) continue;
-        s_list[filled][threadIdx.x] = k;
-        if (++filled == kPolarList) drain();
+      for (uint32_t kb = cell_off[row + (uint32_t)x0]; kb < k1; kb += 4) {
+        // four candidates' records in flight at a time (same candidate order)
+        float4 a4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a4[u] = __ldg(&recA[kb + u < k1 ? kb + u : k1 - 1]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t k = kb + u;
+          const float rx = __fsub_rn(a4[u].x, me.x), ry = __fsub_rn(a4[u].y, me.y);
+          const float r2 = __fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry));
+          if (k >= k1 || !(r2 < any_cut_sq)) continue;
+          const float4 b4 = __ldg(&recB[k]);
+          if (__float_as_uint(b4.y) == i) continue;
+          if (!me_dip && !(__float_as_uint(b4.x) & kPolarHasDipole)) continue;
+          s_list[filled][threadIdx.x] = k;
+          if (++filled == kPolarList) drain();
+        }
       }
     }
   }
