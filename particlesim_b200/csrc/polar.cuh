@@ -244,8 +244,9 @@ __global__ void __launch_bounds__(kPolarThreads)
         const float rx = __fsub_rn(a4.x, me.x), ry = __fsub_rn(a4.y, me.y);
         const float r2 = __fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry));
         const float jc = __fmul_rn(3.0f, a4.w);
-        const bool use0 = me_dip && r2 < my_cut_sq;              // me as the polar body i
-        const bool use1 = j_dip && r2 < __fmul_rn(jc, jc);       // the candidate as i, me its neighbour: reaction
+        const bool other = __float_as_uint(b4.y) != i;           // the body itself is in its own cell
+        const bool use0 = other && me_dip && r2 < my_cut_sq;     // me as the polar body i
+        const bool use1 = other && j_dip && r2 < __fmul_rn(jc, jc);  // the candidate as i, me its neighbour: reaction
         const float j_kq = fabsf(a4.z) < kEps ? 0.0f : P.k_e * a4.z;
         const float j_ke = (j_dip && P.dipole_model == 1 && !(fabsf(j_qeff) < kEps)) ? P.k_e * j_qeff : 0.0f;
         const float jex = __fadd_rn(a4.x, b4.z), jey = __fadd_rn(a4.y, b4.w);
@@ -284,6 +285,7 @@ __global__ void __launch_bounds__(kPolarThreads)
       const float4 a4 = __ldg(&recA[k]);
       const uint32_t jbits = __float_as_uint(b4.x);
       const bool j_dip = (jbits & kPolarHasDipole) != 0;
+      if (__float_as_uint(b4.y) == i || (!me_dip && !j_dip)) continue;  // the body itself; ion / ion: no polar term
       const float rx = __fsub_rn(a4.x, me.x), ry = __fsub_rn(a4.y, me.y);
       const float r2 = __fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry));
       uint32_t jsp = jbits & 0xffu;
@@ -353,9 +355,7 @@ __global__ void __launch_bounds__(kPolarThreads)
           const float rx = __fsub_rn(a4[u].x, me.x), ry = __fsub_rn(a4[u].y, me.y);
           const float r2 = __fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry));
           if (k >= k1 || !(r2 < any_cut_sq)) continue;
-          const float4 b4 = __ldg(&recB[k]);
-          if (__float_as_uint(b4.y) == i) continue;
-          if (!me_dip && !(__float_as_uint(b4.x) & kPolarHasDipole)) continue;
+          // (the body itself and ion / ion pairs are dropped in the second pass, which reads record B anyway)
           s_list[filled][threadIdx.x] = k;
           if (++filled == kPolarList) drain();
         }
