@@ -17,7 +17,8 @@ namespace psim {
 
 constexpr uint32_t kPolarHasDipole = 1u << 8;
 
-// records in cell order: A = {x, y, charge, radius}, B = {species | flags, body index, e.rel_pos}
+// records in cell order: A = {x, y, charge, radius with the sign bit set if the body has a dipole}, B = {species | flags,
+// body index, e.rel_pos}
 __global__ void __launch_bounds__(256)
     polar_records_kernel(const uint32_t* __restrict__ order, uint32_t n, const float4* __restrict__ pqr,
                          const uint8_t* __restrict__ species, const uint8_t* __restrict__ ecount,
@@ -36,7 +37,7 @@ __global__ void __launch_bounds__(256)
       r = erel[eoff[b]];
       local_max = fmaxf(local_max, __fmul_rn(3.0f, p.w));
     }
-    recA[k] = p;
+    recA[k] = make_float4(p.x, p.y, p.z, dip ? __uint_as_float(__float_as_uint(p.w) | 0x80000000u) : p.w);
     recB[k] = make_float4(__uint_as_float(sp | (dip ? kPolarHasDipole : 0u)), __uint_as_float(b), r.x, r.y);
   }
 #pragma unroll
@@ -235,7 +236,8 @@ __global__ void __launch_bounds__(kPolarThreads)
       for (int t = 0; t < filled; ++t) {
         const uint32_t k = s_list[t][threadIdx.x];
         const float4 b4 = __ldg(&recB[k]);
-        const float4 a4 = __ldg(&recA[k]);
+        float4 a4 = __ldg(&recA[k]);
+        a4.w = fabsf(a4.w);  // the sign bit is the dipole flag of the distance sweep
         const uint32_t jbits = __float_as_uint(b4.x);
         const bool j_dip = (jbits & kPolarHasDipole) != 0;
         uint32_t jsp = jbits & 0xffu;
@@ -282,7 +284,8 @@ __global__ void __launch_bounds__(kPolarThreads)
     for (int t = 0; t < filled; ++t) {
       const uint32_t k = s_list[t][threadIdx.x];
       const float4 b4 = __ldg(&recB[k]);
-      const float4 a4 = __ldg(&recA[k]);
+      float4 a4 = __ldg(&recA[k]);
+      a4.w = fabsf(a4.w);  // the sign bit is the dipole flag of the distance sweep
       const uint32_t jbits = __float_as_uint(b4.x);
       const bool j_dip = (jbits & kPolarHasDipole) != 0;
       if (__float_as_uint(b4.y) == i || (!me_dip && !j_dip)) continue;  // the body itself; ion / ion: no polar term
@@ -355,7 +358,10 @@ __global__ void __launch_bounds__(kPolarThreads)
           const float rx = __fsub_rn(a4[u].x, me.x), ry = __fsub_rn(a4[u].y, me.y);
           const float r2 = __fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry));
           if (k >= k1 || !(r2 < any_cut_sq)) continue;
-          // (the body itself and ion / ion pairs are dropped in the second pass, which reads record B anyway)
+          // A body without a dipole only interacts with dipoles (the flag rides on the sign of record A's radius, so
+          // this loop never reads record B); a dipole takes every candidate in range, and the body itself is dropped
+          // in the second pass.
+          if (!me_dip && !(__float_as_uint(a4[u].w) >> 31)) continue;
           s_list[filled][threadIdx.x] = k;
           if (++filled == kPolarList) drain();
         }
