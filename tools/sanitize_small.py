@@ -10,14 +10,14 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from helpers import KE, clustered, electrolyte  # noqa: E402
 from particlesim_b200 import Bodies, Simulation  # noqa: E402
 
-for gen, n in ((electrolyte, 30_011), (clustered, 20_003)):
+for gen, n in ((electrolyte, 20_011), (clustered, 12_003)):
     bd = gen(n)
     if gen is electrolyte:
         bd["species"][:2000] = 1
     b = Bodies(bd["pos"], vel=bd.get("vel"), mass=bd["mass"], radius=bd["radius"], charge=bd["charge"],
                species=bd["species"], ebody=bd.get("ebody"), erel=bd.get("erel"))
-    for mode in (1, 2, 0):
-        sim = Simulation(b, bd["hw"], bd["hh"], parity_mode=mode, strict_centres=(mode != 0))
+    for mode, strict in ((1, True), (2, True), (0, True), (0, False)):
+        sim = Simulation(b, bd["hw"], bd["hh"], parity_mode=mode, strict_centres=strict)
         sim.config.coulomb_constant = float(KE)
         for _ in range(2):
             sim.step_device()
@@ -29,6 +29,6 @@ for gen, n in ((electrolyte, 30_011), (clustered, 20_003)):
         nodes = sim.quadtree.nodes
         sim._call("psim_cell_build", bd["hw"], bd["hh"], 11.88)
         sim._neighbors(np.arange(0, n, 97), 3.96, False)
-        print(gen.__name__, mode, len(nodes), sim.stats()["max_depth"], flush=True)
+        print(gen.__name__, mode, strict, len(nodes), sim.stats()["max_depth"], flush=True)
         sim.close()
 print("sanitize run done")
