@@ -788,7 +788,7 @@ int32_t build_async(psim_ctx* ctx, int mode, float hw, float hh) {
                     ctx->strict.cand_cap, no_intq ? nullptr : ctx->strict.qstat, ctx->strict.qc};
   }
   {
-    static const int minb = getenv("PSIM_EMIT_MINB") ? atoi(getenv("PSIM_EMIT_MINB")) : 10;
+    static const int minb = getenv("PSIM_EMIT_MINB") ? atoi(getenv("PSIM_EMIT_MINB")) : 12;
     auto kern = minb >= 12 ? tree_emit_kernel<12> : minb >= 10 ? tree_emit_kernel<10> : minb >= 8 ? tree_emit_kernel<8> : tree_emit_kernel<5>;
     kern<<<emit_grid, 128, 0, st>>>(ctx->keys[1], ctx->keys[1], ctx->tree_plan, kTreePasses, n, per_block, ctx->le,
                                     ctx->nodebase, b.pqr, b.accm, ctx->cfg.leaf_capacity, ctx->cfg.thread_capacity,
