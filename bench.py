@@ -361,6 +361,10 @@ def run_ours(args):
     if world == 1:
         # ---- roofline of the dominant kernel (bh_group_bodies_kernel = phase quadtree_field) --------
         sim._call("psim_build", 0, 0.0, 0.0)
+        try:  # which way the build made the node charges (psim_build_info): exact integer prefix or level sweeps
+            line["build_path"] = sim.build_info()
+        except Exception as ex:  # diagnostics only
+            line["build_path"] = {"error": str(ex)}
         cnt = np.zeros(4, np.uint64)
         sim._call("psim_field_counters", cnt.ctypes.data)
         opened, accepted, pairs, wsteps = (int(x) for x in cnt)
