@@ -167,6 +167,13 @@ impl Context {
         self.check(unsafe { psim_stats_get(self.0, &mut st) })?;
         Ok(st)
     }
+    /// how the last build made the node charges: `[integer prefix path (1) or level sweeps (0), charged bodies,
+    /// sum |q| of the integer charges, non-integer charges]` (`psim_build_info`)
+    pub fn build_info(&self) -> Result<[u64; 4]> {
+        let mut out = [0u64; 4];
+        self.check(unsafe { psim_build_info(self.0, out.as_mut_ptr()) })?;
+        Ok(out)
+    }
     /// NCCL communicator for the sharded hot path (`id` from `unique_id()` on rank 0, distributed by the host).
     pub fn comm_init(&self, id: &[u8; 128], rank: u32, nranks: u32) -> Result<()> {
         self.check(unsafe { psim_comm_init(self.0, id.as_ptr(), rank, nranks) })
